@@ -1,0 +1,242 @@
+"""Thin Python owner of one ``avsep_handle``: weight upload and pointer marshalling for the C ABI.
+
+PyTorch is used for device memory and streams only; every FLOP of the path runs in libavsep.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+STAGE_NAMES = ("audio_embed", "audio_enc", "visual_pool", "visual_embed", "visual_enc", "fused")
+
+
+@dataclass(frozen=True)
+class EngineConfig:
+    freq_bins: int
+    d_model: int
+    nhead: int
+    num_encoder_layers: int
+    num_fusion_layers: int
+    num_speakers: int
+    precision: str = "bf16"
+
+
+def _prec_code(p: str) -> int:
+    if p in ("bf16", "bfloat16"):
+        return _lib.PREC_BF16
+    if p in ("tf32", "fp32", "float32"):
+        return _lib.PREC_TF32
+    raise ValueError(f"unknown precision {p!r} (use 'bf16' or 'tf32')")
+
+
+def expected_shapes(cfg: EngineConfig) -> dict:
+    """state_dict contract of the reference module: key -> shape."""
+    d, F, S = cfg.d_model, cfg.freq_bins, cfg.num_speakers
+    out = {
+        "audio_encoder.input_proj.0.weight": (d, F, 3), "audio_encoder.input_proj.0.bias": (d,),
+        "audio_encoder.input_proj.2.weight": (d, d, 3), "audio_encoder.input_proj.2.bias": (d,),
+        "audio_encoder.pos_enc.pe": (1, 5000, d), "visual_encoder.pos_enc.pe": (1, 5000, d),
+        "visual_encoder.frame_proj.weight": (d, 128), "visual_encoder.frame_proj.bias": (d,),
+        "fusion.norm.weight": (d,), "fusion.norm.bias": (d,),
+        "decoder.decoder.0.weight": (2 * d, d), "decoder.decoder.0.bias": (2 * d,),
+        "decoder.decoder.3.weight": (S * F, 2 * d), "decoder.decoder.3.bias": (S * F,),
+    }
+    cin = 1
+    for idx, cout in ((0, 32), (3, 64), (6, 128)):
+        out[f"visual_encoder.conv.{idx}.weight"] = (cout, cin, 3, 3)
+        out[f"visual_encoder.conv.{idx}.bias"] = (cout,)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            out[f"visual_encoder.conv.{idx + 1}.{k}"] = (cout,)
+        cin = cout
+    for pre in ("audio_encoder", "visual_encoder"):
+        for l in range(cfg.num_encoder_layers):
+            p = f"{pre}.transformer.layers.{l}"
+            out.update({
+                f"{p}.self_attn.in_proj_weight": (3 * d, d), f"{p}.self_attn.in_proj_bias": (3 * d,),
+                f"{p}.self_attn.out_proj.weight": (d, d), f"{p}.self_attn.out_proj.bias": (d,),
+                f"{p}.linear1.weight": (4 * d, d), f"{p}.linear1.bias": (4 * d,),
+                f"{p}.linear2.weight": (d, 4 * d), f"{p}.linear2.bias": (d,),
+                f"{p}.norm1.weight": (d,), f"{p}.norm1.bias": (d,),
+                f"{p}.norm2.weight": (d,), f"{p}.norm2.bias": (d,),
+            })
+    for l in range(cfg.num_fusion_layers):
+        p = f"fusion.layers.{l}"
+        out.update({
+            f"{p}.cross_attn.in_proj_weight": (3 * d, d), f"{p}.cross_attn.in_proj_bias": (3 * d,),
+            f"{p}.cross_attn.out_proj.weight": (d, d), f"{p}.cross_attn.out_proj.bias": (d,),
+            f"{p}.ff.0.weight": (4 * d, d), f"{p}.ff.0.bias": (4 * d,),
+            f"{p}.ff.3.weight": (d, 4 * d), f"{p}.ff.3.bias": (d,),
+            f"{p}.norm1.weight": (d,), f"{p}.norm1.bias": (d,),
+            f"{p}.norm2.weight": (d,), f"{p}.norm2.bias": (d,),
+        })
+    return out
+
+
+class Engine:
+    """One C handle bound to one CUDA device."""
+
+    def __init__(self, cfg: EngineConfig, device: int):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = int(device)
+        c = _lib.AvsepConfig(cfg.freq_bins, cfg.d_model, cfg.nhead, cfg.num_encoder_layers,
+                             cfg.num_fusion_layers, cfg.num_speakers, _prec_code(cfg.precision), self.device)
+        h = C.c_void_p()
+        if self.lib.avsep_create(C.byref(c), C.byref(h)) != 0:
+            raise RuntimeError("avsep_create: " + self.lib.avsep_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.avsep_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {self.lib.avsep_last_error(self.h).decode()}")
+
+    # ---- weights --------------------------------------------------------------------------------
+    def load_state(self, state: dict, fill_missing: bool = False):
+        """state: reference key -> torch tensor / numpy array.  Missing keys are an error unless
+        ``fill_missing`` (stand-alone sub-modules), in which case neutral values are used."""
+        want = expected_shapes(self.cfg)
+        for key, shape in want.items():
+            if key in state:
+                v = state[key]
+                arr = v.detach().to("cpu", torch.float32).contiguous().numpy() if isinstance(v, torch.Tensor) \
+                    else np.ascontiguousarray(v, dtype=np.float32)
+            elif fill_missing:
+                neutral_one = key.endswith("running_var") or (key.endswith(".weight") and len(shape) == 1)
+                arr = np.ones(shape, np.float32) if neutral_one else np.zeros(shape, np.float32)
+            else:
+                raise KeyError(f"state_dict is missing {key!r}")
+            if tuple(arr.shape) != tuple(shape):
+                raise ValueError(f"{key}: expected shape {shape}, got {tuple(arr.shape)}")
+            shp = (C.c_int64 * len(shape))(*shape)
+            self._check(self.lib.avsep_set_weight(self.h, key.encode(), arr.ctypes.data_as(C.c_void_p),
+                                                  _lib.DTYPE_F32, shp, len(shape)), "avsep_set_weight")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._check(self.lib.avsep_finalize_weights(self.h, C.c_void_p(stream)), "avsep_finalize_weights")
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _dev_f32(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if not t.is_cuda or t.device.index != self.device:
+            raise RuntimeError(f"{name} must live on cuda:{self.device} (there is no CPU path)")
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, mixed: torch.Tensor, frames: torch.Tensor):
+        mixed = self._dev_f32(mixed, "mixed_spec")
+        frames = self._dev_f32(frames, "lip_frames")
+        B, F, T = mixed.shape
+        Bf, N, Hh, Ww = frames.shape
+        if F != self.cfg.freq_bins:
+            raise ValueError(f"mixed_spec has {F} frequency bins, model expects {self.cfg.freq_bins}")
+        if Bf != B:
+            raise ValueError("batch size of mixed_spec and lip_frames differ")
+        S = self.cfg.num_speakers
+        sep = torch.empty((B, S, F, T), device=mixed.device, dtype=torch.float32)
+        masks = torch.empty_like(sep)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_forward(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
+                                        sep.data_ptr(), masks.data_ptr(), None, 0, self._stream())
+        self._check(rc, "avsep_forward")
+        return sep, masks
+
+    def forward_host(self, mixed: torch.Tensor, frames: torch.Tensor, sep: torch.Tensor = None,
+                     masks: torch.Tensor = None):
+        """CPU tensors in, CPU tensors out; H2D, kernels and D2H all inside the C call (pinned memory advised)."""
+        mixed = mixed.contiguous().float()
+        frames = frames.contiguous().float()
+        B, F, T = mixed.shape
+        _, N, Hh, Ww = frames.shape
+        S = self.cfg.num_speakers
+        if sep is None:
+            sep = torch.empty((B, S, F, T), dtype=torch.float32).pin_memory()
+        if masks is None:
+            masks = torch.empty((B, S, F, T), dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_forward_host(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
+                                             sep.data_ptr(), masks.data_ptr(), self._stream())
+        self._check(rc, "avsep_forward_host")
+        return sep, masks
+
+    def launch_count(self) -> int:
+        return int(self.lib.avsep_last_launch_count(self.h))
+
+    # ---- sub-modules -------------------------------------------------------------------------------
+    def audio_encoder(self, mixed):
+        mixed = self._dev_f32(mixed, "mixed_spec")
+        B, F, T = mixed.shape
+        out = torch.empty((B, T, self.cfg.d_model), device=mixed.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_audio_encoder(self.h, mixed.data_ptr(), B, T, out.data_ptr(), self._stream())
+        self._check(rc, "avsep_audio_encoder")
+        return out
+
+    def visual_encoder(self, frames, target_len: int):
+        frames = self._dev_f32(frames, "lip_frames")
+        B, N, Hh, Ww = frames.shape
+        out = torch.empty((B, int(target_len), self.cfg.d_model), device=frames.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_visual_encoder(self.h, frames.data_ptr(), B, N, Hh, Ww, int(target_len),
+                                               out.data_ptr(), self._stream())
+        self._check(rc, "avsep_visual_encoder")
+        return out
+
+    def fusion(self, audio, visual):
+        audio = self._dev_f32(audio, "audio")
+        visual = self._dev_f32(visual, "visual")
+        B, T, d = audio.shape
+        L = visual.shape[1]
+        out = torch.empty_like(audio)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_fusion(self.h, audio.data_ptr(), visual.data_ptr(), B, T, L, out.data_ptr(),
+                                       self._stream())
+        self._check(rc, "avsep_fusion")
+        return out
+
+    def decoder(self, fused, mixed):
+        fused = self._dev_f32(fused, "fused")
+        mixed = self._dev_f32(mixed, "mixed_spec")
+        B, T, d = fused.shape
+        F, S = self.cfg.freq_bins, self.cfg.num_speakers
+        sep = torch.empty((B, S, F, T), device=fused.device, dtype=torch.float32)
+        masks = torch.empty_like(sep)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_decoder(self.h, fused.data_ptr(), mixed.data_ptr(), B, T, sep.data_ptr(),
+                                        masks.data_ptr(), self._stream())
+        self._check(rc, "avsep_decoder")
+        return sep, masks
+
+    # ---- debug -------------------------------------------------------------------------------------
+    def set_debug(self, on: bool):
+        self._check(self.lib.avsep_set_debug(self.h, 1 if on else 0), "avsep_set_debug")
+
+    def get_stage(self, name: str) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self.lib.avsep_debug_get_stage(self.h, name.encode(), None, 0, C.byref(n)), "avsep_debug_get_stage")
+        out = np.empty(n.value, dtype=np.float32)
+        self._check(self.lib.avsep_debug_get_stage(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), n.value,
+                                                   C.byref(n)), "avsep_debug_get_stage")
+        return out

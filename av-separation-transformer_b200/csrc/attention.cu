@@ -1,0 +1,281 @@
+// Flash-style multi-head attention (no T x T materialisation, online softmax), forward only.
+//
+// Self-attention of the encoder stacks (reference: nn.TransformerEncoderLayer, model.py:48-52,97-101) and the
+// audio-queries-visual cross-attention of CrossModalFusion (model.py:155,169).  For cross-attention the K/V rows
+// are produced on load: the K/V projection is computed once on the N visual frames and the reference's
+// F.interpolate(mode='linear', align_corners=False) (model.py:114-116) is applied to the projected rows while the
+// tile is staged into shared memory (interp and projection commute: W(Ax)+b = A(Wx+b), rows of A sum to 1).
+//
+// One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows; K/V tiles of 64 rows; bf16 tensor-core
+// contractions with fp32 accumulation, fp32 softmax statistics, exp2 with the 1/sqrt(hd)*log2(e) scale folded in.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace avsep {
+
+namespace {
+
+struct AttnDev {
+  const __nv_bfloat16* q;
+  const void* k;
+  const void* v;
+  __nv_bfloat16* out;
+  int ldq, ldkv, ldo;
+  int H, Lq, Lk, nsrc;
+  float scale_log2;
+  float lerp_scale;   // (float)nsrc / Lk, as ATen computes it
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int QT = 64;   // query rows per CTA
+constexpr int KT = 64;   // key/value rows per tile
+
+// Stage ROWS x HD bf16 rows into padded shared memory; rows >= nrows are zero.
+template <int HD>
+__device__ __forceinline__ void load_tile_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, int ld, int row0,
+                                               int nrows) {
+  constexpr int LDS = HD + 8;
+  constexpr int CH = HD / 8;
+  for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (row0 + r < nrows) val = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(row0 + r) * ld + c * 8);
+    *reinterpret_cast<uint4*>(dst + r * LDS + c * 8) = val;
+  }
+}
+
+// Same, but each output row t is the linear interpolation of two fp32 source rows (ATen upsample_linear1d,
+// align_corners=False: src = max(scale*(t+0.5)-0.5, 0); i0 = floor(src); i1 = min(i0+1, n-1); lam = src-i0).
+template <int HD>
+__device__ __forceinline__ void load_tile_lerp(__nv_bfloat16* dst, const float* src, int ld, int row0, int nrows,
+                                               int nsrc, float scale) {
+  constexpr int LDS = HD + 8;
+  constexpr int CH = HD / 8;
+  for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    const int t = row0 + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (t < nrows) {
+      const float sp = fmaxf(scale * (static_cast<float>(t) + 0.5f) - 0.5f, 0.0f);
+      int i0 = static_cast<int>(sp);
+      if (i0 > nsrc - 1) i0 = nsrc - 1;
+      const int i1 = min(i0 + 1, nsrc - 1);
+      const float w1 = sp - static_cast<float>(i0);
+      const float w0 = 1.0f - w1;
+      const float4* p0 = reinterpret_cast<const float4*>(src + static_cast<size_t>(i0) * ld + c * 8);
+      const float4* p1 = reinterpret_cast<const float4*>(src + static_cast<size_t>(i1) * ld + c * 8);
+      const float4 a0 = __ldg(p0), a1 = __ldg(p0 + 1), b0 = __ldg(p1), b1 = __ldg(p1 + 1);
+      val.x = pack_bf16x2(w0 * a0.x + w1 * b0.x, w0 * a0.y + w1 * b0.y);
+      val.y = pack_bf16x2(w0 * a0.z + w1 * b0.z, w0 * a0.w + w1 * b0.w);
+      val.z = pack_bf16x2(w0 * a1.x + w1 * b1.x, w0 * a1.y + w1 * b1.y);
+      val.w = pack_bf16x2(w0 * a1.z + w1 * b1.z, w0 * a1.w + w1 * b1.w);
+    }
+    *reinterpret_cast<uint4*>(dst + r * LDS + c * 8) = val;
+  }
+}
+
+template <int HD, bool LERP>
+__global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
+  constexpr int LDS = HD + 8;           // padded row (elements): 16-byte rows shifted by 4 banks -> conflict-free ldmatrix
+  constexpr int KS = HD / 16;           // k-steps over the head dimension
+  constexpr int NT_O = HD / 8;          // output n-tiles
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sK = sQ + QT * LDS;
+  __nv_bfloat16* sV = sK + KT * LDS;
+
+  const int q0 = blockIdx.x * QT;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const __nv_bfloat16* qsrc = p.q + static_cast<size_t>(b) * p.Lq * p.ldq + h * HD;
+  load_tile_bf16<HD>(sQ, qsrc, p.ldq, q0, p.Lq);
+  __syncthreads();
+
+  // Q fragments stay in registers for the whole K/V sweep.
+  uint32_t qf[KS][4];
+  {
+    const int row = warp * 16 + (lane & 15);
+    const int col = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ + row * LDS + ks * 16 + col));
+  }
+
+  float o[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  const int num_kv_tiles = (p.Lk + KT - 1) / KT;
+  for (int jt = 0; jt < num_kv_tiles; ++jt) {
+    const int kv0 = jt * KT;
+    __syncthreads();   // previous tile fully consumed
+    if constexpr (LERP) {
+      const float* ksrc = reinterpret_cast<const float*>(p.k) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
+      const float* vsrc = reinterpret_cast<const float*>(p.v) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
+      load_tile_lerp<HD>(sK, ksrc, p.ldkv, kv0, p.Lk, p.nsrc, p.lerp_scale);
+      load_tile_lerp<HD>(sV, vsrc, p.ldkv, kv0, p.Lk, p.nsrc, p.lerp_scale);
+    } else {
+      const __nv_bfloat16* ksrc =
+          reinterpret_cast<const __nv_bfloat16*>(p.k) + static_cast<size_t>(b) * p.Lk * p.ldkv + h * HD;
+      const __nv_bfloat16* vsrc =
+          reinterpret_cast<const __nv_bfloat16*>(p.v) + static_cast<size_t>(b) * p.Lk * p.ldkv + h * HD;
+      load_tile_bf16<HD>(sK, ksrc, p.ldkv, kv0, p.Lk);
+      load_tile_bf16<HD>(sV, vsrc, p.ldkv, kv0, p.Lk);
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {   // pairs of 8-wide kv n-tiles
+        uint32_t bf[4];
+        const int row = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int col = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(bf, smem_u32(sK + row * LDS + col));
+        mma_bf16_16816(s[2 * np], qf[ks], bf[0], bf[1]);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], bf[2], bf[3]);
+      }
+    }
+
+    // ---- online softmax (rows lane/4 and lane/4 + 8; columns 2*(lane%4)+{0,1} of each n-tile) ----
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = kv0 + nt * 8 + 2 * (lane & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = (c + (e & 1)) < p.Lk;
+        const float val = ok ? s[nt][e] * p.scale_log2 : -INFINITY;
+        s[nt][e] = val;
+        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+      }
+    }
+    float alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);     // finite: every tile has at least one valid column
+      alpha[r] = exp2f(m_run[r] - m_new);
+      m_run[r] = m_new;
+      l_run[r] *= alpha[r];
+    }
+    uint32_t pf[4][4];   // P as A fragments for the 4 k-steps over this kv tile
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - m_run[0]);
+      const float p1 = exp2f(s[nt][1] - m_run[0]);
+      const float p2 = exp2f(s[nt][2] - m_run[1]);
+      const float p3 = exp2f(s[nt][3] - m_run[1]);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int i = 0; i < NT_O; ++i) {
+      o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
+      o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
+    }
+
+    // ---- O += P V ----
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {          // 16 kv rows per step
+#pragma unroll
+      for (int np = 0; np < NT_O / 2; ++np) { // pairs of 8-wide hd n-tiles
+        uint32_t bf[4];
+        const int row = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+        const int col = np * 16 + (lane >> 4) * 8;
+        ldmatrix_x4_trans(bf, smem_u32(sV + row * LDS + col));
+        mma_bf16_16816(o[2 * np], pf[ks], bf[0], bf[1]);
+        mma_bf16_16816(o[2 * np + 1], pf[ks], bf[2], bf[3]);
+      }
+    }
+  }
+
+  // ---- normalise and store ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = 1.0f / l_run[0];
+  const float inv1 = 1.0f / l_run[1];
+  const int r0 = q0 + warp * 16 + (lane >> 2);
+  const int r1 = r0 + 8;
+  __nv_bfloat16* obase = p.out + static_cast<size_t>(b) * p.Lq * p.ldo + h * HD + 2 * (lane & 3);
+#pragma unroll
+  for (int nt = 0; nt < NT_O; ++nt) {
+    if (r0 < p.Lq)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r0) * p.ldo + nt * 8) =
+          pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+    if (r1 < p.Lq)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r1) * p.ldo + nt * 8) =
+          pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+  }
+}
+
+template <int HD, bool LERP>
+const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
+  constexpr int SMEM = 3 * 64 * (HD + 8) * 2;
+  static bool attr_done = false;
+  auto kern = attention_kernel<HD, LERP>;
+  if (!attr_done && SMEM > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return "attention: cudaFuncSetAttribute failed";
+    attr_done = true;
+  }
+  dim3 grid((Lq + QT - 1) / QT, H, B);
+  kern<<<grid, 128, SMEM, s>>>(d);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
+}
+
+}  // namespace
+
+const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p) {
+  if (prec != PREC_BF16) return "attention: only the bf16 path is implemented";
+  if (p.B <= 0 || p.Lq <= 0 || p.Lk <= 0) return "attention: empty problem";
+  AttnDev d;
+  d.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  d.k = p.k; d.v = p.v;
+  d.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  d.ldq = p.ldq; d.ldkv = p.ldkv; d.ldo = p.ldo;
+  d.H = p.H; d.Lq = p.Lq; d.Lk = p.Lk; d.nsrc = p.lerp_src;
+  d.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.hd));
+  d.lerp_scale = p.lerp_src > 0 ? static_cast<float>(p.lerp_src) / static_cast<float>(p.Lk) : 0.f;
+  const bool lerp = p.lerp_src > 0;
+  if ((p.ldq & 7) || (p.ldo & 1) || (lerp ? (p.ldkv & 3) : (p.ldkv & 7))) return "attention: misaligned leading dimension";
+  switch (p.hd) {
+    case 16: return lerp ? launch_t<16, true>(s, d, p.B, p.H, p.Lq) : launch_t<16, false>(s, d, p.B, p.H, p.Lq);
+    case 32: return lerp ? launch_t<32, true>(s, d, p.B, p.H, p.Lq) : launch_t<32, false>(s, d, p.B, p.H, p.Lq);
+    case 64: return lerp ? launch_t<64, true>(s, d, p.B, p.H, p.Lq) : launch_t<64, false>(s, d, p.B, p.H, p.Lq);
+    case 128: return lerp ? launch_t<128, true>(s, d, p.B, p.H, p.Lq) : launch_t<128, false>(s, d, p.B, p.H, p.Lq);
+    default: return "attention: head dim must be 16, 32, 64 or 128";
+  }
+}
+
+}  // namespace avsep

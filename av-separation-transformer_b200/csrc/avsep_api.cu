@@ -1,0 +1,864 @@
+// C-ABI layer of libavsep.so (see include/avsep.h): handle, weight prepack, workspace plan and the forward
+// orchestration of AVSeparationTransformer.forward (reference: model.py:268-276 and everything it calls).
+#include "../../include/avsep.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace avsep;
+
+namespace {
+
+std::string g_create_error;
+
+inline uint16_t f2bf_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+__global__ void op_to_f32_kernel(const __nv_bfloat16* in, float* out, size_t n) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+// out[b, t, :] = lerp of x[b, i0(t), :], x[b, i1(t), :]   (F.interpolate linear, align_corners=False; model.py:115)
+__global__ void interp_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int T, int d,
+                                   float scale) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const float sp = fmaxf(scale * (static_cast<float>(t) + 0.5f) - 0.5f, 0.0f);
+  int i0 = static_cast<int>(sp);
+  if (i0 > N - 1) i0 = N - 1;
+  const int i1 = min(i0 + 1, N - 1);
+  const float w1 = sp - static_cast<float>(i0), w0 = 1.0f - w1;
+  const float* r0 = x + (static_cast<size_t>(b) * N + i0) * d;
+  const float* r1 = x + (static_cast<size_t>(b) * N + i1) * d;
+  float* o = out + (static_cast<size_t>(b) * T + t) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) o[c] = w0 * r0[c] + w1 * r1[c];
+}
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct EncLayerW {
+  const void *wqkv, *wo, *w1, *w2;
+  const float *bqkv, *bo, *b1, *b2, *n1g, *n1b, *n2g, *n2b;
+};
+struct FusLayerW {
+  const void *wq, *wo, *w1, *w2;
+  const float *bq, *bo, *b1, *b2, *n1g, *n1b, *n2g, *n2b;
+};
+
+struct Workspace {   // carved from one base pointer; all offsets 1 KB aligned
+  int B = 0, T = 0, N = 0, Hh = 0, Ww = 0;
+  size_t bytes = 0;
+  // audio side
+  void *xp, *h1, *a_op, *qkv_a, *attn_a, *ffn_a;
+  float *x_a, *y_a;
+  // visual side
+  void *pooled, *v_op, *qkv_v, *attn_v, *ffn_v;
+  float *x_v, *y_v, *kvn;
+};
+
+}  // namespace
+
+struct avsep_handle {
+  avsep_config cfg{};
+  int Fp = 0;
+  int num_sms = 148;
+  std::string err;
+  std::map<std::string, HostTensor> host_w;
+  bool finalized = false;
+  uint8_t* d_weights = nullptr;
+  size_t weight_bytes = 0;
+  // device views into d_weights
+  const void *wc1 = nullptr, *wc2 = nullptr, *wproj = nullptr, *wkv_all = nullptr, *wdec0 = nullptr, *wdec3 = nullptr;
+  const float *bc1 = nullptr, *bc2 = nullptr, *bproj = nullptr, *bkv_all = nullptr, *bdec0 = nullptr, *bdec3 = nullptr;
+  const float *pe_a = nullptr, *pe_v = nullptr, *fng = nullptr, *fnb = nullptr;
+  CnnWeights cnn{};
+  std::vector<EncLayerW> enc_a, enc_v;
+  std::vector<FusLayerW> fus;
+  // cached library-owned workspace
+  void* own_ws = nullptr;
+  size_t own_ws_bytes = 0;
+  // host-path staging
+  float *io_mixed = nullptr, *io_frames = nullptr, *io_sep = nullptr, *io_masks = nullptr;
+  size_t io_cap[4] = {0, 0, 0, 0};
+  // debug
+  bool debug = false;
+  std::map<std::string, std::pair<float*, size_t>> snaps;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int fail(avsep_handle* h, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return 1;
+}
+
+#define CK(expr)                                                        \
+  do {                                                                  \
+    const char* _e = (expr);                                            \
+    if (_e != nullptr) return fail(h, std::string(_e) + " [" #expr "]"); \
+    ++h->launches;                                                      \
+  } while (0)
+
+#define CUDA_OK(expr)                                                                           \
+  do {                                                                                          \
+    cudaError_t _c = (expr);                                                                    \
+    if (_c != cudaSuccess) return fail(h, std::string(#expr ": ") + cudaGetErrorString(_c));    \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t op_size(const avsep_handle* h) { return h->cfg.precision == AVSEP_PREC_TF32 ? 4 : 2; }
+
+// ---- workspace -------------------------------------------------------------------------------
+size_t carve_workspace(const avsep_handle* h, Workspace& w, uint8_t* base, int B, int T, int N, int Hh, int Ww) {
+  const size_t d = h->cfg.d_model, os = op_size(h);
+  const size_t Ma = static_cast<size_t>(B) * T, Map = static_cast<size_t>(B) * (T + 2), Mv = static_cast<size_t>(B) * N;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  w.B = B; w.T = T; w.N = N; w.Hh = Hh; w.Ww = Ww;
+  w.xp = take(Map * h->Fp * os);
+  w.h1 = take(Map * d * os);
+  w.x_a = static_cast<float*>(take(Ma * d * 4));
+  w.y_a = static_cast<float*>(take(Ma * d * 4));
+  w.a_op = take(Ma * d * os);
+  w.qkv_a = take(Ma * 3 * d * os);
+  w.attn_a = take(Ma * d * os);
+  w.ffn_a = take(Ma * 4 * d * os);
+  w.pooled = take(Mv * 128 * os);
+  w.x_v = static_cast<float*>(take(Mv * d * 4));
+  w.y_v = static_cast<float*>(take(Mv * d * 4));
+  w.v_op = take(Mv * d * os);
+  w.qkv_v = take(Mv * 3 * d * os);
+  w.attn_v = take(Mv * d * os);
+  w.ffn_v = take(Mv * 4 * d * os);
+  w.kvn = static_cast<float*>(take(Mv * h->cfg.num_fusion_layers * 2 * d * 4));
+  w.bytes = off;
+  return off;
+}
+
+int check_shape(avsep_handle* h, int B, int T, int N, int Hh, int Ww) {
+  if (!h->finalized) return fail(h, "weights not finalized: call avsep_finalize_weights first");
+  if (B < 1 || T < 1 || N < 1 || Hh < 1 || Ww < 1) return fail(h, "empty input: B, T, N, H, W must be >= 1");
+  if (T > 5000 || N > 5000) return fail(h, "sequence longer than the positional table (max_len=5000, model.py:286)");
+  return 0;
+}
+
+int get_workspace(avsep_handle* h, Workspace& w, void* user_ws, size_t user_bytes, int B, int T, int N, int Hh, int Ww) {
+  const size_t need = carve_workspace(h, w, nullptr, B, T, N, Hh, Ww);
+  uint8_t* base = nullptr;
+  if (user_ws != nullptr) {
+    if (user_bytes < need) return fail(h, "workspace too small: see avsep_workspace_bytes");
+    if ((reinterpret_cast<uintptr_t>(user_ws) & 1023) != 0) return fail(h, "workspace must be 1024-byte aligned");
+    base = static_cast<uint8_t*>(user_ws);
+  } else {
+    if (h->own_ws_bytes < need) {
+      if (h->own_ws) cudaFree(h->own_ws);
+      h->own_ws = nullptr;
+      h->own_ws_bytes = 0;
+      CUDA_OK(cudaMalloc(&h->own_ws, need));
+      h->own_ws_bytes = need;
+    }
+    base = static_cast<uint8_t*>(h->own_ws);
+  }
+  carve_workspace(h, w, base, B, T, N, Hh, Ww);
+  return 0;
+}
+
+// ---- debug snapshots ---------------------------------------------------------------------------
+int snapshot(avsep_handle* h, cudaStream_t s, const char* name, const void* ptr, size_t count, bool is_op) {
+  if (!h->debug) return 0;
+  auto& slot = h->snaps[name];
+  if (slot.second < count) {
+    if (slot.first) cudaFree(slot.first);
+    slot.first = nullptr;
+    CUDA_OK(cudaMalloc(&slot.first, count * sizeof(float)));
+  }
+  slot.second = count;
+  if (is_op && h->cfg.precision == AVSEP_PREC_BF16) {
+    op_to_f32_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(ptr), slot.first, count);
+  } else {
+    CUDA_OK(cudaMemcpyAsync(slot.first, ptr, count * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+// ---- stage helpers -----------------------------------------------------------------------------
+int linear(avsep_handle* h, cudaStream_t s, const void* A, int M, int K, const void* W, const float* bias, int N, int act,
+           float* out_f32, void* out_op) {
+  GemmProblem p{};
+  p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K;
+  p.taps = 1; p.tap_stride = 0; p.row_shift = 0;
+  GemmEpilogue e;
+  e.bias = bias; e.act = act;
+  e.out_f32 = out_f32; e.ld_f32 = N;
+  e.out_op = out_op; e.ld_op = N;
+  CK(launch_gemm(s, h->cfg.precision, p, e));
+  return 0;
+}
+
+int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>& layers, int B, int L, float* x,
+                  float* y, void* a_op, void* qkv, void* attn, void* ffn, const float* final_g, const float* final_b) {
+  const int d = h->cfg.d_model, H = h->cfg.nhead, M = B * L, prec = h->cfg.precision;
+  const size_t os = op_size(h);
+  for (size_t l = 0; l < layers.size(); ++l) {
+    const EncLayerW& w = layers[l];
+    if (linear(h, s, a_op, M, d, w.wqkv, w.bqkv, 3 * d, ACT_NONE, nullptr, qkv)) return 1;
+    AttnProblem ap{};
+    ap.q = qkv; ap.ldq = 3 * d;
+    ap.k = static_cast<const uint8_t*>(qkv) + static_cast<size_t>(d) * os;
+    ap.v = static_cast<const uint8_t*>(qkv) + static_cast<size_t>(2 * d) * os;
+    ap.ldkv = 3 * d;
+    ap.out = attn; ap.ldo = d;
+    ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = L; ap.Lk = L; ap.lerp_src = 0;
+    CK(launch_attention(s, prec, ap));
+    if (linear(h, s, attn, M, d, w.wo, w.bo, d, ACT_NONE, y, nullptr)) return 1;
+    CK(launch_add_layernorm(s, prec, x, y, w.n2g, w.n2b, x, a_op, M, d));
+    if (linear(h, s, a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
+    if (linear(h, s, ffn, M, 4 * d, w.w2, w.b2, d, ACT_NONE, y, nullptr)) return 1;
+    const bool last = (l + 1 == layers.size());
+    const float* g = last ? final_g : layers[l + 1].n1g;
+    const float* b = last ? final_b : layers[l + 1].n1b;
+    CK(launch_add_layernorm(s, prec, x, y, g, b, x, a_op, M, d));
+  }
+  return 0;
+}
+
+// AudioEncoder up to (not including) the transformer: Conv1d+ReLU x2, +PE  (model.py:56-58)
+int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed) {
+  const int d = h->cfg.d_model, F = h->cfg.freq_bins, B = w.B, T = w.T, prec = h->cfg.precision;
+  const int Map = B * (T + 2);
+  CK(launch_prep_audio(s, prec, mixed, w.xp, B, F, T, h->Fp));
+  {
+    GemmProblem p{};
+    p.A = w.xp; p.lda = h->Fp; p.rowsA = Map; p.M = Map; p.W = h->wc1; p.ldw = 3 * h->Fp; p.N = d; p.K = h->Fp;
+    p.taps = 3; p.tap_stride = h->Fp; p.row_shift = -1;
+    GemmEpilogue e;
+    e.bias = h->bc1; e.act = ACT_RELU; e.rowmap = ROW_PAD2PAD; e.Lp = T + 2;
+    e.out_op = w.h1; e.ld_op = d;
+    CK(launch_gemm(s, prec, p, e));
+  }
+  {
+    GemmProblem p{};
+    p.A = w.h1; p.lda = d; p.rowsA = Map; p.M = Map; p.W = h->wc2; p.ldw = 3 * d; p.N = d; p.K = d;
+    p.taps = 3; p.tap_stride = d; p.row_shift = -1;
+    GemmEpilogue e;
+    e.bias = h->bc2; e.act = ACT_RELU; e.rowmap = ROW_PAD2COMPACT; e.Lp = T + 2;
+    e.pe = h->pe_a;
+    e.out_f32 = w.x_a; e.ld_f32 = d;
+    CK(launch_gemm(s, prec, p, e));
+  }
+  return snapshot(h, s, "audio_embed", w.x_a, static_cast<size_t>(B) * T * d, false);
+}
+
+// VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110)
+int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames) {
+  const int d = h->cfg.d_model, B = w.B, N = w.N, prec = h->cfg.precision;
+  const int Mv = B * N;
+  CK(launch_visual_cnn(s, prec, frames, Mv, w.Hh, w.Ww, h->cnn, w.pooled, h->num_sms));
+  if (snapshot(h, s, "visual_pool", w.pooled, static_cast<size_t>(Mv) * 128, true)) return 1;
+  GemmProblem p{};
+  p.A = w.pooled; p.lda = 128; p.rowsA = Mv; p.M = Mv; p.W = h->wproj; p.ldw = 128; p.N = d; p.K = 128;
+  p.taps = 1;
+  GemmEpilogue e;
+  e.bias = h->bproj; e.pe = h->pe_v; e.pe_period = N;
+  e.out_f32 = w.x_v; e.ld_f32 = d;
+  CK(launch_gemm(s, prec, p, e));
+  return snapshot(h, s, "visual_embed", w.x_v, static_cast<size_t>(Mv) * d, false);
+}
+
+// CrossModalFusion (model.py:145-149,166-173).  In: x_a residual stream, a_op = LN_{layer0.norm1}(x_a),
+// v_op = visual rows (L_src per utterance).  Out: a_op = fusion.norm(x) in operand precision.
+int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
+  const int d = h->cfg.d_model, H = h->cfg.nhead, B = w.B, T = w.T, prec = h->cfg.precision;
+  const int Ma = B * T, Mv = B * L_src, Lf = h->cfg.num_fusion_layers;
+  // K/V projection of every fusion layer in one GEMM on the un-interpolated visual rows
+  if (linear(h, s, w.v_op, Mv, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, w.kvn, nullptr)) return 1;
+  for (int l = 0; l < Lf; ++l) {
+    const FusLayerW& fw = h->fus[l];
+    if (linear(h, s, w.a_op, Ma, d, fw.wq, fw.bq, d, ACT_NONE, nullptr, w.qkv_a)) return 1;
+    AttnProblem ap{};
+    ap.q = w.qkv_a; ap.ldq = d;
+    ap.k = w.kvn + static_cast<size_t>(l) * 2 * d;
+    ap.v = w.kvn + static_cast<size_t>(l) * 2 * d + d;
+    ap.ldkv = Lf * 2 * d;
+    ap.out = w.attn_a; ap.ldo = d;
+    ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = T; ap.Lk = T; ap.lerp_src = L_src;
+    CK(launch_attention(s, prec, ap));
+    if (linear(h, s, w.attn_a, Ma, d, fw.wo, fw.bo, d, ACT_NONE, w.y_a, nullptr)) return 1;
+    CK(launch_add_layernorm(s, prec, w.x_a, w.y_a, fw.n2g, fw.n2b, w.x_a, w.a_op, Ma, d));
+    if (linear(h, s, w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
+    if (linear(h, s, w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, ACT_NONE, w.y_a, nullptr)) return 1;
+    const bool last = (l + 1 == Lf);
+    const float* g = last ? h->fng : h->fus[l + 1].n1g;
+    const float* b = last ? h->fnb : h->fus[l + 1].n1b;
+    CK(launch_add_layernorm(s, prec, w.x_a, w.y_a, g, b, w.x_a, w.a_op, Ma, d));
+  }
+  return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
+}
+
+// SeparationDecoder.forward + .separate (model.py:201-220): a_op = fused rows in operand precision.
+int decoder_stage(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, float* separated, float* masks) {
+  const int d = h->cfg.d_model, F = h->cfg.freq_bins, S = h->cfg.num_speakers, B = w.B, T = w.T;
+  const int Ma = B * T;
+  if (linear(h, s, w.a_op, Ma, d, h->wdec0, h->bdec0, 2 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
+  GemmProblem p{};
+  p.A = w.ffn_a; p.lda = 2 * d; p.rowsA = Ma; p.M = Ma; p.W = h->wdec3; p.ldw = 2 * d; p.N = S * F; p.K = 2 * d;
+  p.taps = 1;
+  GemmEpilogue e;
+  e.kind = EPI_TAIL;
+  e.bias = h->bdec3;
+  e.mixed = mixed; e.masks = masks; e.separated = separated; e.F = F; e.S = S; e.T = T;
+  CK(launch_gemm(s, h->cfg.precision, p, e));
+  return 0;
+}
+
+int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* frames,
+                   float* separated, float* masks) {
+  const int d = h->cfg.d_model, prec = h->cfg.precision;
+  const int Ma = w.B * w.T, Mv = w.B * w.N;
+  // --- audio branch ---
+  if (audio_frontend(h, s, w, mixed)) return 1;
+  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
+                    h->fus[0].n1b))
+    return 1;
+  if (snapshot(h, s, "audio_enc", w.x_a, static_cast<size_t>(Ma) * d, false)) return 1;
+  // --- visual branch ---
+  if (visual_frontend(h, s, w, frames)) return 1;
+  CK(launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  if (encoder_stack(h, s, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
+    return 1;
+  if (snapshot(h, s, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
+  // --- fusion + decoder ---
+  if (fusion_stack(h, s, w, w.N)) return 1;
+  return decoder_stage(h, s, w, mixed, separated, masks);
+}
+
+// ---- weight access helpers ---------------------------------------------------------------------
+const HostTensor* find_w(avsep_handle* h, const std::string& key, std::initializer_list<int64_t> shape) {
+  auto it = h->host_w.find(key);
+  if (it == h->host_w.end()) {
+    h->err = "missing weight: " + key;
+    return nullptr;
+  }
+  std::vector<int64_t> want(shape);
+  if (it->second.shape != want) {
+    h->err = "bad shape for weight: " + key;
+    return nullptr;
+  }
+  return &it->second;
+}
+
+struct ArenaBuilder {
+  std::vector<uint8_t> bytes;
+  size_t add(const void* src, size_t n) {
+    const size_t off = align_up(bytes.size(), 256);
+    bytes.resize(off + n);
+    if (src) memcpy(bytes.data() + off, src, n);
+    return off;
+  }
+  size_t add_f32(const float* src, size_t n) { return add(src, n * 4); }
+  size_t add_op(const float* src, size_t n, bool tf32) {
+    if (tf32) return add(src, n * 4);
+    std::vector<uint16_t> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = f2bf_host(src[i]);
+    return add(tmp.data(), n * 2);
+  }
+};
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int avsep_create(const avsep_config* cfg, avsep_handle** out) {
+  if (!cfg || !out) return fail(nullptr, "avsep_create: null argument");
+  *out = nullptr;
+  if (cfg->freq_bins < 1 || cfg->d_model < 8 || cfg->nhead < 1 || cfg->num_encoder_layers < 1 ||
+      cfg->num_fusion_layers < 1 || cfg->num_speakers < 1)
+    return fail(nullptr, "avsep_create: all sizes must be positive (at least one encoder and one fusion layer)");
+  if (cfg->d_model % cfg->nhead != 0) return fail(nullptr, "avsep_create: d_model must be divisible by nhead");
+  const int hd = cfg->d_model / cfg->nhead;
+  if (hd != 16 && hd != 32 && hd != 64 && hd != 128)
+    return fail(nullptr, "avsep_create: head dim (d_model/nhead) must be 16, 32, 64 or 128");
+  if (cfg->d_model % 8 != 0 || cfg->d_model > 1024)
+    return fail(nullptr, "avsep_create: d_model must be a multiple of 8 and <= 1024");
+  if (cfg->precision != AVSEP_PREC_BF16 && cfg->precision != AVSEP_PREC_TF32)
+    return fail(nullptr, "avsep_create: unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, "avsep_create: no CUDA device (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "avsep_create: bad device ordinal");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, "avsep_create: device query failed");
+  if (prop.major != 10) return fail(nullptr, "avsep_create: kernels are built for sm_100a (B200) only");
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, "avsep_create: cudaSetDevice failed");
+  if (const char* e = gemm_init()) return fail(nullptr, e);
+  avsep_handle* h = new avsep_handle();
+  h->cfg = *cfg;
+  h->Fp = (cfg->freq_bins + 7) / 8 * 8;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+void avsep_destroy(avsep_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->d_weights) cudaFree(h->d_weights);
+  if (h->own_ws) cudaFree(h->own_ws);
+  if (h->io_mixed) cudaFree(h->io_mixed);
+  if (h->io_frames) cudaFree(h->io_frames);
+  if (h->io_sep) cudaFree(h->io_sep);
+  if (h->io_masks) cudaFree(h->io_masks);
+  for (auto& kv : h->snaps)
+    if (kv.second.first) cudaFree(kv.second.first);
+  delete h;
+}
+
+const char* avsep_last_error(const avsep_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int avsep_set_weight(avsep_handle* h, const char* key, const void* host_data, int32_t dtype, const int64_t* shape,
+                     int32_t ndim) {
+  if (!h || !key || (!host_data && ndim >= 0) || ndim < 0 || ndim > 8) return fail(h, "avsep_set_weight: bad argument");
+  if (dtype == AVSEP_DTYPE_I64) return 0;   // num_batches_tracked: unused in eval mode
+  if (dtype != AVSEP_DTYPE_F32) return fail(h, "avsep_set_weight: only fp32 tensors are accepted");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) return fail(h, "avsep_set_weight: negative dimension");
+    t.shape.push_back(shape[i]);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  t.data.assign(static_cast<const float*>(host_data), static_cast<const float*>(host_data) + n);
+  h->host_w[key] = std::move(t);
+  h->finalized = false;
+  return 0;
+}
+
+int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
+  if (!h) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  const int64_t d = h->cfg.d_model, F = h->cfg.freq_bins, S = h->cfg.num_speakers, Fp = h->Fp;
+  const int Le = h->cfg.num_encoder_layers, Lf = h->cfg.num_fusion_layers;
+  const bool tf32 = h->cfg.precision == AVSEP_PREC_TF32;
+  ArenaBuilder ar;
+  std::map<std::string, size_t> off;
+#define GETW(var, key, ...)                                  \
+  const HostTensor* var = find_w(h, key, {__VA_ARGS__});     \
+  if (!var) return 1;
+
+  // --- AudioEncoder Conv1d weights: (Cout, Cin, 3) -> (Cout, 3*Cin_pad), k = tap*Cin_pad + c
+  {
+    GETW(w0, "audio_encoder.input_proj.0.weight", d, F, 3);
+    GETW(b0, "audio_encoder.input_proj.0.bias", d);
+    GETW(w2, "audio_encoder.input_proj.2.weight", d, d, 3);
+    GETW(b2, "audio_encoder.input_proj.2.bias", d);
+    std::vector<float> p0(static_cast<size_t>(d) * 3 * Fp, 0.f), p2(static_cast<size_t>(d) * 3 * d, 0.f);
+    for (int64_t o = 0; o < d; ++o)
+      for (int64_t c = 0; c < F; ++c)
+        for (int tap = 0; tap < 3; ++tap) p0[(o * 3 + tap) * Fp + c] = w0->data[(o * F + c) * 3 + tap];
+    for (int64_t o = 0; o < d; ++o)
+      for (int64_t c = 0; c < d; ++c)
+        for (int tap = 0; tap < 3; ++tap) p2[(o * 3 + tap) * d + c] = w2->data[(o * d + c) * 3 + tap];
+    off["wc1"] = ar.add_op(p0.data(), p0.size(), tf32);
+    off["wc2"] = ar.add_op(p2.data(), p2.size(), tf32);
+    off["bc1"] = ar.add_f32(b0->data.data(), d);
+    off["bc2"] = ar.add_f32(b2->data.data(), d);
+    GETW(pea, "audio_encoder.pos_enc.pe", 1, 5000, d);
+    GETW(pev, "visual_encoder.pos_enc.pe", 1, 5000, d);
+    off["pe_a"] = ar.add_f32(pea->data.data(), pea->data.size());
+    off["pe_v"] = ar.add_f32(pev->data.data(), pev->data.size());
+  }
+  // --- encoder stacks
+  for (int stack = 0; stack < 2; ++stack) {
+    const std::string pre = stack == 0 ? "audio_encoder" : "visual_encoder";
+    for (int l = 0; l < Le; ++l) {
+      const std::string p = pre + ".transformer.layers." + std::to_string(l);
+      const std::string t = (stack == 0 ? "a" : "v") + std::to_string(l);
+      GETW(wqkv, p + ".self_attn.in_proj_weight", 3 * d, d);
+      GETW(bqkv, p + ".self_attn.in_proj_bias", 3 * d);
+      GETW(wo, p + ".self_attn.out_proj.weight", d, d);
+      GETW(bo, p + ".self_attn.out_proj.bias", d);
+      GETW(w1, p + ".linear1.weight", 4 * d, d);
+      GETW(b1, p + ".linear1.bias", 4 * d);
+      GETW(w2, p + ".linear2.weight", d, 4 * d);
+      GETW(b2, p + ".linear2.bias", d);
+      GETW(n1g, p + ".norm1.weight", d);
+      GETW(n1b, p + ".norm1.bias", d);
+      GETW(n2g, p + ".norm2.weight", d);
+      GETW(n2b, p + ".norm2.bias", d);
+      off[t + "wqkv"] = ar.add_op(wqkv->data.data(), wqkv->data.size(), tf32);
+      off[t + "wo"] = ar.add_op(wo->data.data(), wo->data.size(), tf32);
+      off[t + "w1"] = ar.add_op(w1->data.data(), w1->data.size(), tf32);
+      off[t + "w2"] = ar.add_op(w2->data.data(), w2->data.size(), tf32);
+      off[t + "bqkv"] = ar.add_f32(bqkv->data.data(), 3 * d);
+      off[t + "bo"] = ar.add_f32(bo->data.data(), d);
+      off[t + "b1"] = ar.add_f32(b1->data.data(), 4 * d);
+      off[t + "b2"] = ar.add_f32(b2->data.data(), d);
+      off[t + "n1g"] = ar.add_f32(n1g->data.data(), d);
+      off[t + "n1b"] = ar.add_f32(n1b->data.data(), d);
+      off[t + "n2g"] = ar.add_f32(n2g->data.data(), d);
+      off[t + "n2b"] = ar.add_f32(n2b->data.data(), d);
+    }
+  }
+  // --- VisualEncoder CNN: fold BatchNorm (eval) into conv weight/bias, repack tap-major, fragment order
+  {
+    const int cins[3] = {1, 32, 64}, couts[3] = {32, 64, 128}, idx[3] = {0, 3, 6};
+    std::vector<float> folded[3], fbias[3];
+    for (int c = 0; c < 3; ++c) {
+      const std::string cp = "visual_encoder.conv." + std::to_string(idx[c]);
+      const std::string bp = "visual_encoder.conv." + std::to_string(idx[c] + 1);
+      GETW(w, cp + ".weight", couts[c], cins[c], 3, 3);
+      GETW(b, cp + ".bias", couts[c]);
+      GETW(g, bp + ".weight", couts[c]);
+      GETW(be, bp + ".bias", couts[c]);
+      GETW(mu, bp + ".running_mean", couts[c]);
+      GETW(var, bp + ".running_var", couts[c]);
+      const int K = 9 * cins[c];
+      folded[c].assign(static_cast<size_t>(couts[c]) * K, 0.f);
+      fbias[c].assign(couts[c], 0.f);
+      for (int o = 0; o < couts[c]; ++o) {
+        const float scale = g->data[o] / sqrtf(var->data[o] + 1e-5f);
+        fbias[c][o] = (b->data[o] - mu->data[o]) * scale + be->data[o];
+        for (int ci = 0; ci < cins[c]; ++ci)
+          for (int tap = 0; tap < 9; ++tap)
+            folded[c][static_cast<size_t>(o) * K + tap * cins[c] + ci] =
+                w->data[(static_cast<size_t>(o) * cins[c] + ci) * 9 + tap] * scale;
+      }
+    }
+    std::vector<uint32_t> p1(visual_cnn_pack_sizes(1)), p2(visual_cnn_pack_sizes(2)), p3(visual_cnn_pack_sizes(3));
+    visual_cnn_pack(folded[0].data(), folded[1].data(), folded[2].data(), p1.data(), p2.data(), p3.data());
+    off["cw1"] = ar.add(p1.data(), p1.size() * 4);
+    off["cw2"] = ar.add(p2.data(), p2.size() * 4);
+    off["cw3"] = ar.add(p3.data(), p3.size() * 4);
+    off["cb1"] = ar.add_f32(fbias[0].data(), 32);
+    off["cb2"] = ar.add_f32(fbias[1].data(), 64);
+    off["cb3"] = ar.add_f32(fbias[2].data(), 128);
+    GETW(wp, "visual_encoder.frame_proj.weight", d, 128);
+    GETW(bp_, "visual_encoder.frame_proj.bias", d);
+    off["wproj"] = ar.add_op(wp->data.data(), wp->data.size(), tf32);
+    off["bproj"] = ar.add_f32(bp_->data.data(), d);
+  }
+  // --- fusion: q rows of the packed in_proj per layer; k|v rows of every layer concatenated
+  {
+    std::vector<float> wkv(static_cast<size_t>(Lf) * 2 * d * d), bkv(static_cast<size_t>(Lf) * 2 * d);
+    for (int l = 0; l < Lf; ++l) {
+      const std::string p = "fusion.layers." + std::to_string(l);
+      const std::string t = "f" + std::to_string(l);
+      GETW(win, p + ".cross_attn.in_proj_weight", 3 * d, d);
+      GETW(bin, p + ".cross_attn.in_proj_bias", 3 * d);
+      GETW(wo, p + ".cross_attn.out_proj.weight", d, d);
+      GETW(bo, p + ".cross_attn.out_proj.bias", d);
+      GETW(w1, p + ".ff.0.weight", 4 * d, d);
+      GETW(b1, p + ".ff.0.bias", 4 * d);
+      GETW(w2, p + ".ff.3.weight", d, 4 * d);
+      GETW(b2, p + ".ff.3.bias", d);
+      GETW(n1g, p + ".norm1.weight", d);
+      GETW(n1b, p + ".norm1.bias", d);
+      GETW(n2g, p + ".norm2.weight", d);
+      GETW(n2b, p + ".norm2.bias", d);
+      off[t + "wq"] = ar.add_op(win->data.data(), static_cast<size_t>(d) * d, tf32);
+      off[t + "bq"] = ar.add_f32(bin->data.data(), d);
+      memcpy(wkv.data() + static_cast<size_t>(l) * 2 * d * d, win->data.data() + d * d, sizeof(float) * 2 * d * d);
+      memcpy(bkv.data() + static_cast<size_t>(l) * 2 * d, bin->data.data() + d, sizeof(float) * 2 * d);
+      off[t + "wo"] = ar.add_op(wo->data.data(), wo->data.size(), tf32);
+      off[t + "w1"] = ar.add_op(w1->data.data(), w1->data.size(), tf32);
+      off[t + "w2"] = ar.add_op(w2->data.data(), w2->data.size(), tf32);
+      off[t + "bo"] = ar.add_f32(bo->data.data(), d);
+      off[t + "b1"] = ar.add_f32(b1->data.data(), 4 * d);
+      off[t + "b2"] = ar.add_f32(b2->data.data(), d);
+      off[t + "n1g"] = ar.add_f32(n1g->data.data(), d);
+      off[t + "n1b"] = ar.add_f32(n1b->data.data(), d);
+      off[t + "n2g"] = ar.add_f32(n2g->data.data(), d);
+      off[t + "n2b"] = ar.add_f32(n2b->data.data(), d);
+    }
+    off["wkv"] = ar.add_op(wkv.data(), wkv.size(), tf32);
+    off["bkv"] = ar.add_f32(bkv.data(), bkv.size());
+    GETW(fg, "fusion.norm.weight", d);
+    GETW(fb, "fusion.norm.bias", d);
+    off["fng"] = ar.add_f32(fg->data.data(), d);
+    off["fnb"] = ar.add_f32(fb->data.data(), d);
+  }
+  // --- decoder
+  {
+    GETW(w0, "decoder.decoder.0.weight", 2 * d, d);
+    GETW(b0, "decoder.decoder.0.bias", 2 * d);
+    GETW(w3, "decoder.decoder.3.weight", S * F, 2 * d);
+    GETW(b3, "decoder.decoder.3.bias", S * F);
+    off["wdec0"] = ar.add_op(w0->data.data(), w0->data.size(), tf32);
+    off["wdec3"] = ar.add_op(w3->data.data(), w3->data.size(), tf32);
+    off["bdec0"] = ar.add_f32(b0->data.data(), 2 * d);
+    off["bdec3"] = ar.add_f32(b3->data.data(), S * F);
+  }
+#undef GETW
+  // upload
+  if (h->d_weights) cudaFree(h->d_weights);
+  h->d_weights = nullptr;
+  CUDA_OK(cudaMalloc(&h->d_weights, ar.bytes.size()));
+  h->weight_bytes = ar.bytes.size();
+  CUDA_OK(cudaMemcpyAsync(h->d_weights, ar.bytes.data(), ar.bytes.size(), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  auto P = [&](const std::string& k) -> const void* { return h->d_weights + off.at(k); };
+  auto PF = [&](const std::string& k) -> const float* { return reinterpret_cast<const float*>(h->d_weights + off.at(k)); };
+  h->wc1 = P("wc1"); h->wc2 = P("wc2"); h->bc1 = PF("bc1"); h->bc2 = PF("bc2");
+  h->pe_a = PF("pe_a"); h->pe_v = PF("pe_v");
+  h->wproj = P("wproj"); h->bproj = PF("bproj");
+  h->wkv_all = P("wkv"); h->bkv_all = PF("bkv"); h->fng = PF("fng"); h->fnb = PF("fnb");
+  h->wdec0 = P("wdec0"); h->wdec3 = P("wdec3"); h->bdec0 = PF("bdec0"); h->bdec3 = PF("bdec3");
+  h->cnn.w1 = reinterpret_cast<const uint32_t*>(P("cw1")); h->cnn.b1 = PF("cb1");
+  h->cnn.w2 = reinterpret_cast<const uint32_t*>(P("cw2")); h->cnn.b2 = PF("cb2");
+  h->cnn.w3 = reinterpret_cast<const uint32_t*>(P("cw3")); h->cnn.b3 = PF("cb3");
+  h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();
+  for (int stack = 0; stack < 2; ++stack)
+    for (int l = 0; l < Le; ++l) {
+      const std::string t = (stack == 0 ? "a" : "v") + std::to_string(l);
+      EncLayerW w;
+      w.wqkv = P(t + "wqkv"); w.wo = P(t + "wo"); w.w1 = P(t + "w1"); w.w2 = P(t + "w2");
+      w.bqkv = PF(t + "bqkv"); w.bo = PF(t + "bo"); w.b1 = PF(t + "b1"); w.b2 = PF(t + "b2");
+      w.n1g = PF(t + "n1g"); w.n1b = PF(t + "n1b"); w.n2g = PF(t + "n2g"); w.n2b = PF(t + "n2b");
+      (stack == 0 ? h->enc_a : h->enc_v).push_back(w);
+    }
+  for (int l = 0; l < Lf; ++l) {
+    const std::string t = "f" + std::to_string(l);
+    FusLayerW w;
+    w.wq = P(t + "wq"); w.wo = P(t + "wo"); w.w1 = P(t + "w1"); w.w2 = P(t + "w2");
+    w.bq = PF(t + "bq"); w.bo = PF(t + "bo"); w.b1 = PF(t + "b1"); w.b2 = PF(t + "b2");
+    w.n1g = PF(t + "n1g"); w.n1b = PF(t + "n1b"); w.n2g = PF(t + "n2g"); w.n2b = PF(t + "n2b");
+    h->fus.push_back(w);
+  }
+  h->finalized = true;
+  return 0;
+}
+
+size_t avsep_workspace_bytes(avsep_handle* h, int32_t B, int32_t T, int32_t N, int32_t Hh, int32_t Ww) {
+  if (!h || B < 1 || T < 1 || N < 1) return 0;
+  Workspace w;
+  return carve_workspace(h, w, nullptr, B, T, N, Hh, Ww);
+}
+
+int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T, int32_t N,
+                  int32_t Hh, int32_t Ww, float* separated, float* masks, void* workspace, size_t workspace_bytes,
+                  void* cuda_stream) {
+  if (!h) return 1;
+  if (!mixed_spec || !lip_frames || !separated || !masks) return fail(h, "avsep_forward: null buffer");
+  if (check_shape(h, B, T, N, Hh, Ww)) return 1;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  Workspace w;
+  if (get_workspace(h, w, workspace, workspace_bytes, B, T, N, Hh, Ww)) return 1;
+  h->launches = 0;
+  return forward_device(h, static_cast<cudaStream_t>(cuda_stream), w, mixed_spec, lip_frames, separated, masks);
+}
+
+int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
+                       int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream) {
+  if (!h) return 1;
+  if (!mixed_spec || !lip_frames || !separated || !masks) return fail(h, "avsep_forward_host: null buffer");
+  if (check_shape(h, B, T, N, Hh, Ww)) return 1;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t n_mixed = static_cast<size_t>(B) * h->cfg.freq_bins * T;
+  const size_t n_frames = static_cast<size_t>(B) * N * Hh * Ww;
+  const size_t n_out = static_cast<size_t>(B) * h->cfg.num_speakers * h->cfg.freq_bins * T;
+  float** bufs[4] = {&h->io_mixed, &h->io_frames, &h->io_sep, &h->io_masks};
+  const size_t need[4] = {n_mixed, n_frames, n_out, n_out};
+  for (int i = 0; i < 4; ++i) {
+    if (h->io_cap[i] < need[i]) {
+      if (*bufs[i]) cudaFree(*bufs[i]);
+      *bufs[i] = nullptr;
+      h->io_cap[i] = 0;
+      CUDA_OK(cudaMalloc(bufs[i], need[i] * sizeof(float)));
+      h->io_cap[i] = need[i];
+    }
+  }
+  Workspace w;
+  if (get_workspace(h, w, nullptr, 0, B, T, N, Hh, Ww)) return 1;
+  CUDA_OK(cudaMemcpyAsync(h->io_mixed, mixed_spec, n_mixed * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(h->io_frames, lip_frames, n_frames * 4, cudaMemcpyHostToDevice, s));
+  h->launches = 0;
+  if (forward_device(h, s, w, h->io_mixed, h->io_frames, h->io_sep, h->io_masks)) return 1;
+  CUDA_OK(cudaMemcpyAsync(separated, h->io_sep, n_out * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(masks, h->io_masks, n_out * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int64_t avsep_last_launch_count(const avsep_handle* h) { return h ? h->launches : 0; }
+
+// ---- sub-module forwards ------------------------------------------------------------------------
+int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int32_t T, float* out_BTd,
+                        void* cuda_stream) {
+  if (!h) return 1;
+  if (!mixed_spec || !out_BTd) return fail(h, "avsep_audio_encoder: null buffer");
+  if (check_shape(h, B, T, 1, 1, 1)) return 1;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  Workspace w;
+  if (get_workspace(h, w, nullptr, 0, B, T, 1, 1, 1)) return 1;
+  const int d = h->cfg.d_model, Ma = B * T, prec = h->cfg.precision;
+  h->launches = 0;
+  if (audio_frontend(h, s, w, mixed_spec)) return 1;
+  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  if (encoder_stack(h, s, h->enc_a, B, T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, nullptr, nullptr)) return 1;
+  CUDA_OK(cudaMemcpyAsync(out_BTd, w.x_a, static_cast<size_t>(Ma) * d * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int avsep_visual_encoder(avsep_handle* h, const float* lip_frames, int32_t B, int32_t N, int32_t Hh, int32_t Ww,
+                         int32_t target_len, float* out_BTd, void* cuda_stream) {
+  if (!h) return 1;
+  if (!lip_frames || !out_BTd) return fail(h, "avsep_visual_encoder: null buffer");
+  if (check_shape(h, B, 1, N, Hh, Ww)) return 1;
+  if (target_len < 1) return fail(h, "avsep_visual_encoder: target_len must be >= 1");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  Workspace w;
+  if (get_workspace(h, w, nullptr, 0, B, 1, N, Hh, Ww)) return 1;
+  const int d = h->cfg.d_model, Mv = B * N, prec = h->cfg.precision;
+  h->launches = 0;
+  if (visual_frontend(h, s, w, lip_frames)) return 1;
+  CK(launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  if (encoder_stack(h, s, h->enc_v, B, N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) return 1;
+  interp_rows_kernel<<<dim3(target_len, B), 128, 0, s>>>(w.x_v, out_BTd, N, target_len, d,
+                                                         static_cast<float>(N) / static_cast<float>(target_len));
+  CUDA_OK(cudaGetLastError());
+  ++h->launches;
+  return 0;
+}
+
+int avsep_fusion(avsep_handle* h, const float* audio_BTd, const float* visual_BLd, int32_t B, int32_t T, int32_t L,
+                 float* out_BTd, void* cuda_stream) {
+  if (!h) return 1;
+  if (!audio_BTd || !visual_BLd || !out_BTd) return fail(h, "avsep_fusion: null buffer");
+  if (check_shape(h, B, T, L, 1, 1)) return 1;
+  if (L != T) return fail(h, "avsep_fusion: audio and visual must have the same length (model.py:131-133)");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  Workspace w;
+  if (get_workspace(h, w, nullptr, 0, B, T, L, 1, 1)) return 1;
+  const int d = h->cfg.d_model, Ma = B * T, Mv = B * L, prec = h->cfg.precision;
+  h->launches = 0;
+  CUDA_OK(cudaMemcpyAsync(w.x_a, audio_BTd, static_cast<size_t>(Ma) * d * 4, cudaMemcpyDeviceToDevice, s));
+  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->fus[0].n1g, h->fus[0].n1b, nullptr, w.a_op, Ma, d));
+  CK(launch_add_layernorm(s, prec, visual_BLd, nullptr, nullptr, nullptr, nullptr, w.v_op, Mv, d));   // cast only
+  const bool dbg = h->debug;
+  h->debug = false;
+  const int rc = fusion_stack(h, s, w, L);   // identity interpolation (L == T)
+  h->debug = dbg;
+  if (rc) return 1;
+  // fused rows in fp32: recompute the final LayerNorm from the fp32 residual stream straight into the caller's buffer
+  const int save_prec = h->cfg.precision;
+  CK(launch_add_layernorm(s, PREC_TF32, w.x_a, nullptr, h->fng, h->fnb, nullptr, out_BTd, Ma, d));
+  (void)save_prec;
+  return 0;
+}
+
+int avsep_decoder(avsep_handle* h, const float* fused_BTd, const float* mixed_spec, int32_t B, int32_t T,
+                  float* separated, float* masks, void* cuda_stream) {
+  if (!h) return 1;
+  if (!fused_BTd || !mixed_spec || !separated || !masks) return fail(h, "avsep_decoder: null buffer");
+  if (check_shape(h, B, T, 1, 1, 1)) return 1;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  Workspace w;
+  if (get_workspace(h, w, nullptr, 0, B, T, 1, 1, 1)) return 1;
+  const int d = h->cfg.d_model, Ma = B * T;
+  h->launches = 0;
+  CK(launch_add_layernorm(s, h->cfg.precision, fused_BTd, nullptr, nullptr, nullptr, nullptr, w.a_op, Ma, d));
+  return decoder_stage(h, s, w, mixed_spec, separated, masks);
+}
+
+// ---- debug ---------------------------------------------------------------------------------------
+int avsep_set_debug(avsep_handle* h, int32_t enable) {
+  if (!h) return 1;
+  h->debug = enable != 0;
+  return 0;
+}
+
+int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, size_t capacity, size_t* count) {
+  if (!h || !name || !count) return fail(h, "avsep_debug_get_stage: bad argument");
+  auto it = h->snaps.find(name);
+  if (it == h->snaps.end()) return fail(h, std::string("no snapshot named ") + name);
+  *count = it->second.second;
+  if (host_out == nullptr) return 0;
+  if (capacity < it->second.second) return fail(h, "avsep_debug_get_stage: buffer too small");
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(host_out, it->second.first, it->second.second * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- kernel-level test hooks -----------------------------------------------------------------------
+int avsep_test_gemm(avsep_handle* h, const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,
+                    int32_t K, int32_t act, int32_t force_bn, void* cuda_stream) {
+  if (!h) return 1;
+  GemmProblem p{};
+  p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K; p.taps = 1;
+  GemmEpilogue e;
+  e.bias = bias; e.act = act; e.out_f32 = out; e.ld_f32 = N;
+  CK(launch_gemm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, p, e, force_bn));
+  return 0;
+}
+
+int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
+                      int32_t L, int32_t N, int32_t K, void* cuda_stream) {
+  if (!h) return 1;
+  GemmProblem p{};
+  const int Mp = B * (L + 2);
+  p.A = A_padded; p.lda = K; p.rowsA = Mp; p.M = Mp; p.W = W3; p.ldw = 3 * K; p.N = N; p.K = K;
+  p.taps = 3; p.tap_stride = K; p.row_shift = -1;
+  GemmEpilogue e;
+  e.bias = bias; e.rowmap = ROW_PAD2COMPACT; e.Lp = L + 2; e.out_f32 = out; e.ld_f32 = N;
+  CK(launch_gemm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, p, e));
+  return 0;
+}
+
+int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
+                         int32_t hd, int32_t Lq, int32_t Lk, int32_t lerp_src, void* cuda_stream) {
+  if (!h) return 1;
+  AttnProblem ap{};
+  ap.q = q; ap.ldq = H * hd; ap.k = k; ap.v = v; ap.ldkv = H * hd; ap.out = out; ap.ldo = H * hd;
+  ap.B = B; ap.H = H; ap.hd = hd; ap.Lq = Lq; ap.Lk = Lk; ap.lerp_src = lerp_src;
+  CK(launch_attention(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, ap));
+  return 0;
+}
+
+int avsep_test_add_layernorm(avsep_handle* h, const float* x, const float* y, const float* gamma, const float* beta,
+                             float* x_out, void* out_op, int32_t M, int32_t d, void* cuda_stream) {
+  if (!h) return 1;
+  CK(launch_add_layernorm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, x, y, gamma, beta, x_out, out_op, M, d));
+  return 0;
+}
+
+int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_t M, int32_t Hh, int32_t Ww, void* pooled,
+                          void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "weights not finalized");
+  CK(launch_visual_cnn(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, frames, M, Hh, Ww, h->cnn, pooled,
+                       h->num_sms));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Internal (C++) interface between the C-ABI layer (avsep_api.cu) and the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace avsep {
+
+enum Precision { PREC_BF16 = 0, PREC_TF32 = 1 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+// How accumulator row m of the GEMM maps to an output row.
+//   ROW_IDENT       out row = m
+//   ROW_PAD2PAD     rows live in a per-utterance padded space of Lp = L+2 rows (zero halo row on each side,
+//                   the Conv1d zero padding); out row = m, halo rows are written as zeros
+//   ROW_PAD2COMPACT padded space in, compact (B*L) rows out; halo rows are dropped
+enum RowMap { ROW_IDENT = 0, ROW_PAD2PAD = 1, ROW_PAD2COMPACT = 2 };
+enum EpiKind { EPI_STD = 0, EPI_TAIL = 1 };
+
+struct GemmProblem {
+  const void* A;   // [rowsA, K] K-major activations (bf16 or fp32/tf32), leading dimension lda (elements)
+  int lda;
+  int rowsA;       // rows that exist in A (TMA zero-fills outside)
+  int M;           // accumulator rows to produce
+  const void* W;   // [N, taps*tap_stride] K-major weights, leading dimension ldw
+  int ldw;
+  int N;
+  int K;           // reduction length per tap
+  int taps;        // 1 = plain GEMM, 3 = Conv1d(k=3) as three row-shifted passes into the same accumulator
+  int tap_stride;  // column offset between taps in W
+  int row_shift;   // A row offset of tap 0 relative to the accumulator row (-1 for padding=1)
+};
+
+struct GemmEpilogue {
+  int kind = EPI_STD;
+  const float* bias = nullptr;   // [N]
+  int act = ACT_NONE;
+  int rowmap = ROW_IDENT;
+  int Lp = 0;                    // padded rows per utterance for the PAD modes
+  const float* pe = nullptr;     // positional table [max_len, N] added after the activation
+  int pe_period = 0;             // ROW_IDENT: position = m % pe_period
+  float* out_f32 = nullptr;      // fp32 output (residual-stream precision), leading dimension ld_f32
+  int ld_f32 = 0;
+  void* out_op = nullptr;        // operand-precision output (bf16, or fp32 in the tf32 path) for the next GEMM
+  int ld_op = 0;
+  // EPI_TAIL (SeparationDecoder head): masks = sigmoid(acc + bias) -> masks[b,s,f,t]; separated = masks * mixed[b,f,t]
+  const float* mixed = nullptr;
+  float* masks = nullptr;
+  float* separated = nullptr;
+  int F = 0, S = 0, T = 0;
+};
+
+// Returns nullptr on success or a static error string.
+const char* gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn = 0);
+
+// x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
+// out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).
+const char* launch_add_layernorm(cudaStream_t s, int prec, const float* x, const float* y, const float* gamma,
+                                 const float* beta, float* x_out, void* out_op, int M, int d);
+
+// mixed (B,F,T) fp32 -> Xp (B, T+2, Fp) operand precision, zero halo rows and zero pad columns.
+const char* launch_prep_audio(cudaStream_t s, int prec, const float* mixed, void* xp, int B, int F, int T, int Fp);
+
+struct AttnProblem {
+  const void* q; int ldq;          // operand-precision rows [B*Lq, ldq], head h at columns h*hd
+  const void* k; const void* v;    // self: operand precision rows [B*Lk, ldkv]; cross (lerp): fp32 rows [B*Nsrc, ldkv]
+  int ldkv;
+  void* out; int ldo;              // operand precision [B*Lq, ldo]
+  int B, H, hd, Lq, Lk;
+  int lerp_src;                    // 0 = plain; >0 = K/V hold lerp_src source rows per utterance, interpolated to Lk rows
+};
+const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p);
+
+struct CnnWeights {                // BN-folded, fragment-ordered (see visual_cnn.cu)
+  const uint32_t* w1; const float* b1;
+  const uint32_t* w2; const float* b2;
+  const uint32_t* w3; const float* b3;
+};
+// frames (M,H,W) fp32 -> pooled (M,128) operand precision
+const char* launch_visual_cnn(cudaStream_t s, int prec, const float* frames, int M, int H, int W, const CnnWeights& w,
+                              void* pooled, int num_sms);
+size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint32)
+void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3);
+
+}  // namespace avsep

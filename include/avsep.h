@@ -1,0 +1,125 @@
+/*
+ * avsep.h - C ABI of the B200-native AVSeparationTransformer forward path (libavsep.so).
+ *
+ * The reference (danieleschmidt/AV-Separation-Transformer) is pure Python on PyTorch and has no
+ * FFI / operator / plugin layer of its own: its drop-in boundary for this path is the nn.Module
+ *     AVSeparationTransformer.__init__(freq_bins, d_model, nhead, num_encoder_layers,
+ *                                      num_fusion_layers, num_speakers, dropout)      model.py:240-249
+ *     AVSeparationTransformer.forward(mixed_spec, lip_frames) -> (separated, masks)    model.py:268-276
+ * plus its state_dict key set.  The entry points below are what a ctypes/pybind
+ * binding of that module binds instead of torch.nn: plain pointers and sizes, no torch types.
+ * INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; avsep_last_error(h) gives the message.
+ *     No C++ exception crosses this boundary.
+ *   - a handle is bound to one CUDA device; calls are stream-ordered on the caller's stream and never
+ *     synchronise internally (except avsep_forward_host and the *_debug / *_test helpers).
+ *   - device buffers are owned by the caller; the library owns only the prepacked weights and, when the
+ *     caller passes workspace == NULL, a cached workspace per shape.
+ *   - eval-mode semantics only (dropout = identity, BatchNorm running statistics): model.py:159,164,197,288.
+ */
+#ifndef AVSEP_H_
+#define AVSEP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AVSEP_API __attribute__((visibility("default")))
+#else
+#define AVSEP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct avsep_handle avsep_handle;
+
+enum { AVSEP_PREC_BF16 = 0, AVSEP_PREC_TF32 = 1 };
+enum { AVSEP_DTYPE_F32 = 0, AVSEP_DTYPE_I64 = 1 };
+
+/* Constructor arguments of the reference module (model.py:240-249) + execution options. */
+typedef struct avsep_config {
+  int32_t freq_bins;
+  int32_t d_model;
+  int32_t nhead;
+  int32_t num_encoder_layers;
+  int32_t num_fusion_layers;
+  int32_t num_speakers;
+  int32_t precision; /* AVSEP_PREC_*: operand precision of the tensor-core contractions */
+  int32_t device;    /* CUDA device ordinal */
+} avsep_config;
+
+/* Replaces AVSeparationTransformer.__init__ (model.py:240-266). */
+AVSEP_API int avsep_create(const avsep_config* cfg, avsep_handle** out);
+AVSEP_API void avsep_destroy(avsep_handle* h);
+AVSEP_API const char* avsep_last_error(const avsep_handle* h); /* h may be NULL: error of the last failed create */
+
+/* Replaces nn.Module.load_state_dict: one call per state_dict entry, reference key names
+ * (e.g. "audio_encoder.input_proj.0.weight"), HOST pointer, fp32 (or int64 for
+ * num_batches_tracked, which is accepted and ignored).  Data is copied. */
+AVSEP_API int avsep_set_weight(avsep_handle* h, const char* key, const void* host_data, int32_t dtype, const int64_t* shape,
+                     int32_t ndim);
+/* BN fold, Conv1d tap repack, operand-precision cast, upload.  Fails if a key is missing or mis-shaped. */
+AVSEP_API int avsep_finalize_weights(avsep_handle* h, void* cuda_stream);
+
+/* Scratch bytes avsep_forward needs for this shape (0 on error). */
+AVSEP_API size_t avsep_workspace_bytes(avsep_handle* h, int32_t B, int32_t T, int32_t N, int32_t Hh, int32_t Ww);
+
+/* Replaces AVSeparationTransformer.forward (model.py:268-276).  DEVICE pointers:
+ *   mixed_spec (B,F,T) fp32, lip_frames (B,N,Hh,Ww) fp32 -> separated, masks (B,S,F,T) fp32 contiguous.
+ * workspace may be NULL (library-owned, cached per shape). */
+AVSEP_API int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T, int32_t N,
+                  int32_t Hh, int32_t Ww, float* separated, float* masks, void* workspace, size_t workspace_bytes,
+                  void* cuda_stream);
+
+/* Same call with HOST buffers (pinned memory recommended): H2D copies, forward and D2H copies are issued on
+ * the stream and the call returns after the results have landed (the e2e path of bench.py). */
+AVSEP_API int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
+                       int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream);
+
+/* Number of kernels the last avsep_forward on this handle launched. */
+AVSEP_API int64_t avsep_last_launch_count(const avsep_handle* h);
+
+/* Sub-module forwards (reference: AudioEncoder.forward model.py:54-60, VisualEncoder.forward model.py:103-117,
+ * CrossModalFusion.forward model.py:145-149, SeparationDecoder.forward/.separate model.py:201-220).
+ * DEVICE pointers, fp32, contiguous. */
+AVSEP_API int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int32_t T, float* out_BTd,
+                        void* cuda_stream);
+AVSEP_API int avsep_visual_encoder(avsep_handle* h, const float* lip_frames, int32_t B, int32_t N, int32_t Hh, int32_t Ww,
+                         int32_t target_len, float* out_BTd, void* cuda_stream);
+AVSEP_API int avsep_fusion(avsep_handle* h, const float* audio_BTd, const float* visual_BLd, int32_t B, int32_t T, int32_t L,
+                 float* out_BTd, void* cuda_stream);
+AVSEP_API int avsep_decoder(avsep_handle* h, const float* fused_BTd, const float* mixed_spec, int32_t B, int32_t T,
+                  float* separated, float* masks, void* cuda_stream);
+
+/* Debug: when enabled, avsep_forward keeps fp32 snapshots of intermediate stages
+ * ("audio_embed", "audio_enc", "visual_pool", "visual_embed", "visual_enc", "fused"). */
+AVSEP_API int avsep_set_debug(avsep_handle* h, int32_t enable);
+/* Copies a snapshot to a HOST buffer of `capacity` floats; returns the element count in *count. Synchronises. */
+AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, size_t capacity, size_t* count);
+
+/* Kernel-level test hooks (DEVICE pointers; used by tests/ to check each kernel against a torch fp32 reference).
+ *   gemm: out[M,N] = act(A[M,K] @ W[N,K]^T + bias), A/W in operand precision (bf16 or fp32), out fp32.
+ *   conv1d: taps=3 implicit GEMM over a zero-haloed activation: A [B*(L+2), K], W [N, 3*K] (k = tap*K + c),
+ *           out fp32 [B*L, N] (ROW_PAD2COMPACT).
+ *   attention: q [B*Lq, H*hd], k/v [B*Lk, H*hd] bf16 (lerp_src = 0) or fp32 [B*lerp_src, H*hd] (lerp on load).
+ *   add_layernorm: x_out = x + y, out = LN(x_out) in operand precision.
+ *   visual_cnn: frames (M,Hh,Ww) -> pooled (M,128) operand precision, using the handle's conv weights. */
+AVSEP_API int avsep_test_gemm(avsep_handle* h, const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,
+                    int32_t K, int32_t act, int32_t force_bn, void* cuda_stream);
+AVSEP_API int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
+                      int32_t L, int32_t N, int32_t K, void* cuda_stream);
+AVSEP_API int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
+                         int32_t hd, int32_t Lq, int32_t Lk, int32_t lerp_src, void* cuda_stream);
+AVSEP_API int avsep_test_add_layernorm(avsep_handle* h, const float* x, const float* y, const float* gamma, const float* beta,
+                             float* x_out, void* out_op, int32_t M, int32_t d, void* cuda_stream);
+AVSEP_API int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_t M, int32_t Hh, int32_t Ww, void* pooled,
+                          void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSEP_H_ */
