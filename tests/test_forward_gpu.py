@@ -1,0 +1,146 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against (a) the committed golden vectors produced by
+the real reference, (b) the CPU oracle on the same seeded inputs, (c) size-independent properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avsep_oracle as onp
+from oracle import avsep_oracle_torch as otorch
+from oracle.weights import CONFIGS, make_inputs, make_state_dict
+from tests.helpers import (GOLDEN_CASES, STAGES, TOL, build_model, case_tensors, err_report, load_golden,
+                           subsample_stage)
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, mixed, frames):
+    sep, masks = model(torch.from_numpy(mixed).cuda(), torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    return sep.cpu().numpy(), masks.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_bf16_path_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    cfg, P, mixed, frames = case_tensors(meta)
+    model = build_model(cfg, P, "bf16")
+    model.prepack()
+    model.engine.set_debug(True)
+    sep, masks = _run(model, mixed, frames)
+    assert sep.shape == (meta["B"], cfg.num_speakers, cfg.freq_bins, meta["T"]) and masks.shape == sep.shape
+    sf, st = meta["stride_f"], meta["stride_t"]
+    rep = err_report(sep[:, :, ::sf, ::st], masks[:, :, ::sf, ::st], z["separated"], z["masks"], mixed[:, ::sf, ::st])
+    stage_err = {}
+    shapes = {"audio_embed": (meta["B"], meta["T"], cfg.d_model), "audio_enc": (meta["B"], meta["T"], cfg.d_model),
+              "visual_pool": (meta["B"], meta["N"], 128), "visual_embed": (meta["B"], meta["N"], cfg.d_model),
+              "visual_enc": (meta["B"], meta["N"], cfg.d_model), "fused": (meta["B"], meta["T"], cfg.d_model)}
+    for k in STAGES:
+        got = subsample_stage(model.engine.get_stage(k).reshape(shapes[k]))
+        ref = z["stage_" + k]
+        stage_err[k] = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    print(name, rep, stage_err)
+    assert masks.min() >= 0.0 and masks.max() <= 1.0
+    assert rep["masks"] < TOL["bf16"], (rep, stage_err)
+    assert rep["separated_scaled"] < TOL["bf16"], (rep, stage_err)
+    if meta["kind"] == "randn":
+        assert rep["separated_abs"] < TOL["bf16"] * max(1.0, float(np.abs(mixed).max())), rep
+    for k, v in stage_err.items():
+        assert v < 5e-2, (k, v)
+
+
+def test_against_live_oracle_other_seeds():
+    cfg = CONFIGS["tiny2"]
+    for seed in (21, 22):
+        P = make_state_dict(cfg, seed=seed, gain=2.0)
+        mixed, frames = make_inputs(cfg, 3, 40, 12, 16, 16, seed=seed, kind="randn")
+        model = build_model(cfg, P, "bf16")
+        sep, masks = _run(model, mixed, frames)
+        sep_ref, masks_ref = onp.forward(P, cfg, mixed, frames)
+        rep = err_report(sep, masks, sep_ref, masks_ref, mixed)
+        assert rep["masks"] < TOL["bf16"] and rep["separated_scaled"] < TOL["bf16"], rep
+
+
+def test_edge_shapes_batch1_short_sequences():
+    cfg = CONFIGS["tiny"]
+    P = make_state_dict(cfg, seed=31, gain=2.0)
+    model = build_model(cfg, P, "bf16")
+    for (B, T, N, Hh, Ww) in ((1, 1, 1, 8, 8), (1, 3, 2, 5, 7), (2, 130, 3, 16, 16), (1, 16, 64, 16, 16)):
+        mixed, frames = make_inputs(cfg, B, T, N, Hh, Ww, seed=T, kind="randn")
+        sep, masks = _run(model, mixed, frames)
+        sep_ref, masks_ref = onp.forward(P, cfg, mixed, frames)
+        rep = err_report(sep, masks, sep_ref, masks_ref, mixed)
+        assert rep["masks"] < TOL["bf16"] and rep["separated_scaled"] < TOL["bf16"], ((B, T, N, Hh, Ww), rep)
+
+
+def test_full_size_properties_and_batch_independence():
+    """BASELINE.json configs[1] (B=256, default model): no op mixes utterances, so a shard of the batch must give
+    bit-identical rows; separated == masks * mixed exactly; masks in [0,1]; spot-check rows against the CPU port."""
+    cfg = CONFIGS["default"]
+    P = make_state_dict(cfg, seed=41, gain=2.0)
+    B, T, N = 256, 63, 50
+    mixed, frames = make_inputs(cfg, B, T, N, 32, 32, seed=41, kind="dataset")
+    model = build_model(cfg, P, "bf16")
+    sep, masks = _run(model, mixed, frames)
+    assert np.isfinite(sep).all() and masks.min() >= 0.0 and masks.max() <= 1.0
+    assert np.array_equal(sep, masks * mixed[:, None])
+    sub = slice(100, 132)
+    sep_s, masks_s = _run(model, mixed[sub], frames[sub])
+    assert np.array_equal(masks_s, masks[sub]) and np.array_equal(sep_s, sep[sub])
+    idx = [0, 127, 255]
+    sep_ref, masks_ref = otorch.forward(otorch.to_torch(P), cfg, torch.from_numpy(mixed[idx]), torch.from_numpy(frames[idx]))
+    rep = err_report(sep[idx], masks[idx], sep_ref.numpy(), masks_ref.numpy(), mixed[idx])
+    assert rep["masks"] < TOL["bf16"] and rep["separated_scaled"] < TOL["bf16"], rep
+
+
+def test_host_buffer_entry_point_matches_device_entry_point():
+    cfg = CONFIGS["tiny2"]
+    P = make_state_dict(cfg, seed=51, gain=2.0)
+    mixed, frames = make_inputs(cfg, 4, 32, 10, 16, 16, seed=51, kind="randn")
+    model = build_model(cfg, P, "bf16")
+    sep_d, masks_d = _run(model, mixed, frames)
+    sep_h, masks_h = model(torch.from_numpy(mixed).pin_memory(), torch.from_numpy(frames).pin_memory())
+    assert not sep_h.is_cuda
+    assert np.array_equal(sep_h.numpy(), sep_d) and np.array_equal(masks_h.numpy(), masks_d)
+
+
+def test_submodule_dropins_match_oracle():
+    """Reference tests drive the sub-modules directly (tests/test_model.py:77-179), incl. F=65, hd=16, N=10 -> T=50/20."""
+    from avsep_b200 import AudioEncoder, CrossModalFusion, SeparationDecoder, VisualEncoder
+    cfg = CONFIGS["tiny"]
+    P = make_state_dict(cfg, seed=61, gain=2.0)
+    mixed, frames = make_inputs(cfg, 2, 32, 10, 16, 16, seed=61, kind="randn")
+    tt = lambda pre: {k[len(pre):]: torch.from_numpy(np.asarray(v)) for k, v in P.items() if k.startswith(pre)}
+    ae = AudioEncoder(cfg.freq_bins, cfg.d_model, cfg.nhead, cfg.num_encoder_layers)
+    ae.load_state_dict(tt("audio_encoder."))
+    a = ae.cuda()(torch.from_numpy(mixed).cuda()).cpu().numpy()
+    a_ref = onp.audio_encoder(P, cfg, mixed)
+    assert a.shape == (2, 32, cfg.d_model) and np.abs(a - a_ref).max() < 5e-2 * max(1, np.abs(a_ref).max())
+    ve = VisualEncoder(cfg.d_model, cfg.nhead, cfg.num_encoder_layers)
+    ve.load_state_dict(tt("visual_encoder."))
+    ve = ve.cuda()
+    for target in (20, 32, 50):
+        v = ve(torch.from_numpy(frames).cuda(), target_len=target).cpu().numpy()
+        v_ref = onp.visual_encoder(P, cfg, frames, target)
+        assert v.shape == (2, target, cfg.d_model) and np.abs(v - v_ref).max() < 5e-2 * max(1, np.abs(v_ref).max())
+    fu = CrossModalFusion(cfg.d_model, cfg.nhead, cfg.num_fusion_layers)
+    fu.load_state_dict(tt("fusion."))
+    v32 = onp.visual_encoder(P, cfg, frames, 32)
+    f = fu.cuda()(torch.from_numpy(a_ref).cuda(), torch.from_numpy(v32).cuda()).cpu().numpy()
+    f_ref = onp.fusion(P, cfg, a_ref, v32)
+    assert np.abs(f - f_ref).max() < 5e-2 * max(1, np.abs(f_ref).max())
+    de = SeparationDecoder(cfg.d_model, cfg.freq_bins, cfg.num_speakers)
+    de.load_state_dict(tt("decoder."))
+    m = de.cuda()(torch.from_numpy(f_ref).cuda()).cpu().numpy()
+    m_ref = onp.decoder_masks(P, cfg, f_ref)
+    assert m.shape == (2, 2, cfg.freq_bins, 32) and np.abs(m - m_ref).max() < TOL["bf16"]
+    assert m.min() >= 0 and m.max() <= 1
+
+
+def test_errors_are_loud():
+    cfg = CONFIGS["tiny"]
+    P = make_state_dict(cfg, seed=1)
+    model = build_model(cfg, P, "bf16")
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 64, 8, device="cuda"), torch.zeros(1, 4, 16, 16, device="cuda"))   # wrong freq_bins
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 65, 5001, device="cuda"), torch.zeros(1, 4, 16, 16, device="cuda"))  # > PE table
