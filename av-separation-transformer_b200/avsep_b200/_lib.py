@@ -43,6 +43,8 @@ SIGNATURES = {
     "avsep_decoder": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "avsep_set_debug": (C.c_int, [_P, _I]),
     "avsep_debug_get_stage": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "avsep_set_profile": (C.c_int, [_P, _I]),
+    "avsep_profile_report": (C.c_int, [_P, C.c_char_p, C.c_size_t, _I]),
     "avsep_test_gemm": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "avsep_test_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "avsep_test_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

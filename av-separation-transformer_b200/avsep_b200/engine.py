@@ -229,6 +229,20 @@ class Engine:
         self._check(rc, "avsep_decoder")
         return sep, masks
 
+    # ---- profiling -------------------------------------------------------------------------------
+    def set_profile(self, on: bool):
+        self._check(self.lib.avsep_set_profile(self.h, 1 if on else 0), "avsep_set_profile")
+
+    def profile_report(self, reset: bool = True) -> dict:
+        """label -> (launches, total_ms) accumulated since the last reset."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.avsep_profile_report(self.h, buf, len(buf), 1 if reset else 0), "avsep_profile_report")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            label, n, ms = line.split()
+            out[label] = (int(n), float(ms))
+        return out
+
     # ---- debug -------------------------------------------------------------------------------------
     def set_debug(self, on: bool):
         self._check(self.lib.avsep_set_debug(self.h, 1 if on else 0), "avsep_set_debug")

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <map>
@@ -98,6 +99,13 @@ struct avsep_handle {
   bool debug = false;
   std::map<std::string, std::pair<float*, size_t>> snaps;
   int64_t launches = 0;
+  // per-launch profiling (cudaEvent pairs on the launching stream)
+  bool profile = false;
+  cudaStream_t prof_stream = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<const char*, size_t>> ev_marks;   // label, index of the start event (stop = +1)
+  std::map<std::string, std::pair<int64_t, double>> prof;  // label -> (launches, total ms)
 };
 
 namespace {
@@ -107,12 +115,32 @@ int fail(avsep_handle* h, const std::string& msg) {
   return 1;
 }
 
-#define CK(expr)                                                        \
+int prof_begin(avsep_handle* h, const char* label) {
+  if (h->ev_used + 2 > h->ev_pool.size()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return 1;
+      h->ev_pool.push_back(e);
+    }
+  }
+  h->ev_marks.emplace_back(label, h->ev_used);
+  cudaEventRecord(h->ev_pool[h->ev_used], h->prof_stream);
+  return 0;
+}
+void prof_end(avsep_handle* h) {
+  cudaEventRecord(h->ev_pool[h->ev_used + 1], h->prof_stream);
+  h->ev_used += 2;
+}
+
+#define CKL(label, expr)                                                \
   do {                                                                  \
+    if (h->profile && prof_begin(h, label)) return fail(h, "profiling: cudaEventCreate failed"); \
     const char* _e = (expr);                                            \
     if (_e != nullptr) return fail(h, std::string(_e) + " [" #expr "]"); \
+    if (h->profile) prof_end(h);                                        \
     ++h->launches;                                                      \
   } while (0)
+#define CK(expr) CKL("other", expr)
 
 #define CUDA_OK(expr)                                                                           \
   do {                                                                                          \
@@ -203,8 +231,8 @@ int snapshot(avsep_handle* h, cudaStream_t s, const char* name, const void* ptr,
 }
 
 // ---- stage helpers -----------------------------------------------------------------------------
-int linear(avsep_handle* h, cudaStream_t s, const void* A, int M, int K, const void* W, const float* bias, int N, int act,
-           float* out_f32, void* out_op) {
+int linear(avsep_handle* h, cudaStream_t s, const char* label, const void* A, int M, int K, const void* W,
+           const float* bias, int N, int act, float* out_f32, void* out_op) {
   GemmProblem p{};
   p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K;
   p.taps = 1; p.tap_stride = 0; p.row_shift = 0;
@@ -212,7 +240,7 @@ int linear(avsep_handle* h, cudaStream_t s, const void* A, int M, int K, const v
   e.bias = bias; e.act = act;
   e.out_f32 = out_f32; e.ld_f32 = N;
   e.out_op = out_op; e.ld_op = N;
-  CK(launch_gemm(s, h->cfg.precision, p, e));
+  CKL(label, launch_gemm(s, h->cfg.precision, p, e));
   return 0;
 }
 
@@ -222,7 +250,7 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
   const size_t os = op_size(h);
   for (size_t l = 0; l < layers.size(); ++l) {
     const EncLayerW& w = layers[l];
-    if (linear(h, s, a_op, M, d, w.wqkv, w.bqkv, 3 * d, ACT_NONE, nullptr, qkv)) return 1;
+    if (linear(h, s, "gemm.qkv", a_op, M, d, w.wqkv, w.bqkv, 3 * d, ACT_NONE, nullptr, qkv)) return 1;
     AttnProblem ap{};
     ap.q = qkv; ap.ldq = 3 * d;
     ap.k = static_cast<const uint8_t*>(qkv) + static_cast<size_t>(d) * os;
@@ -230,24 +258,25 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     ap.ldkv = 3 * d;
     ap.out = attn; ap.ldo = d;
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = L; ap.Lk = L; ap.lerp_src = 0;
-    CK(launch_attention(s, prec, ap));
-    if (linear(h, s, attn, M, d, w.wo, w.bo, d, ACT_NONE, y, nullptr)) return 1;
-    CK(launch_add_layernorm(s, prec, x, y, w.n2g, w.n2b, x, a_op, M, d));
-    if (linear(h, s, a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
-    if (linear(h, s, ffn, M, 4 * d, w.w2, w.b2, d, ACT_NONE, y, nullptr)) return 1;
+    CKL("attn.self", launch_attention(s, prec, ap));
+    if (linear(h, s, "gemm.out_proj", attn, M, d, w.wo, w.bo, d, ACT_NONE, y, nullptr)) return 1;
+    CKL("add_layernorm", launch_add_layernorm(s, prec, x, y, w.n2g, w.n2b, x, a_op, M, d));
+    if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
+    if (linear(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, ACT_NONE, y, nullptr)) return 1;
     const bool last = (l + 1 == layers.size());
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
-    CK(launch_add_layernorm(s, prec, x, y, g, b, x, a_op, M, d));
+    CKL("add_layernorm", launch_add_layernorm(s, prec, x, y, g, b, x, a_op, M, d));
   }
   return 0;
 }
 
 // AudioEncoder up to (not including) the transformer: Conv1d+ReLU x2, +PE  (model.py:56-58)
 int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed) {
+  h->prof_stream = s;
   const int d = h->cfg.d_model, F = h->cfg.freq_bins, B = w.B, T = w.T, prec = h->cfg.precision;
   const int Map = B * (T + 2);
-  CK(launch_prep_audio(s, prec, mixed, w.xp, B, F, T, h->Fp));
+  CKL("prep_audio", launch_prep_audio(s, prec, mixed, w.xp, B, F, T, h->Fp));
   {
     GemmProblem p{};
     p.A = w.xp; p.lda = h->Fp; p.rowsA = Map; p.M = Map; p.W = h->wc1; p.ldw = 3 * h->Fp; p.N = d; p.K = h->Fp;
@@ -255,7 +284,7 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     GemmEpilogue e;
     e.bias = h->bc1; e.act = ACT_RELU; e.rowmap = ROW_PAD2PAD; e.Lp = T + 2;
     e.out_op = w.h1; e.ld_op = d;
-    CK(launch_gemm(s, prec, p, e));
+    CKL("gemm.conv1d_0", launch_gemm(s, prec, p, e));
   }
   {
     GemmProblem p{};
@@ -265,16 +294,17 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     e.bias = h->bc2; e.act = ACT_RELU; e.rowmap = ROW_PAD2COMPACT; e.Lp = T + 2;
     e.pe = h->pe_a;
     e.out_f32 = w.x_a; e.ld_f32 = d;
-    CK(launch_gemm(s, prec, p, e));
+    CKL("gemm.conv1d_2", launch_gemm(s, prec, p, e));
   }
   return snapshot(h, s, "audio_embed", w.x_a, static_cast<size_t>(B) * T * d, false);
 }
 
 // VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110)
 int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames) {
+  h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, N = w.N, prec = h->cfg.precision;
   const int Mv = B * N;
-  CK(launch_visual_cnn(s, prec, frames, Mv, w.Hh, w.Ww, h->cnn, w.pooled, h->num_sms));
+  CKL("visual_cnn", launch_visual_cnn(s, prec, frames, Mv, w.Hh, w.Ww, h->cnn, w.pooled, h->num_sms));
   if (snapshot(h, s, "visual_pool", w.pooled, static_cast<size_t>(Mv) * 128, true)) return 1;
   GemmProblem p{};
   p.A = w.pooled; p.lda = 128; p.rowsA = Mv; p.M = Mv; p.W = h->wproj; p.ldw = 128; p.N = d; p.K = 128;
@@ -282,20 +312,21 @@ int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* 
   GemmEpilogue e;
   e.bias = h->bproj; e.pe = h->pe_v; e.pe_period = N;
   e.out_f32 = w.x_v; e.ld_f32 = d;
-  CK(launch_gemm(s, prec, p, e));
+  CKL("gemm.frame_proj", launch_gemm(s, prec, p, e));
   return snapshot(h, s, "visual_embed", w.x_v, static_cast<size_t>(Mv) * d, false);
 }
 
 // CrossModalFusion (model.py:145-149,166-173).  In: x_a residual stream, a_op = LN_{layer0.norm1}(x_a),
 // v_op = visual rows (L_src per utterance).  Out: a_op = fusion.norm(x) in operand precision.
 int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
+  h->prof_stream = s;
   const int d = h->cfg.d_model, H = h->cfg.nhead, B = w.B, T = w.T, prec = h->cfg.precision;
   const int Ma = B * T, Mv = B * L_src, Lf = h->cfg.num_fusion_layers;
   // K/V projection of every fusion layer in one GEMM on the un-interpolated visual rows
-  if (linear(h, s, w.v_op, Mv, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, w.kvn, nullptr)) return 1;
+  if (linear(h, s, "gemm.cross_kv", w.v_op, Mv, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, w.kvn, nullptr)) return 1;
   for (int l = 0; l < Lf; ++l) {
     const FusLayerW& fw = h->fus[l];
-    if (linear(h, s, w.a_op, Ma, d, fw.wq, fw.bq, d, ACT_NONE, nullptr, w.qkv_a)) return 1;
+    if (linear(h, s, "gemm.cross_q", w.a_op, Ma, d, fw.wq, fw.bq, d, ACT_NONE, nullptr, w.qkv_a)) return 1;
     AttnProblem ap{};
     ap.q = w.qkv_a; ap.ldq = d;
     ap.k = w.kvn + static_cast<size_t>(l) * 2 * d;
@@ -303,24 +334,25 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     ap.ldkv = Lf * 2 * d;
     ap.out = w.attn_a; ap.ldo = d;
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = T; ap.Lk = T; ap.lerp_src = L_src;
-    CK(launch_attention(s, prec, ap));
-    if (linear(h, s, w.attn_a, Ma, d, fw.wo, fw.bo, d, ACT_NONE, w.y_a, nullptr)) return 1;
-    CK(launch_add_layernorm(s, prec, w.x_a, w.y_a, fw.n2g, fw.n2b, w.x_a, w.a_op, Ma, d));
-    if (linear(h, s, w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
-    if (linear(h, s, w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, ACT_NONE, w.y_a, nullptr)) return 1;
+    CKL("attn.cross", launch_attention(s, prec, ap));
+    if (linear(h, s, "gemm.out_proj", w.attn_a, Ma, d, fw.wo, fw.bo, d, ACT_NONE, w.y_a, nullptr)) return 1;
+    CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, w.y_a, fw.n2g, fw.n2b, w.x_a, w.a_op, Ma, d));
+    if (linear(h, s, "gemm.ffn1", w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
+    if (linear(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, ACT_NONE, w.y_a, nullptr)) return 1;
     const bool last = (l + 1 == Lf);
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
-    CK(launch_add_layernorm(s, prec, w.x_a, w.y_a, g, b, w.x_a, w.a_op, Ma, d));
+    CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, w.y_a, g, b, w.x_a, w.a_op, Ma, d));
   }
   return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
 }
 
 // SeparationDecoder.forward + .separate (model.py:201-220): a_op = fused rows in operand precision.
 int decoder_stage(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, float* separated, float* masks) {
+  h->prof_stream = s;
   const int d = h->cfg.d_model, F = h->cfg.freq_bins, S = h->cfg.num_speakers, B = w.B, T = w.T;
   const int Ma = B * T;
-  if (linear(h, s, w.a_op, Ma, d, h->wdec0, h->bdec0, 2 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
+  if (linear(h, s, "gemm.dec0", w.a_op, Ma, d, h->wdec0, h->bdec0, 2 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
   GemmProblem p{};
   p.A = w.ffn_a; p.lda = 2 * d; p.rowsA = Ma; p.M = Ma; p.W = h->wdec3; p.ldw = 2 * d; p.N = S * F; p.K = 2 * d;
   p.taps = 1;
@@ -328,7 +360,7 @@ int decoder_stage(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mi
   e.kind = EPI_TAIL;
   e.bias = h->bdec3;
   e.mixed = mixed; e.masks = masks; e.separated = separated; e.F = F; e.S = S; e.T = T;
-  CK(launch_gemm(s, h->cfg.precision, p, e));
+  CKL("gemm.dec3_tail", launch_gemm(s, h->cfg.precision, p, e));
   return 0;
 }
 
@@ -336,16 +368,17 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
                    float* separated, float* masks) {
   const int d = h->cfg.d_model, prec = h->cfg.precision;
   const int Ma = w.B * w.T, Mv = w.B * w.N;
+  h->prof_stream = s;
   // --- audio branch ---
   if (audio_frontend(h, s, w, mixed)) return 1;
-  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
   if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
                     h->fus[0].n1b))
     return 1;
   if (snapshot(h, s, "audio_enc", w.x_a, static_cast<size_t>(Ma) * d, false)) return 1;
   // --- visual branch ---
   if (visual_frontend(h, s, w, frames)) return 1;
-  CK(launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
   if (encoder_stack(h, s, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
     return 1;
   if (snapshot(h, s, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
@@ -435,6 +468,7 @@ void avsep_destroy(avsep_handle* h) {
   if (h->io_masks) cudaFree(h->io_masks);
   for (auto& kv : h->snaps)
     if (kv.second.first) cudaFree(kv.second.first);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -721,7 +755,7 @@ int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int
   const int d = h->cfg.d_model, Ma = B * T, prec = h->cfg.precision;
   h->launches = 0;
   if (audio_frontend(h, s, w, mixed_spec)) return 1;
-  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
   if (encoder_stack(h, s, h->enc_a, B, T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, nullptr, nullptr)) return 1;
   CUDA_OK(cudaMemcpyAsync(out_BTd, w.x_a, static_cast<size_t>(Ma) * d * 4, cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -740,7 +774,7 @@ int avsep_visual_encoder(avsep_handle* h, const float* lip_frames, int32_t B, in
   const int d = h->cfg.d_model, Mv = B * N, prec = h->cfg.precision;
   h->launches = 0;
   if (visual_frontend(h, s, w, lip_frames)) return 1;
-  CK(launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
   if (encoder_stack(h, s, h->enc_v, B, N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) return 1;
   interp_rows_kernel<<<dim3(target_len, B), 128, 0, s>>>(w.x_v, out_BTd, N, target_len, d,
                                                          static_cast<float>(N) / static_cast<float>(target_len));
@@ -762,8 +796,8 @@ int avsep_fusion(avsep_handle* h, const float* audio_BTd, const float* visual_BL
   const int d = h->cfg.d_model, Ma = B * T, Mv = B * L, prec = h->cfg.precision;
   h->launches = 0;
   CUDA_OK(cudaMemcpyAsync(w.x_a, audio_BTd, static_cast<size_t>(Ma) * d * 4, cudaMemcpyDeviceToDevice, s));
-  CK(launch_add_layernorm(s, prec, w.x_a, nullptr, h->fus[0].n1g, h->fus[0].n1b, nullptr, w.a_op, Ma, d));
-  CK(launch_add_layernorm(s, prec, visual_BLd, nullptr, nullptr, nullptr, nullptr, w.v_op, Mv, d));   // cast only
+  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, nullptr, h->fus[0].n1g, h->fus[0].n1b, nullptr, w.a_op, Ma, d));
+  CKL("add_layernorm", launch_add_layernorm(s, prec, visual_BLd, nullptr, nullptr, nullptr, nullptr, w.v_op, Mv, d));   // cast only
   const bool dbg = h->debug;
   h->debug = false;
   const int rc = fusion_stack(h, s, w, L);   // identity interpolation (L == T)
@@ -771,7 +805,7 @@ int avsep_fusion(avsep_handle* h, const float* audio_BTd, const float* visual_BL
   if (rc) return 1;
   // fused rows in fp32: recompute the final LayerNorm from the fp32 residual stream straight into the caller's buffer
   const int save_prec = h->cfg.precision;
-  CK(launch_add_layernorm(s, PREC_TF32, w.x_a, nullptr, h->fng, h->fnb, nullptr, out_BTd, Ma, d));
+  CKL("add_layernorm", launch_add_layernorm(s, PREC_TF32, w.x_a, nullptr, h->fng, h->fnb, nullptr, out_BTd, Ma, d));
   (void)save_prec;
   return 0;
 }
@@ -787,7 +821,7 @@ int avsep_decoder(avsep_handle* h, const float* fused_BTd, const float* mixed_sp
   if (get_workspace(h, w, nullptr, 0, B, T, 1, 1, 1)) return 1;
   const int d = h->cfg.d_model, Ma = B * T;
   h->launches = 0;
-  CK(launch_add_layernorm(s, h->cfg.precision, fused_BTd, nullptr, nullptr, nullptr, nullptr, w.a_op, Ma, d));
+  CKL("add_layernorm", launch_add_layernorm(s, h->cfg.precision, fused_BTd, nullptr, nullptr, nullptr, nullptr, w.a_op, Ma, d));
   return decoder_stage(h, s, w, mixed_spec, separated, masks);
 }
 
@@ -807,6 +841,39 @@ int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, si
   if (capacity < it->second.second) return fail(h, "avsep_debug_get_stage: buffer too small");
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpy(host_out, it->second.first, it->second.second * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int avsep_set_profile(avsep_handle* h, int32_t enable) {
+  if (!h) return 1;
+  h->profile = enable != 0;
+  return 0;
+}
+
+// Folds the pending event pairs into the per-label totals (synchronises) and writes
+// "label count total_ms\n" lines into buf.  reset != 0 clears the totals afterwards.
+int avsep_profile_report(avsep_handle* h, char* buf, size_t capacity, int32_t reset) {
+  if (!h || !buf || capacity == 0) return fail(h, "avsep_profile_report: bad argument");
+  CUDA_OK(cudaDeviceSynchronize());
+  for (auto& mk : h->ev_marks) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[mk.second], h->ev_pool[mk.second + 1]) == cudaSuccess) {
+      auto& slot = h->prof[mk.first];
+      slot.first += 1;
+      slot.second += ms;
+    }
+  }
+  h->ev_marks.clear();
+  h->ev_used = 0;
+  std::string out;
+  for (auto& kv : h->prof) {
+    char line[160];
+    snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), static_cast<long long>(kv.second.first), kv.second.second);
+    out += line;
+  }
+  if (out.size() + 1 > capacity) return fail(h, "avsep_profile_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  if (reset) h->prof.clear();
   return 0;
 }
 
@@ -848,7 +915,7 @@ int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const vo
 int avsep_test_add_layernorm(avsep_handle* h, const float* x, const float* y, const float* gamma, const float* beta,
                              float* x_out, void* out_op, int32_t M, int32_t d, void* cuda_stream) {
   if (!h) return 1;
-  CK(launch_add_layernorm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, x, y, gamma, beta, x_out, out_op, M, d));
+  CKL("add_layernorm", launch_add_layernorm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, x, y, gamma, beta, x_out, out_op, M, d));
   return 0;
 }
 

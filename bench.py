@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: AVSeparationTransformer.forward on SyntheticAVDataset-shaped input.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward pass of the default model (BASELINE.json configs[1]: freq_bins=257, d_model=256, nhead=4,
+2 encoder + 2 fusion layers, 2 speakers, bf16 operands) over one batch of B=256 one-second utterances per GPU
+(1 s @ 8 kHz: T=63 STFT frames, N=50 lip frames of 32x32).  The batch shards across ranks with no data-path
+collective (weak scaling: per-GPU batch fixed); NCCL is used only for the barrier and the max-over-ranks time.
+Prints ONE JSON line (rank 0).  Metric: separated utterance-seconds per second = B_total * 1 s / forward time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "av-separation-transformer_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "separated utterance-sec/sec"
+UNIT = "utt-s/s"
+MODEL = dict(freq_bins=257, d_model=256, nhead=4, num_encoder_layers=2, num_fusion_layers=2, num_speakers=2)
+CLIP_SECONDS = 1.0
+T_FRAMES, N_FRAMES, FRAME_HW = 63, 50, 32          # dataset.py:63-65,114 at 8 kHz / 1 s / hop 128 / 25 fps x 2 speakers
+CPU_SAMPLE_B = 32                                  # CPU throughput is flat beyond B~32
+
+
+def workload_name(batch):
+    return (f"configs[1]: default model (F=257,d=256,H=4,2+2 layers,S=2), B={batch}/GPU, 1 s @ 8 kHz "
+            f"(T={T_FRAMES}, N={N_FRAMES}, {FRAME_HW}x{FRAME_HW}), SyntheticAVDataset-shaped")
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithmic work per kernel class, per forward of B utterances (SURVEY.md section 8d formulas)
+# ----------------------------------------------------------------------------------------------
+def kernel_work(B):
+    d, F, S = MODEL["d_model"], MODEL["freq_bins"], MODEL["num_speakers"]
+    Le, Lf, T, N = MODEL["num_encoder_layers"], MODEL["num_fusion_layers"], T_FRAMES, N_FRAMES
+    Ma, Mv = B * T, B * N
+    rows_enc = Le * (Ma + Mv)
+    cnn_per_frame = 2 * 256 * 32 * 9 + 2 * 64 * 64 * 288 + 2 * 16 * 128 * 576
+    flops = {
+        "gemm.conv1d_0": 2 * Ma * d * 3 * F, "gemm.conv1d_2": 2 * Ma * d * 3 * d,
+        "gemm.qkv": rows_enc * 2 * 3 * d * d, "gemm.out_proj": (rows_enc + Lf * Ma) * 2 * d * d,
+        "gemm.ffn1": (rows_enc + Lf * Ma) * 2 * 4 * d * d, "gemm.ffn2": (rows_enc + Lf * Ma) * 2 * 4 * d * d,
+        "gemm.cross_q": Lf * Ma * 2 * d * d, "gemm.cross_kv": Mv * 2 * (Lf * 2 * d) * d,
+        "attn.self": Le * B * 4 * d * (T * T + N * N), "attn.cross": Lf * B * 4 * d * T * T,
+        "visual_cnn": Mv * cnn_per_frame, "gemm.frame_proj": Mv * 2 * 128 * d,
+        "gemm.dec0": Ma * 2 * 2 * d * d, "gemm.dec3_tail": Ma * 2 * S * F * 2 * d,
+    }
+    n_ln = 2 + 2 * Le * 2 + 2 * Lf            # launches per forward
+    ln_rows = (1 + 2 * Le) * Ma + (1 + 2 * Le) * Mv + 2 * Lf * Ma
+    bytes_ = {
+        # x (fp32) + y (fp32) in, x (fp32) + normalised operand (bf16) out = 14 B per element
+        "add_layernorm": ln_rows * d * 14,
+        # masks + separated fp32 out, mixed fp32 in, bf16 A operand in
+        "gemm.dec3_tail": Ma * S * F * 8 + B * F * T * 4 + Ma * 2 * d * 2,
+        "prep_audio": B * F * T * 4 + B * (T + 2) * ((F + 7) // 8 * 8) * 2,
+    }
+    return flops, bytes_, n_ln
+
+
+def total_flops(B):
+    return sum(kernel_work(B)[0].values())
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle port) -- the ONLY place bench.py touches oracle/
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_throughput(state, mixed, frames, min_seconds=10.0, max_reps=8):
+    import torch
+    from oracle import avsep_oracle_torch as otorch
+    from oracle.weights import ModelConfig
+    cfg = ModelConfig(**MODEL)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: v.detach().cpu() for k, v in state.items()}
+    otorch.forward(P, cfg, mixed, frames)            # warm-up
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
+        t0 = time.perf_counter()
+        otorch.forward(P, cfg, mixed, frames)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return mixed.shape[0] * CLIP_SECONDS / best, cores, best, len(times)
+
+
+def build_state(seed=0):
+    """Random-init weights of the architecture (torch default init, as the reference constructs them), with
+    non-trivial BatchNorm statistics.  Uses only torch.nn parameter containers -- no kernels involved."""
+    import torch
+    from avsep_b200 import AVSeparationTransformer
+    torch.manual_seed(seed)
+    model = AVSeparationTransformer(**MODEL, precision="bf16")
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn(buf.shape, generator=g))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+    return model
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU forward (oracle port on torch CPU ops, all host threads)."""
+    if rank != 0:
+        return
+    import torch
+    from avsep_b200.synth import synthetic_batch
+    model = build_state()
+    state = model.state_dict()
+    mixed, frames = synthetic_batch(CPU_SAMPLE_B, MODEL["freq_bins"], T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=100)
+    from oracle import avsep_oracle_torch as otorch
+    from oracle.weights import ModelConfig
+    cfg = ModelConfig(**MODEL)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: v.detach().cpu() for k, v in state.items()}
+    for _ in range(max(1, min(args.warmup, 3))):
+        otorch.forward(P, cfg, mixed, frames)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        otorch.forward(P, cfg, mixed, frames)
+    dt = time.perf_counter() - t0
+    value = args.steps * CPU_SAMPLE_B * CLIP_SECONDS / dt
+    sample = f"B={CPU_SAMPLE_B} utterances of the same workload per step (CPU throughput is flat beyond B~32)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from avsep_b200.synth import synthetic_batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    F, S = MODEL["freq_bins"], MODEL["num_speakers"]
+    model = build_state().to(dev)
+    model.prepack(dev)
+    eng = model.engine
+    # rotating input sets: inputs (69 MB) + outputs (133 MB) + activations (~350 MB) per step already exceed the
+    # 126 MB L2; three distinct input sets make sure no step re-reads the previous step's inputs from L2.
+    n_sets = 3
+    sets = [synthetic_batch(B, F, T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=1000 * rank + i, device=dev)
+            for i in range(n_sets)]
+    sep = torch.empty((B, S, F, T_FRAMES), device=dev)
+    masks = torch.empty_like(sep)
+    import ctypes as C
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        mixed, frames = sets[i % n_sets]
+        rc = eng.lib.avsep_forward(eng.h, mixed.data_ptr(), frames.data_ptr(), B, T_FRAMES, N_FRAMES, FRAME_HW,
+                                   FRAME_HW, sep.data_ptr(), masks.data_ptr(), None, 0,
+                                   C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(eng.lib.avsep_last_error(eng.h).decode())
+
+    for i in range(args.warmup):
+        step(i)
+    launches_per_step = eng.launch_count()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if rank == 0 else 0)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B * CLIP_SECONDS / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public host-buffer call; pinned inputs H2D and results D2H every step -----------------
+    h_sets = [(m.cpu().pin_memory(), f.cpu().pin_memory()) for m, f in sets[:2]]
+    h_sep = torch.empty((B, S, F, T_FRAMES)).pin_memory()
+    h_masks = torch.empty((B, S, F, T_FRAMES)).pin_memory()
+    e2e_steps = max(2, min(args.steps, 10))
+    for i in range(2):
+        eng.forward_host(h_sets[i % 2][0], h_sets[i % 2][1], h_sep, h_masks)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.forward_host(h_sets[i % 2][0], h_sets[i % 2][1], h_sep, h_masks)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * B * CLIP_SECONDS * e2e_steps / e2e_s
+    h2d = (h_sets[0][0].numel() + h_sets[0][1].numel()) * 4
+    d2h = (h_sep.numel() + h_masks.numel()) * 4
+
+    # ---- per-kernel pass (same steps again, every launch bracketed by CUDA events on the launching stream) ----
+    eng.set_profile(True)
+    eng.profile_report(reset=True)
+    prof_steps = max(2, min(args.steps, 10))
+    for i in range(prof_steps):
+        step(i)
+    prof = eng.profile_report(reset=True)
+    eng.set_profile(False)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    flops, bytes_, _ = kernel_work(B)
+    tot_ms = sum(v[1] for v in prof.values()) or 1.0
+    breakdown = {}
+    for label, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        per_step_ms = ms / prof_steps
+        entry = {"launches_per_step": n // prof_steps, "ms_per_step": round(per_step_ms, 4),
+                 "share": round(ms / tot_ms, 4)}
+        if label in flops and label != "gemm.dec3_tail":
+            entry["tflops"] = round(flops[label] / (per_step_ms * 1e-3) / 1e12, 2)
+            entry["frac_of_tensor_peak"] = round(entry["tflops"] / peaks["tensor_sustained"], 4)
+        if label in bytes_:
+            entry["gbs"] = round(bytes_[label] / (per_step_ms * 1e-3) / 1e9, 1)
+            entry["frac_of_hbm_peak"] = round(entry["gbs"] / peaks["hbm"], 4)
+        breakdown[label] = entry
+    top = next(iter(breakdown))
+    te = breakdown[top]
+    n_top = max(1, te["launches_per_step"])
+    if "tflops" in te:
+        roofline = {"kernel": top, "bound": "tensor", "achieved": te["tflops"], "peak": peaks["tensor_sustained"],
+                    "unit": "TFLOP/s", "frac": round(te["tflops"] / peaks["tensor_sustained"], 4), "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)",
+                    "launch_ms": round(te["ms_per_step"] / n_top, 4),
+                    "algorithmic_flops_per_launch": flops[top] / n_top}
+    else:
+        roofline = {"kernel": top, "bound": "hbm", "achieved": te["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": round(te["gbs"] / peaks["hbm"], 4), "traffic": None, "peak_source": peaks["source"],
+                    "launch_ms": round(te["ms_per_step"] / n_top, 4),
+                    "algorithmic_bytes_per_launch": bytes_[top] / n_top}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(B), "global_batch": world * B, "parallelism": f"batch-sharded x{world}",
+                   "l2": f"{n_sets} rotating input sets; per-step footprint (inputs+outputs+activations) > 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "avsep_forward_host (pinned host buffers, copies inside the timed call)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "gflop_per_step": total_flops(B) / 1e9,
+        "model_tflops": round(total_flops(B) / (ms_per_step * 1e-3) / 1e12, 2),
+        "roofline": roofline,
+        "kernels": breakdown,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        m_cpu, f_cpu = sets[0][0][:CPU_SAMPLE_B].cpu(), sets[0][1][:CPU_SAMPLE_B].cpu()
+        v, cores, best, reps = cpu_reference_throughput(model.state_dict(), m_cpu, f_cpu)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"first {CPU_SAMPLE_B} utterances of the same batch, best of {reps} forwards "
+                                         f"({best * 1e3:.0f} ms each), torch CPU ops, {cores} threads"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--batch", str(args.batch)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,11 @@ AVSEP_API int avsep_set_debug(avsep_handle* h, int32_t enable);
 /* Copies a snapshot to a HOST buffer of `capacity` floats; returns the element count in *count. Synchronises. */
 AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, size_t capacity, size_t* count);
 
+/* Per-kernel timing: when enabled every launch of the forward is bracketed by a cudaEvent pair on the launching
+ * stream.  avsep_profile_report synchronises and writes one "label launches total_ms" line per kernel class. */
+AVSEP_API int avsep_set_profile(avsep_handle* h, int32_t enable);
+AVSEP_API int avsep_profile_report(avsep_handle* h, char* buf, size_t capacity, int32_t reset);
+
 /* Kernel-level test hooks (DEVICE pointers; used by tests/ to check each kernel against a torch fp32 reference).
  *   gemm: out[M,N] = act(A[M,K] @ W[N,K]^T + bias), A/W in operand precision (bf16 or fp32), out fp32.
  *   conv1d: taps=3 implicit GEMM over a zero-haloed activation: A [B*(L+2), K], W [N, 3*K] (k = tap*K + c),
