@@ -229,6 +229,10 @@ class Engine:
         self._check(rc, "avsep_decoder")
         return sep, masks
 
+    def set_option(self, name: str, value: int):
+        """Execution options: 'fuse_ln' (0/1), 'host_chunk' (utterances per pipeline chunk of forward_host)."""
+        self._check(self.lib.avsep_set_option(self.h, name.encode(), int(value)), "avsep_set_option")
+
     # ---- profiling -------------------------------------------------------------------------------
     def set_profile(self, on: bool):
         self._check(self.lib.avsep_set_profile(self.h, 1 if on else 0), "avsep_set_profile")

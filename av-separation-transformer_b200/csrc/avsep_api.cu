@@ -80,6 +80,7 @@ struct avsep_handle {
   std::string err;
   std::map<std::string, HostTensor> host_w;
   bool finalized = false;
+  bool fuse_ln = true;   // residual+LayerNorm in the GEMM epilogue when the row fits one tile
   uint8_t* d_weights = nullptr;
   size_t weight_bytes = 0;
   // device views into d_weights
@@ -95,6 +96,9 @@ struct avsep_handle {
   // host-path staging
   float *io_mixed = nullptr, *io_frames = nullptr, *io_sep = nullptr, *io_masks = nullptr;
   size_t io_cap[4] = {0, 0, 0, 0};
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> host_ev;
+  int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
   // debug
   bool debug = false;
   std::map<std::string, std::pair<float*, size_t>> snaps;
@@ -244,6 +248,48 @@ int linear(avsep_handle* h, cudaStream_t s, const char* label, const void* A, in
   return 0;
 }
 
+// GEMM (epilogue fields of `e` already set: bias/act/pe/rowmap) followed by
+//   x_out = value (+ resid);  out_op = LayerNorm_{g,b}(x_out)   (g == null: out_op = cast(x_out))
+// Fused into the GEMM epilogue when the row fits one tile (EPI_LN), otherwise GEMM -> y, then the warp-shuffle
+// add+LayerNorm kernel.  rows_out = number of output rows; y = scratch [rows_out, N] fp32.
+int gemm_resid_ln(avsep_handle* h, cudaStream_t s, const char* label, const GemmProblem& p, GemmEpilogue e,
+                  const float* resid, float* x_out, const float* g, const float* b, void* out_op, int rows_out,
+                  float* y) {
+  const int prec = h->cfg.precision;
+  if (h->fuse_ln && gemm_ln_fusable(p.N)) {
+    e.kind = EPI_LN;
+    e.resid = resid;
+    e.out_f32 = x_out; e.ld_f32 = p.N;
+    e.ln_gamma = g; e.ln_beta = b;
+    e.out_op = out_op; e.ld_op = p.N;
+    CKL(label, launch_gemm(s, prec, p, e));
+    return 0;
+  }
+  e.kind = EPI_STD;
+  e.out_op = nullptr;
+  if (resid != nullptr) {
+    e.out_f32 = y; e.ld_f32 = p.N;
+    CKL(label, launch_gemm(s, prec, p, e));
+    CKL("add_layernorm", launch_add_layernorm(s, prec, resid, y, g, b, x_out, out_op, rows_out, p.N));
+  } else {
+    e.out_f32 = x_out; e.ld_f32 = p.N;
+    CKL(label, launch_gemm(s, prec, p, e));
+    CKL("add_layernorm", launch_add_layernorm(s, prec, x_out, nullptr, g, b, nullptr, out_op, rows_out, p.N));
+  }
+  return 0;
+}
+
+int linear_resid_ln(avsep_handle* h, cudaStream_t s, const char* label, const void* A, int M, int K, const void* W,
+                    const float* bias, int N, float* x, const float* g, const float* b, void* out_op, float* y) {
+  GemmProblem p{};
+  p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K; p.taps = 1;
+  GemmEpilogue e;
+  e.bias = bias;
+  return gemm_resid_ln(h, s, label, p, e, x, x, g, b, out_op, M, y);
+}
+
+// nn.TransformerEncoderLayer x L (pre-norm, ReLU FFN; model.py:48-52,59; torch transformer.py:946-950).
+// In: x (fp32 residual stream), a_op = LN_{layer0.norm1}(x).  Out: x, a_op = LN_{final}(x) (or cast when final_g == null).
 int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>& layers, int B, int L, float* x,
                   float* y, void* a_op, void* qkv, void* attn, void* ffn, const float* final_g, const float* final_b) {
   const int d = h->cfg.d_model, H = h->cfg.nhead, M = B * L, prec = h->cfg.precision;
@@ -259,20 +305,19 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     ap.out = attn; ap.ldo = d;
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = L; ap.Lk = L; ap.lerp_src = 0;
     CKL("attn.self", launch_attention(s, prec, ap));
-    if (linear(h, s, "gemm.out_proj", attn, M, d, w.wo, w.bo, d, ACT_NONE, y, nullptr)) return 1;
-    CKL("add_layernorm", launch_add_layernorm(s, prec, x, y, w.n2g, w.n2b, x, a_op, M, d));
+    if (linear_resid_ln(h, s, "gemm.out_proj", attn, M, d, w.wo, w.bo, d, x, w.n2g, w.n2b, a_op, y)) return 1;
     if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
-    if (linear(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, ACT_NONE, y, nullptr)) return 1;
     const bool last = (l + 1 == layers.size());
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
-    CKL("add_layernorm", launch_add_layernorm(s, prec, x, y, g, b, x, a_op, M, d));
+    if (linear_resid_ln(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, x, g, b, a_op, y)) return 1;
   }
   return 0;
 }
 
-// AudioEncoder up to (not including) the transformer: Conv1d+ReLU x2, +PE  (model.py:56-58)
-int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed) {
+// AudioEncoder up to (not including) the transformer: Conv1d+ReLU x2, +PE (model.py:56-58), then the first
+// layer's LayerNorm: x_a (fp32) and a_op = LN_{g,b}(x_a).
+int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* g, const float* b) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, F = h->cfg.freq_bins, B = w.B, T = w.T, prec = h->cfg.precision;
   const int Map = B * (T + 2);
@@ -293,14 +338,14 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     GemmEpilogue e;
     e.bias = h->bc2; e.act = ACT_RELU; e.rowmap = ROW_PAD2COMPACT; e.Lp = T + 2;
     e.pe = h->pe_a;
-    e.out_f32 = w.x_a; e.ld_f32 = d;
-    CKL("gemm.conv1d_2", launch_gemm(s, prec, p, e));
+    if (gemm_resid_ln(h, s, "gemm.conv1d_2", p, e, nullptr, w.x_a, g, b, w.a_op, B * T, w.y_a)) return 1;
   }
   return snapshot(h, s, "audio_embed", w.x_a, static_cast<size_t>(B) * T * d, false);
 }
 
-// VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110)
-int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames) {
+// VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110), then the
+// first layer's LayerNorm: x_v (fp32) and v_op = LN_{g,b}(x_v).
+int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames, const float* g, const float* b) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, N = w.N, prec = h->cfg.precision;
   const int Mv = B * N;
@@ -311,8 +356,7 @@ int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* 
   p.taps = 1;
   GemmEpilogue e;
   e.bias = h->bproj; e.pe = h->pe_v; e.pe_period = N;
-  e.out_f32 = w.x_v; e.ld_f32 = d;
-  CKL("gemm.frame_proj", launch_gemm(s, prec, p, e));
+  if (gemm_resid_ln(h, s, "gemm.frame_proj", p, e, nullptr, w.x_v, g, b, w.v_op, Mv, w.y_v)) return 1;
   return snapshot(h, s, "visual_embed", w.x_v, static_cast<size_t>(Mv) * d, false);
 }
 
@@ -335,14 +379,13 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     ap.out = w.attn_a; ap.ldo = d;
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = T; ap.Lk = T; ap.lerp_src = L_src;
     CKL("attn.cross", launch_attention(s, prec, ap));
-    if (linear(h, s, "gemm.out_proj", w.attn_a, Ma, d, fw.wo, fw.bo, d, ACT_NONE, w.y_a, nullptr)) return 1;
-    CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, w.y_a, fw.n2g, fw.n2b, w.x_a, w.a_op, Ma, d));
+    if (linear_resid_ln(h, s, "gemm.out_proj", w.attn_a, Ma, d, fw.wo, fw.bo, d, w.x_a, fw.n2g, fw.n2b, w.a_op, w.y_a))
+      return 1;
     if (linear(h, s, "gemm.ffn1", w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
-    if (linear(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, ACT_NONE, w.y_a, nullptr)) return 1;
     const bool last = (l + 1 == Lf);
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
-    CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, w.y_a, g, b, w.x_a, w.a_op, Ma, d));
+    if (linear_resid_ln(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, w.x_a, g, b, w.a_op, w.y_a)) return 1;
   }
   return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
 }
@@ -366,19 +409,17 @@ int decoder_stage(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mi
 
 int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* frames,
                    float* separated, float* masks) {
-  const int d = h->cfg.d_model, prec = h->cfg.precision;
+  const int d = h->cfg.d_model;
   const int Ma = w.B * w.T, Mv = w.B * w.N;
   h->prof_stream = s;
   // --- audio branch ---
-  if (audio_frontend(h, s, w, mixed)) return 1;
-  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
                     h->fus[0].n1b))
     return 1;
   if (snapshot(h, s, "audio_enc", w.x_a, static_cast<size_t>(Ma) * d, false)) return 1;
   // --- visual branch ---
-  if (visual_frontend(h, s, w, frames)) return 1;
-  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  if (visual_frontend(h, s, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
     return 1;
   if (snapshot(h, s, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
@@ -469,6 +510,9 @@ void avsep_destroy(avsep_handle* h) {
   for (auto& kv : h->snaps)
     if (kv.second.first) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->host_ev) cudaEventDestroy(e);
+  for (int i = 0; i < 3; ++i)
+    if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
   delete h;
 }
 
@@ -709,16 +753,17 @@ int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_fra
 
 int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
                        int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream) {
+  // Software pipeline over chunks of the batch: H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 run
+  // concurrently on three streams (PCIe is full duplex), so the call costs ~max(copy-in, compute, copy-out).
   if (!h) return 1;
   if (!mixed_spec || !lip_frames || !separated || !masks) return fail(h, "avsep_forward_host: null buffer");
   if (check_shape(h, B, T, N, Hh, Ww)) return 1;
   CUDA_OK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const size_t n_mixed = static_cast<size_t>(B) * h->cfg.freq_bins * T;
-  const size_t n_frames = static_cast<size_t>(B) * N * Hh * Ww;
-  const size_t n_out = static_cast<size_t>(B) * h->cfg.num_speakers * h->cfg.freq_bins * T;
+  const size_t F = h->cfg.freq_bins, S = h->cfg.num_speakers;
+  const size_t mixed_per = F * T, frames_per = static_cast<size_t>(N) * Hh * Ww, out_per = S * F * T;
   float** bufs[4] = {&h->io_mixed, &h->io_frames, &h->io_sep, &h->io_masks};
-  const size_t need[4] = {n_mixed, n_frames, n_out, n_out};
+  const size_t need[4] = {B * mixed_per, B * frames_per, B * out_per, B * out_per};
   for (int i = 0; i < 4; ++i) {
     if (h->io_cap[i] < need[i]) {
       if (*bufs[i]) cudaFree(*bufs[i]);
@@ -728,15 +773,51 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
       h->io_cap[i] = need[i];
     }
   }
+  if (h->hs[0] == nullptr) {
+    for (int i = 0; i < 3; ++i) CUDA_OK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+  }
+  const int Bc = h->host_chunk > 0 && h->host_chunk < B ? h->host_chunk : B;
+  const int nchunks = (B + Bc - 1) / Bc;
+  while (static_cast<int>(h->host_ev.size()) < 2 * nchunks + 2) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->host_ev.push_back(e);
+  }
   Workspace w;
-  if (get_workspace(h, w, nullptr, 0, B, T, N, Hh, Ww)) return 1;
-  CUDA_OK(cudaMemcpyAsync(h->io_mixed, mixed_spec, n_mixed * 4, cudaMemcpyHostToDevice, s));
-  CUDA_OK(cudaMemcpyAsync(h->io_frames, lip_frames, n_frames * 4, cudaMemcpyHostToDevice, s));
+  if (get_workspace(h, w, nullptr, 0, Bc, T, N, Hh, Ww)) return 1;
+  cudaStream_t s_in = h->hs[0], s_comp = h->hs[1], s_out = h->hs[2];
+  // order after whatever the caller queued on its stream
+  cudaEvent_t ev_start = h->host_ev[2 * nchunks];
+  CUDA_OK(cudaEventRecord(ev_start, s));
+  CUDA_OK(cudaStreamWaitEvent(s_in, ev_start, 0));
+  CUDA_OK(cudaStreamWaitEvent(s_comp, ev_start, 0));
+  CUDA_OK(cudaStreamWaitEvent(s_out, ev_start, 0));
   h->launches = 0;
-  if (forward_device(h, s, w, h->io_mixed, h->io_frames, h->io_sep, h->io_masks)) return 1;
-  CUDA_OK(cudaMemcpyAsync(separated, h->io_sep, n_out * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(masks, h->io_masks, n_out * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * Bc;
+    const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+    CUDA_OK(cudaMemcpyAsync(h->io_mixed + b0 * mixed_per, mixed_spec + b0 * mixed_per, bc * mixed_per * 4,
+                            cudaMemcpyHostToDevice, s_in));
+    CUDA_OK(cudaMemcpyAsync(h->io_frames + b0 * frames_per, lip_frames + b0 * frames_per, bc * frames_per * 4,
+                            cudaMemcpyHostToDevice, s_in));
+    CUDA_OK(cudaEventRecord(h->host_ev[2 * c], s_in));
+    CUDA_OK(cudaStreamWaitEvent(s_comp, h->host_ev[2 * c], 0));
+    Workspace wc = w;
+    wc.B = bc;
+    if (forward_device(h, s_comp, wc, h->io_mixed + b0 * mixed_per, h->io_frames + b0 * frames_per,
+                       h->io_sep + b0 * out_per, h->io_masks + b0 * out_per))
+      return 1;
+    CUDA_OK(cudaEventRecord(h->host_ev[2 * c + 1], s_comp));
+    CUDA_OK(cudaStreamWaitEvent(s_out, h->host_ev[2 * c + 1], 0));
+    CUDA_OK(cudaMemcpyAsync(separated + b0 * out_per, h->io_sep + b0 * out_per, bc * out_per * 4,
+                            cudaMemcpyDeviceToHost, s_out));
+    CUDA_OK(cudaMemcpyAsync(masks + b0 * out_per, h->io_masks + b0 * out_per, bc * out_per * 4,
+                            cudaMemcpyDeviceToHost, s_out));
+  }
+  cudaEvent_t ev_end = h->host_ev[2 * nchunks + 1];
+  CUDA_OK(cudaEventRecord(ev_end, s_out));
+  CUDA_OK(cudaStreamWaitEvent(s, ev_end, 0));
+  CUDA_OK(cudaStreamSynchronize(s_out));
   return 0;
 }
 
@@ -752,10 +833,9 @@ int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   Workspace w;
   if (get_workspace(h, w, nullptr, 0, B, T, 1, 1, 1)) return 1;
-  const int d = h->cfg.d_model, Ma = B * T, prec = h->cfg.precision;
+  const int d = h->cfg.d_model, Ma = B * T;
   h->launches = 0;
-  if (audio_frontend(h, s, w, mixed_spec)) return 1;
-  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_a, nullptr, h->enc_a[0].n1g, h->enc_a[0].n1b, nullptr, w.a_op, Ma, d));
+  if (audio_frontend(h, s, w, mixed_spec, h->enc_a[0].n1g, h->enc_a[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_a, B, T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, nullptr, nullptr)) return 1;
   CUDA_OK(cudaMemcpyAsync(out_BTd, w.x_a, static_cast<size_t>(Ma) * d * 4, cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -771,10 +851,9 @@ int avsep_visual_encoder(avsep_handle* h, const float* lip_frames, int32_t B, in
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   Workspace w;
   if (get_workspace(h, w, nullptr, 0, B, 1, N, Hh, Ww)) return 1;
-  const int d = h->cfg.d_model, Mv = B * N, prec = h->cfg.precision;
+  const int d = h->cfg.d_model;
   h->launches = 0;
-  if (visual_frontend(h, s, w, lip_frames)) return 1;
-  CKL("add_layernorm", launch_add_layernorm(s, prec, w.x_v, nullptr, h->enc_v[0].n1g, h->enc_v[0].n1b, nullptr, w.v_op, Mv, d));
+  if (visual_frontend(h, s, w, lip_frames, h->enc_v[0].n1g, h->enc_v[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_v, B, N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) return 1;
   interp_rows_kernel<<<dim3(target_len, B), 128, 0, s>>>(w.x_v, out_BTd, N, target_len, d,
                                                          static_cast<float>(N) / static_cast<float>(target_len));
@@ -887,6 +966,28 @@ int avsep_test_gemm(avsep_handle* h, const void* A, const void* W, const float* 
   e.bias = bias; e.act = act; e.out_f32 = out; e.ld_f32 = N;
   CK(launch_gemm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, p, e, force_bn));
   return 0;
+}
+
+// out-proj/FFN2-style GEMM with the fused residual + LayerNorm epilogue: x (in/out, fp32 [M,N]) += A W^T + bias;
+// out_op = LN_{gamma,beta}(x) in operand precision.
+int avsep_test_gemm_ln(avsep_handle* h, const void* A, const void* W, const float* bias, float* x, const float* gamma,
+                       const float* beta, void* out_op, int32_t M, int32_t N, int32_t K, void* cuda_stream) {
+  if (!h) return 1;
+  GemmProblem p{};
+  p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K; p.taps = 1;
+  GemmEpilogue e;
+  e.kind = EPI_LN;
+  e.bias = bias; e.resid = x; e.out_f32 = x; e.ld_f32 = N; e.ln_gamma = gamma; e.ln_beta = beta;
+  e.out_op = out_op; e.ld_op = N;
+  CK(launch_gemm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, p, e));
+  return 0;
+}
+
+int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
+  if (!h || !name) return 1;
+  if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
+  if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
+  return fail(h, std::string("unknown option ") + name);
 }
 
 int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,

@@ -1,4 +1,4 @@
-// TMA-fed tcgen05 GEMM for sm_100a with fused epilogues.
+// Persistent TMA-fed tcgen05 GEMM for sm_100a with fused epilogues.
 //
 //   acc[m, n] = sum_{tap < taps} sum_{k < K} A[m + row_shift + tap, k] * W[n, tap*tap_stride + k]
 //
@@ -6,14 +6,21 @@
 // taps = 3 is nn.Conv1d(k=3, padding=1) as an implicit GEMM: three row-shifted TMA views of the
 // zero-haloed activation accumulate into the same TMEM tile (reference: model.py:37-42,56).
 //
-// Structure (one 128 x n_tile output tile per CTA, 192 threads):
-//   warp 0 / lane 0 : TMA producer  - cp.async.bulk.tensor A/W tiles (128B swizzle) into a STAGES-deep ring
-//   warp 1 / lane 0 : MMA issuer    - tcgen05.mma (M=128, N=n_tile, K=16|8) accumulating in TMEM,
-//                                     tcgen05.commit releases smem stages / signals the epilogue
-//   warps 2..5      : epilogue      - tcgen05.ld (thread = accumulator row), bias / ReLU / exact GELU /
-//                                     positional-encoding add / Conv1d halo handling, or the decoder tail
-//                                     (sigmoid, x mixed_spec, (B,S,F,T) stores coalesced along T)
-// Two or more CTAs are resident per SM (<= 113 KB smem each), so one CTA's epilogue overlaps another's main loop.
+// One persistent CTA per SM (320 threads) walks 128 x n_tile output tiles (m fastest, so CTAs that run together
+// share the weight tile in L2):
+//   warp 0 / lane 0 : TMA producer  - cp.async.bulk.tensor A/W tiles (128B swizzle) into a 4-deep smem ring that
+//                                     runs ahead across tile boundaries
+//   warp 1 / lane 0 : MMA issuer    - tcgen05.mma (M=128, N=n_tile<=256, K=16 bf16 | 8 tf32) into one of TWO TMEM
+//                                     accumulator stages; tcgen05.commit frees smem stages / publishes the tile
+//   warps 2..9      : epilogue      - two warps per TMEM lane quarter (interleaved 32-column chunks), so tile i's
+//                                     epilogue overlaps tile i+1's main loop.  Thread = accumulator row.
+// Epilogues (template EPI):
+//   EPI_STD  bias / ReLU / exact GELU / positional-encoding add / Conv1d halo handling, fp32 and/or bf16 stores
+//   EPI_TAIL SeparationDecoder head: sigmoid, x mixed_spec, (B,S,F,T) stores coalesced along T (model.py:204-220)
+//   EPI_LN   EPI_STD value + residual add, write the fp32 residual stream, then LayerNorm of the full row
+//            (n_tile == N == d_model <= 256, row held in registers, exact two-pass statistics merged across the
+//            two column halves) and write the normalised bf16 operand of the next GEMM -- the fused
+//            residual+LayerNorm of every encoder / fusion sub-layer (model.py:149,168-172).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,21 +32,22 @@ namespace avsep {
 namespace {
 
 constexpr int BM = 128;
+constexpr int BN_MAX = 256;
+constexpr int STAGES = 4;
 constexpr int TILE_K_BYTES = 128;            // one 128-byte swizzle span per row per stage
 constexpr int A_STAGE_BYTES = BM * TILE_K_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int B_STAGE_BYTES = BN_MAX * TILE_K_BYTES;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][2 halves] float2
+constexpr int SMEM_TOTAL = RED_OFFSET + 2 * 128 * 2 * 8 + 1024;
+constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator stages
 
 struct GemmDev {
   int M, N, K, taps, tap_stride, row_shift, n_tile;
   GemmEpilogue e;
-};
-
-template <int BN_MAX, int STAGES>
-struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BN_MAX * TILE_K_BYTES;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
 template <bool TF32>
@@ -75,24 +83,102 @@ __device__ __forceinline__ void store_op_chunk(void* out_op, size_t off, const f
   }
 }
 
-template <int BN_MAX, int STAGES, bool TF32>
-__global__ void __launch_bounds__(NUM_THREADS, (BN_MAX <= 128 ? 2 : 1))
+// Row bookkeeping shared by the epilogues: where accumulator row m goes and which PE row it takes.
+struct RowInfo {
+  bool valid, zero_row;
+  long long orow;
+  int pos;
+};
+__device__ __forceinline__ RowInfo row_info(const GemmEpilogue& e, int m, int M) {
+  RowInfo r;
+  r.valid = m < M;
+  r.zero_row = false;
+  r.orow = m;
+  r.pos = 0;
+  if (e.rowmap == ROW_IDENT) {
+    if (e.pe_period > 0) r.pos = m % e.pe_period;
+  } else {
+    const int b = m / e.Lp;
+    const int tp = m - b * e.Lp;
+    const bool halo = (tp == 0) || (tp == e.Lp - 1);
+    r.pos = tp - 1;
+    if (e.rowmap == ROW_PAD2PAD) {
+      r.zero_row = halo;
+    } else {
+      r.valid = r.valid && !halo;
+      r.orow = static_cast<long long>(b) * (e.Lp - 2) + (tp - 1);
+    }
+  }
+  return r;
+}
+
+// acc chunk -> value chunk: + bias, activation, + PE, halo zeroing.
+__device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo& ri, const uint32_t (&v)[32],
+                                            float (&val)[32], int col0, int ncols, int N) {
+  const bool full = (ncols == 32);
+  if (full && e.bias != nullptr && (N & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+      val[j] = __uint_as_float(v[j]) + b4.x;
+      val[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+      val[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+      val[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float bj = (e.bias != nullptr && j < ncols) ? __ldg(e.bias + col0 + j) : 0.0f;
+      val[j] = __uint_as_float(v[j]) + bj;
+    }
+  }
+  if (e.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = fmaxf(val[j], 0.0f);
+  } else if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = gelu_erf(val[j]);
+  }
+  if (e.pe != nullptr && ri.valid) {
+    const float* pr = e.pe + static_cast<size_t>(ri.pos) * N + col0;
+    if (full && (N & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(pr + j));
+        val[j] += p4.x; val[j + 1] += p4.y; val[j + 2] += p4.z; val[j + 3] += p4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) val[j] += __ldg(pr + j);
+    }
+  }
+  if (ri.zero_row) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = 0.0f;
+  }
+}
+
+template <int EPI, bool TF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
-  using L = SmemLayout<BN_MAX, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator stage complete
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator stage drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* red = reinterpret_cast<float2*>(smem + RED_OFFSET);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * p.n_tile;
   constexpr int ELEMS_PER_TILE = TF32 ? 32 : 64;                 // elements per 128-byte K span
   const int kt_per_tap = (p.K + ELEMS_PER_TILE - 1) / ELEMS_PER_TILE;
   const int num_kt = kt_per_tap * p.taps;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + p.n_tile - 1) / p.n_tile;
+  const int total_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -102,10 +188,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN_MAX);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,157 +205,237 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       const uint32_t stage_bytes = A_STAGE_BYTES + static_cast<uint32_t>(p.n_tile) * TILE_K_BYTES;
-      for (int kt = 0; kt < num_kt; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = kt / kt_per_tap;
-        const int kk = (kt - tap * kt_per_tap) * ELEMS_PER_TILE;
-        uint8_t* a_dst = smem + s * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kk, m0 + p.row_shift + tap);
-        tma_load_2d(b_dst, &tmW, &full_bar[s], tap * p.tap_stride + kk, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * BM;
+        const int n0 = (tile / m_tiles) * p.n_tile;
+        for (int kt = 0; kt < num_kt; ++kt, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = kt / kt_per_tap;
+          const int kk = (kt - tap * kt_per_tap) * ELEMS_PER_TILE;
+          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kk, m0 + p.row_shift + tap);
+          tma_load_2d(b_dst, &tmW, &full_bar[s], tap * p.tap_stride + kk, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc(TF32 ? 2u : 1u, BM, static_cast<uint32_t>(p.n_tile));
-      for (int kt = 0; kt < num_kt; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aph ^ 1);        // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-        const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
-        const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr, 1024);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN_MAX);
+        for (int kt = 0; kt < num_kt; ++kt, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per stage: advance the start address by 32 B (>>4 = 2)
-          const uint32_t acc = (kt | k) != 0 ? 1u : 0u;
-          if constexpr (TF32) umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-          else                umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+          for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per stage: advance the start address by 32 B (>>4 = 2)
+            const uint32_t accum = (kt | k) != 0 ? 1u : 0u;
+            if constexpr (TF32) umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+            else                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+          }
+          umma_commit(&empty_bar[s]);      // smem stage reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);      // smem stage reusable once these MMAs have read it
+        umma_commit(&tfull_bar[acc]);      // accumulator stage complete
       }
-      umma_commit(accum_bar);            // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
+    // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int m = m0 + r;
     const GemmEpilogue& e = p.e;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      const int m0 = (tile % m_tiles) * BM;
+      const int n0 = (tile / m_tiles) * p.n_tile;
+      const int m = m0 + r;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN_MAX);
 
-    bool valid = m < p.M;
-    bool zero_row = false;
-    long long orow = m;
-    int pos = 0;
-    if (e.kind == EPI_STD) {
-      if (e.rowmap == ROW_IDENT) {
-        if (e.pe_period > 0) pos = m % e.pe_period;
-      } else {
-        const int b = m / e.Lp;
-        const int tp = m - b * e.Lp;
-        const bool halo = (tp == 0) || (tp == e.Lp - 1);
-        pos = tp - 1;
-        if (e.rowmap == ROW_PAD2PAD) {
-          zero_row = halo;
-        } else {
-          valid = valid && !halo;
-          orow = static_cast<long long>(b) * (e.Lp - 2) + (tp - 1);
-        }
-      }
-    }
-    int tb = 0, tt = 0;
-    if (e.kind == EPI_TAIL) {
-      tb = m / e.T;
-      tt = m - tb * e.T;
-    }
-
-    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-      const int col0 = n0 + c0;
-      if (col0 >= p.N) break;                      // uniform across the CTA
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
-      tmem_ld_wait();
-      const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
-      if (!valid) continue;
-      float val[32];
-      const bool full = (ncols == 32);
-      if (full && e.bias != nullptr && (p.N & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
-          val[j] = __uint_as_float(v[j]) + b4.x;
-          val[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-          val[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-          val[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float bj = (e.bias != nullptr && j < ncols) ? __ldg(e.bias + col0 + j) : 0.0f;
-          val[j] = __uint_as_float(v[j]) + bj;
-        }
-      }
-
-      if (e.kind == EPI_TAIL) {
+      if constexpr (EPI == EPI_TAIL) {
         // SeparationDecoder head (model.py:204-207,220): column c = s*F + f; lanes are consecutive t, so the
         // (B,S,F,T) stores and the mixed_spec (B,F,T) loads are both contiguous across the warp.
-        int s = col0 / e.F;
-        int f = col0 - s * e.F;
+        const bool valid = m < p.M;
+        const int tb = m / e.T;
+        const int tt = m - tb * e.T;
+        const float* mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
+        for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
+          const int col0 = n0 + c0;
+          if (col0 >= p.N) break;                      // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+          const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
+          const int s0 = col0 / e.F;
+          const int f0 = col0 - s0 * e.F;
+          float mx[32];
+          if (valid) {                                 // all mixed_spec loads in flight before any store
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < ncols) {
-            const float mk = 1.0f / (1.0f + __expf(-val[j]));
-            const size_t o = ((static_cast<size_t>(tb) * e.S + s) * e.F + f) * e.T + tt;
-            const float mx = __ldg(e.mixed + (static_cast<size_t>(tb) * e.F + f) * e.T + tt);
-            e.masks[o] = mk;
-            e.separated[o] = mk * mx;
-            if (++f == e.F) { f = 0; ++s; }
+            for (int j = 0; j < 32; ++j) {
+              int f = f0 + j;
+              while (f >= e.F) f -= e.F;
+              mx[j] = (j < ncols) ? __ldg(mixed_row + static_cast<size_t>(f) * e.T) : 0.f;
+            }
+          }
+          tmem_ld_wait();
+          if (valid) {
+            int s = s0, f = f0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < ncols) {
+                const float z = __uint_as_float(v[j]) + __ldg(e.bias + col0 + j);
+                const float mk = 1.0f / (1.0f + __expf(-z));
+                const size_t o = ((static_cast<size_t>(tb) * e.S + s) * e.F + f) * e.T + tt;
+                __stcs(e.masks + o, mk);
+                __stcs(e.separated + o, mk * mx[j]);
+                if (++f == e.F) { f = 0; ++s; }
+              }
+            }
           }
         }
-        continue;
-      }
-
-      if (e.act == ACT_RELU) {
+      } else if constexpr (EPI == EPI_LN) {
+        // bias/act/PE value, + residual, fp32 residual-stream store, LayerNorm over the whole row, operand store.
+        const RowInfo ri = row_info(e, m, p.M);
+        float val[4][32];
+        float sum = 0.f;
+        int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = fmaxf(val[j], 0.0f);
-      } else if (e.act == ACT_GELU) {
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c0 = (2 * ci + half) * 32;
+          if (c0 < p.n_tile) {                          // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            value_chunk(e, ri, v, val[ci], c0, 32, p.N);
+            if (ri.valid) {
+              if (e.resid != nullptr) {
+                const float4* rp = reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(ri.orow) * p.N + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = gelu_erf(val[j]);
-      }
-      if (e.pe != nullptr) {
-        const float* pr = e.pe + static_cast<size_t>(pos) * p.N + col0;
+                for (int j = 0; j < 8; ++j) {
+                  const float4 x4 = rp[j];
+                  val[ci][4 * j] += x4.x; val[ci][4 * j + 1] += x4.y;
+                  val[ci][4 * j + 2] += x4.z; val[ci][4 * j + 3] += x4.w;
+                }
+              }
+              if (e.out_f32 != nullptr) {
+                float4* op = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) val[j] += __ldg(pr + j);
-      }
-      if (zero_row) {
+                for (int j = 0; j < 8; ++j)
+                  op[j] = make_float4(val[ci][4 * j], val[ci][4 * j + 1], val[ci][4 * j + 2], val[ci][4 * j + 3]);
+              }
+            }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = 0.0f;
-      }
-      if (e.out_f32 != nullptr) {
-        float* o = e.out_f32 + static_cast<size_t>(orow) * e.ld_f32 + col0;
-        if (full && (e.ld_f32 & 3) == 0) {
+            for (int j = 0; j < 32; ++j) sum += val[ci][j];
+            cnt += 32;
+          }
+        }
+        // accumulator fully read: hand the TMEM stage back before the statistics / stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (e.ln_gamma != nullptr) {
+          // exact two-pass statistics of this half, merged with the other half (Chan's parallel formula)
+          const float n_h = static_cast<float>(cnt);
+          const float mean_h = cnt > 0 ? sum / n_h : 0.f;
+          float m2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
-        } else {
+          for (int ci = 0; ci < 4; ++ci) {
+            if ((2 * ci + half) * 32 < p.n_tile) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncols) o[j] = val[j];
+              for (int j = 0; j < 32; ++j) {
+                const float dlt = val[ci][j] - mean_h;
+                m2 += dlt * dlt;
+              }
+            }
+          }
+          float2* slot = red + ((lt & 1) * 128 + r) * 2;
+          slot[half] = make_float2(mean_h, m2);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          const float2 other = slot[half ^ 1];
+          const float n_o = static_cast<float>(p.n_tile - cnt);
+          const float n_all = static_cast<float>(p.n_tile);
+          const float dm = other.x - mean_h;
+          const float mean = mean_h + dm * (n_o / n_all);
+          const float m2_all = m2 + other.y + dm * dm * (n_h * n_o / n_all);
+          const float rstd = rsqrtf(m2_all / n_all + 1e-5f);
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const int c0 = (2 * ci + half) * 32;
+            if (c0 < p.n_tile) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + c0 + j));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + c0 + j));
+                val[ci][j] = (val[ci][j] - mean) * rstd * g4.x + b4.x;
+                val[ci][j + 1] = (val[ci][j + 1] - mean) * rstd * g4.y + b4.y;
+                val[ci][j + 2] = (val[ci][j + 2] - mean) * rstd * g4.z + b4.z;
+                val[ci][j + 3] = (val[ci][j + 3] - mean) * rstd * g4.w + b4.w;
+              }
+            }
+          }
+        }
+        if (ri.valid && e.out_op != nullptr) {
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            const int c0 = (2 * ci + half) * 32;
+            if (c0 < p.n_tile)
+              store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + c0, val[ci], 32, true);
+          }
+        }
+        continue;   // tempty already signalled
+      } else {
+        const RowInfo ri = row_info(e, m, p.M);
+        for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
+          const int col0 = n0 + c0;
+          if (col0 >= p.N) break;                      // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+          tmem_ld_wait();
+          const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
+          if (!ri.valid) continue;
+          float val[32];
+          value_chunk(e, ri, v, val, col0, ncols, p.N);
+          const bool full = (ncols == 32);
+          if (e.out_f32 != nullptr) {
+            float* o = e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + col0;
+            if (full && (e.ld_f32 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = val[j];
+            }
+          }
+          if (e.out_op != nullptr) {
+            const bool vec = full && ((e.ld_op & 7) == 0);
+            store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + col0, val, ncols, vec);
+          }
         }
       }
-      if (e.out_op != nullptr) {
-        const bool vec = full && ((e.ld_op & 7) == 0);
-        store_op_chunk<TF32>(e.out_op, static_cast<size_t>(orow) * e.ld_op + col0, val, ncols, vec);
-      }
+      // release this accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
 
@@ -273,7 +443,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN_MAX);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -281,6 +451,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // host side
 // ------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_num_sms = 0;
 
 const char* encode_2d(CUtensorMap* map, bool tf32, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer) {
@@ -299,18 +470,18 @@ const char* encode_2d(CUtensorMap* map, bool tf32, const void* ptr, uint64_t inn
   return nullptr;
 }
 
-template <int BN_MAX, int STAGES, bool TF32>
+template <int EPI, bool TF32>
 const char* launch_cfg(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& d) {
-  using L = SmemLayout<BN_MAX, STAGES>;
   static bool attr_done = false;
-  auto kern = gemm_tcgen05_kernel<BN_MAX, STAGES, TF32>;
+  auto kern = gemm_tcgen05_kernel<EPI, TF32>;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess)
       return "gemm: cudaFuncSetAttribute(smem) failed";
     attr_done = true;
   }
-  dim3 grid((d.M + BM - 1) / BM, (d.N + d.n_tile - 1) / d.n_tile, 1);
-  kern<<<grid, NUM_THREADS, L::TOTAL, s>>>(ta, tw, d);
+  const int tiles = ((d.M + BM - 1) / BM) * ((d.N + d.n_tile - 1) / d.n_tile);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, NUM_THREADS, SMEM_TOTAL, s>>>(ta, tw, d);
   if (cudaGetLastError() != cudaSuccess) return "gemm: kernel launch failed";
   return nullptr;
 }
@@ -324,20 +495,37 @@ const char* gemm_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
       qres != cudaDriverEntryPointSuccess || fn == nullptr)
     return "gemm: cuTensorMapEncodeTiled entry point not found (driver too old?)";
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return "gemm: device query failed";
+  g_num_sms = prop.multiProcessorCount;
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return nullptr;
 }
+
+bool gemm_ln_fusable(int N) { return N <= BN_MAX && N >= 32 && (N % 32) == 0; }
 
 const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn) {
   if (const char* err = gemm_init()) return err;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
   const bool tf32 = (prec == PREC_TF32);
-  // n_tile: split N evenly over ceil(N / bn_max) tiles, rounded up to the UMMA N granularity (16).
-  int bn_max = force_bn > 0 ? force_bn : (p.N > 128 && (p.N % 128 != 0 || p.N >= 512) ? 256 : 128);
-  if (e.kind == EPI_TAIL) bn_max = force_bn > 0 ? force_bn : 256;
-  const int ntiles = (p.N + bn_max - 1) / bn_max;
-  int n_tile = ((p.N + ntiles - 1) / ntiles + 15) / 16 * 16;
-  if (n_tile > bn_max) n_tile = bn_max;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  int n_tile;
+  if (e.kind == EPI_LN) {
+    if (!gemm_ln_fusable(p.N)) return "gemm: LayerNorm epilogue needs N <= 256 and N % 32 == 0";
+    if (e.ld_f32 != p.N && e.out_f32 != nullptr) return "gemm: LayerNorm epilogue expects dense fp32 rows";
+    n_tile = p.N;
+  } else if (force_bn > 0) {
+    n_tile = force_bn;
+  } else {
+    // widest tile that still gives every SM work; N is split evenly and rounded to the UMMA N granularity (16)
+    int bn = BN_MAX;
+    while (bn > 64 && m_tiles * ((p.N + bn - 1) / bn) < g_num_sms) bn >>= 1;
+    const int ntiles = (p.N + bn - 1) / bn;
+    n_tile = ((p.N + ntiles - 1) / ntiles + 15) / 16 * 16;
+  }
+  if (n_tile > BN_MAX || n_tile < 16 || (n_tile % 16) != 0) return "gemm: bad tile width";
   GemmDev d;
   d.M = p.M; d.N = p.N; d.K = p.K; d.taps = p.taps; d.tap_stride = p.tap_stride; d.row_shift = p.row_shift;
   d.n_tile = n_tile;
@@ -346,12 +534,12 @@ const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const Ge
   const uint32_t box_k = tf32 ? 32 : 64;
   if (const char* err = encode_2d(&ta, tf32, p.A, p.K, p.rowsA, p.lda, box_k, BM)) return err;
   if (const char* err = encode_2d(&tw, tf32, p.W, static_cast<uint64_t>(p.ldw), p.N, p.ldw, box_k, n_tile)) return err;
-  if (bn_max == 128) {
-    return tf32 ? launch_cfg<128, 3, true>(s, ta, tw, d) : launch_cfg<128, 3, false>(s, ta, tw, d);
-  } else if (bn_max == 256) {
-    return tf32 ? launch_cfg<256, 4, true>(s, ta, tw, d) : launch_cfg<256, 4, false>(s, ta, tw, d);
+  switch (e.kind) {
+    case EPI_STD: return tf32 ? launch_cfg<EPI_STD, true>(s, ta, tw, d) : launch_cfg<EPI_STD, false>(s, ta, tw, d);
+    case EPI_TAIL: return tf32 ? launch_cfg<EPI_TAIL, true>(s, ta, tw, d) : launch_cfg<EPI_TAIL, false>(s, ta, tw, d);
+    case EPI_LN: return tf32 ? launch_cfg<EPI_LN, true>(s, ta, tw, d) : launch_cfg<EPI_LN, false>(s, ta, tw, d);
+    default: return "gemm: unknown epilogue";
   }
-  return "gemm: unsupported tile width";
 }
 
 }  // namespace avsep

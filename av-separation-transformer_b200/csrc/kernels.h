@@ -15,7 +15,7 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 //                   the Conv1d zero padding); out row = m, halo rows are written as zeros
 //   ROW_PAD2COMPACT padded space in, compact (B*L) rows out; halo rows are dropped
 enum RowMap { ROW_IDENT = 0, ROW_PAD2PAD = 1, ROW_PAD2COMPACT = 2 };
-enum EpiKind { EPI_STD = 0, EPI_TAIL = 1 };
+enum EpiKind { EPI_STD = 0, EPI_TAIL = 1, EPI_LN = 2 };
 
 struct GemmProblem {
   const void* A;   // [rowsA, K] K-major activations (bf16 or fp32/tf32), leading dimension lda (elements)
@@ -43,6 +43,11 @@ struct GemmEpilogue {
   int ld_f32 = 0;
   void* out_op = nullptr;        // operand-precision output (bf16, or fp32 in the tf32 path) for the next GEMM
   int ld_op = 0;
+  // EPI_LN: value (bias/act/PE/rowmap as above) + resid -> out_f32 (fp32 residual stream, may alias resid), then
+  // LayerNorm(ln_gamma, ln_beta, eps 1e-5) of the full row -> out_op.  ln_gamma == nullptr: out_op = plain cast.
+  const float* resid = nullptr;  // [rows, N] fp32, indexed by the OUTPUT row
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
   // EPI_TAIL (SeparationDecoder head): masks = sigmoid(acc + bias) -> masks[b,s,f,t]; separated = masks * mixed[b,f,t]
   const float* mixed = nullptr;
   float* masks = nullptr;
@@ -53,6 +58,7 @@ struct GemmEpilogue {
 // Returns nullptr on success or a static error string.
 const char* gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
 const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn = 0);
+bool gemm_ln_fusable(int N);   // EPI_LN usable for this row width
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).

@@ -101,6 +101,9 @@ AVSEP_API int avsep_set_debug(avsep_handle* h, int32_t enable);
 /* Copies a snapshot to a HOST buffer of `capacity` floats; returns the element count in *count. Synchronises. */
 AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, size_t capacity, size_t* count);
 
+/* Execution options (A/B testing): "fuse_ln" (default 1) = residual+LayerNorm inside the GEMM epilogue. */
+AVSEP_API int avsep_set_option(avsep_handle* h, const char* name, int32_t value);
+
 /* Per-kernel timing: when enabled every launch of the forward is bracketed by a cudaEvent pair on the launching
  * stream.  avsep_profile_report synchronises and writes one "label launches total_ms" line per kernel class. */
 AVSEP_API int avsep_set_profile(avsep_handle* h, int32_t enable);
@@ -108,6 +111,7 @@ AVSEP_API int avsep_profile_report(avsep_handle* h, char* buf, size_t capacity, 
 
 /* Kernel-level test hooks (DEVICE pointers; used by tests/ to check each kernel against a torch fp32 reference).
  *   gemm: out[M,N] = act(A[M,K] @ W[N,K]^T + bias), A/W in operand precision (bf16 or fp32), out fp32.
+ *   gemm_ln: x += A W^T + bias (fp32, in place); out_op = LayerNorm(x) -- the fused sub-layer epilogue.
  *   conv1d: taps=3 implicit GEMM over a zero-haloed activation: A [B*(L+2), K], W [N, 3*K] (k = tap*K + c),
  *           out fp32 [B*L, N] (ROW_PAD2COMPACT).
  *   attention: q [B*Lq, H*hd], k/v [B*Lk, H*hd] bf16 (lerp_src = 0) or fp32 [B*lerp_src, H*hd] (lerp on load).
@@ -115,6 +119,9 @@ AVSEP_API int avsep_profile_report(avsep_handle* h, char* buf, size_t capacity, 
  *   visual_cnn: frames (M,Hh,Ww) -> pooled (M,128) operand precision, using the handle's conv weights. */
 AVSEP_API int avsep_test_gemm(avsep_handle* h, const void* A, const void* W, const float* bias, float* out, int32_t M, int32_t N,
                     int32_t K, int32_t act, int32_t force_bn, void* cuda_stream);
+AVSEP_API int avsep_test_gemm_ln(avsep_handle* h, const void* A, const void* W, const float* bias, float* x_inout,
+                                 const float* gamma, const float* beta, void* out_op, int32_t M, int32_t N, int32_t K,
+                                 void* cuda_stream);
 AVSEP_API int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
                       int32_t L, int32_t N, int32_t K, void* cuda_stream);
 AVSEP_API int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,

@@ -56,6 +56,32 @@ def test_gemm_tcgen05(eng, M, N, K, act, bn):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (16128, 256, 1024), (77, 64, 64), (300, 128, 512), (130, 32, 64)])
+def test_gemm_fused_residual_layernorm(eng, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g) * 2 + 0.5
+    gamma = torch.randn(N, device="cuda", generator=g)
+    beta = torch.randn(N, device="cuda", generator=g)
+    x_ref = x + A.float() @ W.float().t() + bias
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-5)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    _check(eng, eng.lib.avsep_test_gemm_ln(eng.h, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                           gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), M, N, K, _s()))
+    torch.cuda.synchronize()
+    assert (x - x_ref).abs().max().item() < 2e-3
+    assert (out.float() - ln_ref).abs().max().item() < 5e-2
+    assert (out.float() - ln_ref).abs().mean().item() < 4e-3
+    # cast-only variant (gamma = None): out_op = bf16(x)
+    x2 = x_ref.clone()
+    _check(eng, eng.lib.avsep_test_gemm_ln(eng.h, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x2.data_ptr(),
+                                           None, None, out.data_ptr(), M, N, K, _s()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, x2.bfloat16())
+
+
 @pytest.mark.parametrize("B,L,N,K", [(2, 63, 256, 264), (3, 32, 64, 72), (1, 300, 256, 256), (5, 7, 64, 64)])
 def test_conv1d_implicit_gemm(eng, B, L, N, K):
     g = torch.Generator(device="cuda").manual_seed(B + L + N + K)
