@@ -88,6 +88,8 @@ struct avsep_handle {
   const float *bc1 = nullptr, *bc2 = nullptr, *bproj = nullptr, *bkv_all = nullptr, *bdec0 = nullptr, *bdec3 = nullptr;
   const float *pe_a = nullptr, *pe_v = nullptr, *fng = nullptr, *fnb = nullptr;
   CnnWeights cnn{};
+  const uint8_t *cnn_w2_slabs = nullptr, *cnn_w3_rows = nullptr;   // tcgen05 CNN operands
+  bool cnn_tc = true;     // tensor-core (tcgen05) CNN for 32x32 frames on the bf16 path
   std::vector<EncLayerW> enc_a, enc_v;
   std::vector<FusLayerW> fus;
   // cached library-owned workspace
@@ -235,6 +237,12 @@ int snapshot(avsep_handle* h, cudaStream_t s, const char* name, const void* ptr,
 }
 
 // ---- stage helpers -----------------------------------------------------------------------------
+const char* run_visual_cnn(avsep_handle* h, cudaStream_t s, const float* frames, int M, int Hh, int Ww, void* pooled) {
+  if (h->cnn_tc && Hh == 32 && Ww == 32 && h->cfg.precision == AVSEP_PREC_BF16)
+    return launch_visual_cnn_tc(s, frames, M, h->cnn, h->cnn_w2_slabs, h->cnn_w3_rows, pooled, h->num_sms);
+  return launch_visual_cnn(s, h->cfg.precision, frames, M, Hh, Ww, h->cnn, pooled, h->num_sms);
+}
+
 int linear(avsep_handle* h, cudaStream_t s, const char* label, const void* A, int M, int K, const void* W,
            const float* bias, int N, int act, float* out_f32, void* out_op) {
   GemmProblem p{};
@@ -347,9 +355,9 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
 // first layer's LayerNorm: x_v (fp32) and v_op = LN_{g,b}(x_v).
 int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames, const float* g, const float* b) {
   h->prof_stream = s;
-  const int d = h->cfg.d_model, B = w.B, N = w.N, prec = h->cfg.precision;
+  const int d = h->cfg.d_model, B = w.B, N = w.N;
   const int Mv = B * N;
-  CKL("visual_cnn", launch_visual_cnn(s, prec, frames, Mv, w.Hh, w.Ww, h->cnn, w.pooled, h->num_sms));
+  CKL("visual_cnn", run_visual_cnn(h, s, frames, Mv, w.Hh, w.Ww, w.pooled));
   if (snapshot(h, s, "visual_pool", w.pooled, static_cast<size_t>(Mv) * 128, true)) return 1;
   GemmProblem p{};
   p.A = w.pooled; p.lda = 128; p.rowsA = Mv; p.M = Mv; p.W = h->wproj; p.ldw = 128; p.N = d; p.K = 128;
@@ -630,6 +638,10 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     }
     std::vector<uint32_t> p1(visual_cnn_pack_sizes(1)), p2(visual_cnn_pack_sizes(2)), p3(visual_cnn_pack_sizes(3));
     visual_cnn_pack(folded[0].data(), folded[1].data(), folded[2].data(), p1.data(), p2.data(), p3.data());
+    std::vector<uint8_t> tc2(visual_cnn_tc_w2_bytes()), tc3(visual_cnn_tc_w3_bytes());
+    visual_cnn_tc_pack(folded[1].data(), folded[2].data(), tc2.data(), tc3.data());
+    off["tcw2"] = ar.add(tc2.data(), tc2.size());
+    off["tcw3"] = ar.add(tc3.data(), tc3.size());
     off["cw1"] = ar.add(p1.data(), p1.size() * 4);
     off["cw2"] = ar.add(p2.data(), p2.size() * 4);
     off["cw3"] = ar.add(p3.data(), p3.size() * 4);
@@ -710,6 +722,8 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->cnn.w1 = reinterpret_cast<const uint32_t*>(P("cw1")); h->cnn.b1 = PF("cb1");
   h->cnn.w2 = reinterpret_cast<const uint32_t*>(P("cw2")); h->cnn.b2 = PF("cb2");
   h->cnn.w3 = reinterpret_cast<const uint32_t*>(P("cw3")); h->cnn.b3 = PF("cb3");
+  h->cnn_w2_slabs = static_cast<const uint8_t*>(P("tcw2"));
+  h->cnn_w3_rows = static_cast<const uint8_t*>(P("tcw3"));
   h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();
   for (int stack = 0; stack < 2; ++stack)
     for (int l = 0; l < Le; ++l) {
@@ -987,6 +1001,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
+  if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   return fail(h, std::string("unknown option ") + name);
 }
 
@@ -1024,8 +1039,7 @@ int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_t M, int32
                           void* cuda_stream) {
   if (!h) return 1;
   if (!h->finalized) return fail(h, "weights not finalized");
-  CK(launch_visual_cnn(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, frames, M, Hh, Ww, h->cnn, pooled,
-                       h->num_sms));
+  CK(run_visual_cnn(h, static_cast<cudaStream_t>(cuda_stream), frames, M, Hh, Ww, pooled));
   return 0;
 }
 

@@ -86,6 +86,12 @@ struct CnnWeights {                // BN-folded, fragment-ordered (see visual_cn
 // frames (M,H,W) fp32 -> pooled (M,128) operand precision
 const char* launch_visual_cnn(cudaStream_t s, int prec, const float* frames, int M, int H, int W, const CnnWeights& w,
                               void* pooled, int num_sms);
+// tcgen05 fast path for 32x32 frames, bf16 (visual_cnn_tc.cu)
+size_t visual_cnn_tc_w2_bytes();
+size_t visual_cnn_tc_w3_bytes();
+void visual_cnn_tc_pack(const float* w2, const float* w3, uint8_t* w2_slabs, uint8_t* w3_rows);
+const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
+                                 const uint8_t* w3_rows, void* pooled, int num_sms);
 size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint32)
 void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3);
 

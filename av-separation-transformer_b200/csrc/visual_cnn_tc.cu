@@ -1,0 +1,385 @@
+// VisualEncoder.conv (model.py:81-92,106-107) for 32x32 frames on the 5th-gen tensor cores.
+//
+// One persistent CTA per SM walks groups of 8 frames.  Per group:
+//   for each pair of frames:
+//     conv1 (K = 9 taps, tensor cores via mma.sync, 3 % of the FLOPs)        -> act1 (bf16, smem, 16x16x32 / frame)
+//     conv2 as an implicit GEMM  M = 128 (2 frames x 64 px), N = 64, K = 9x32:
+//       im2col slabs [128 rows x 128 B] (two taps each) are gathered from act1 into a 2-slot ring in the canonical
+//       K-major 128B-swizzle layout, tcgen05.mma accumulates all 18 k-steps in TMEM; the ring lets the gather of
+//       slab j+1 overlap the MMAs of slab j.  Epilogue: tcgen05.ld -> bias(BN-folded)+ReLU -> act2 (bf16, smem)
+//   conv3 as an implicit GEMM  M = 128 (8 frames x 16 px), N = 128, K = 9x64: one slab per tap gathered from act2,
+//       the matching 16 KB weight slab streamed by TMA (3-slot ring, L2-resident), 36 tcgen05.mma k-steps;
+//       epilogue: tcgen05.ld -> bias+ReLU -> 16-pixel mean by warp shuffles -> pooled (M,128) bf16.
+// BatchNorm (eval) is folded into weights/bias on the host.  Nothing but the 4 KB frame and the 256 B feature row
+// touches HBM.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace avsep {
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int GROUP = 8;                 // frames per conv3 tile
+constexpr int SLAB_BYTES = 128 * 128;    // 128 rows x 128 B
+constexpr int W2_SLABS = 5, W2_SLAB_BYTES = 64 * 128;
+// shared memory map (bytes, all tensor-core regions 1024-aligned)
+constexpr int OFF_RING = 0;                               // 2 x 16 KB  im2col ring (A operand)
+constexpr int OFF_W3 = OFF_RING + 2 * SLAB_BYTES;         // 3 x 16 KB  conv3 weight slabs (TMA)
+constexpr int OFF_W2 = OFF_W3 + 3 * SLAB_BYTES;           // 5 x 8 KB   conv2 weight slabs (resident)
+constexpr int OFF_ACT2 = OFF_W2 + W2_SLABS * W2_SLAB_BYTES;   // 8 frames x 64 px x 128 B
+constexpr int OFF_ACT1 = OFF_ACT2 + GROUP * 64 * 128;     // 2 frames x 256 px x 64 B
+constexpr int OFF_IN = OFF_ACT1 + 2 * 256 * 64;           // 2 frames x 34 x 34 fp32
+constexpr int OFF_MISC = OFF_IN + 2 * 34 * 34 * 4;        // barriers, TMEM slot
+constexpr int TC_SMEM = OFF_MISC + 128 + 1024;            // + alignment slack (<= 227 KB)
+static_assert(TC_SMEM <= 227 * 1024, "visual_cnn_tc: shared memory budget exceeded");
+
+struct CnnTcDev {
+  const float* frames;
+  __nv_bfloat16* pooled;
+  const uint32_t* w1; const float* b1;
+  const uint8_t* w2_slabs; const float* b2;
+  const float* b3;
+  int M, num_groups;
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// act1: 2 pixels per 128-byte line, 16-byte chunk slot XOR-swizzled by the line index.
+__device__ __forceinline__ int act1_chunk_off(int pixel, int c) {   // pixel = f*256 + y*16 + x, c = 8-channel chunk 0..3
+  const int line = pixel >> 1;
+  return line * 128 + ((((pixel & 1) << 2) | c) ^ (line & 7)) * 16;
+}
+// act2: one pixel (64 ch) per 128-byte line, chunk slot XOR-swizzled by the pixel index.
+__device__ __forceinline__ int act2_chunk_off(int pixel, int c) {   // pixel = g*64 + y*8 + x, c = 0..7
+  return pixel * 128 + ((c ^ (pixel & 7)) * 16);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p) {
+  extern __shared__ uint8_t smem_raw_cnn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_cnn) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem + OFF_RING;
+  uint8_t* w3s = smem + OFF_W3;
+  uint8_t* w2s = smem + OFF_W2;
+  uint8_t* act2 = smem + OFF_ACT2;
+  uint8_t* act1 = smem + OFF_ACT1;
+  float* sIn = reinterpret_cast<float*>(smem + OFF_IN);
+  uint64_t* bar_ring = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [2] MMAs that read ring slot s have completed
+  uint64_t* bar_acc = bar_ring + 2;                               // accumulator complete
+  uint64_t* bar_w3 = bar_acc + 1;                                 // [3] W3 slab landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w3 + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+
+  for (int i = tid; i < W2_SLABS * W2_SLAB_BYTES / 16; i += TC_THREADS)
+    reinterpret_cast<uint4*>(w2s)[i] = reinterpret_cast<const uint4*>(p.w2_slabs)[i];
+  for (int i = tid; i < 2 * 34 * 34; i += TC_THREADS) sIn[i] = 0.f;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmW3);
+    mbar_init(&bar_ring[0], 1);
+    mbar_init(&bar_ring[1], 1);
+    mbar_init(bar_acc, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&bar_w3[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();     // W2 slabs were written with generic stores, read by the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc2 = tmem_base;          // 64 columns
+  const uint32_t tmem_acc3 = tmem_base + 64;     // 128 columns
+  const uint32_t idesc2 = umma_idesc(1u, 128, 64);
+  const uint32_t idesc3 = umma_idesc(1u, 128, 128);
+
+  uint32_t n_slab = 0;      // slabs pushed through the ring so far (all threads keep the same count)
+  uint32_t acc_phase = 0;
+  uint32_t n_w3 = 0;        // W3 slabs consumed so far
+
+  // conv1 B fragments and bias (constant, registers)
+  uint32_t bw1[4][2];
+  float bias1[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bw1[nt][0] = __ldg(p.w1 + nt * 64 + lane * 2);
+    bw1[nt][1] = __ldg(p.w1 + nt * 64 + lane * 2 + 1);
+    bias1[nt][0] = __ldg(p.b1 + nt * 8 + 2 * tig);
+    bias1[nt][1] = __ldg(p.b1 + nt * 8 + 2 * tig + 1);
+  }
+  const int k0 = 2 * tig, k1 = 2 * tig + 1;
+  const int off0 = (k0 / 3) * 34 + (k0 % 3), off1 = (k1 / 3) * 34 + (k1 % 3), off8 = 2 * 34 + 2;
+
+  for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+    const int frame0 = grp * GROUP;
+    // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
+    if (tid == 0) {
+      for (int t = 0; t < 3; ++t) {
+        const uint32_t slot = (n_w3 + t) % 3;
+        mbar_arrive_expect_tx(&bar_w3[slot], SLAB_BYTES);
+        tma_load_2d(w3s + slot * SLAB_BYTES, &tmW3, &bar_w3[slot], 0, t * 128);
+      }
+    }
+
+    for (int pair = 0; pair < GROUP / 2; ++pair) {
+      // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) ----
+      for (int i = tid; i < 2 * 256; i += TC_THREADS) {     // one float4 per thread-iteration: 2 frames x 1024 px
+        const int f = i >> 8, rem = i & 255;
+        const int y = rem >> 3, x4 = (rem & 7) * 4;
+        const int fr = frame0 + pair * 2 + f;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fr < p.M) v = __ldg(reinterpret_cast<const float4*>(p.frames + static_cast<size_t>(fr) * 1024 + y * 32 + x4));
+        float* d = sIn + f * 34 * 34 + (y + 1) * 34 + (x4 + 1);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+      __syncthreads();
+
+      // ---- conv1: rows = 2 x 256 output pixels, K = 9 (padded to 16), N = 32 ----
+      for (int t = warp; t < 32; t += TC_THREADS / 32) {
+        uint32_t a[4] = {0, 0, 0, 0};
+        int pix[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int r = t * 16 + gid + 8 * hf;
+          const int f = r >> 8, rem = r & 255, y = rem >> 4, x = rem & 15;
+          pix[hf] = r;
+          const float* base = sIn + f * 34 * 34 + (2 * y) * 34 + 2 * x;
+          a[hf] = pack_bf16x2(base[off0], base[off1]);
+          if (tig == 0) a[2 + hf] = pack_bf16x2(base[off8], 0.f);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(c, a[0], a[1], a[2], a[3], bw1[nt][0], bw1[nt][1]);
+          const float bb0 = bias1[nt][0], bb1 = bias1[nt][1];
+          *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[0], nt) + tig * 4) =
+              pack_bf16x2(fmaxf(c[0] + bb0, 0.f), fmaxf(c[1] + bb1, 0.f));
+          *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[1], nt) + tig * 4) =
+              pack_bf16x2(fmaxf(c[2] + bb0, 0.f), fmaxf(c[3] + bb1, 0.f));
+        }
+      }
+      __syncthreads();
+
+      // ---- conv2: 5 slabs of two taps ----
+      for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+        const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+        if (use > 0) mbar_wait(&bar_ring[slot], (use - 1) & 1);
+        uint8_t* slab = ring + slot * SLAB_BYTES;
+        // 128 rows x 8 chunks; 8 consecutive lanes fill one row (conflict-free), 4 rows per thread
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int id = tid + TC_THREADS * i;
+          const int r = id >> 3, c = id & 7;
+          const int tap = 2 * j + (c >> 2);
+          uint4 val = make_uint4(0, 0, 0, 0);
+          if (tap < 9) {
+            const int f = r >> 6, y2 = (r >> 3) & 7, x2 = r & 7;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int yy = 2 * y2 + ky - 1, xx = 2 * x2 + kx - 1;
+            if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16)
+              val = *reinterpret_cast<const uint4*>(act1 + act1_chunk_off(f * 256 + yy * 16 + xx, c & 3));
+          }
+          *reinterpret_cast<uint4*>(slab + r * 128 + ((c ^ (r & 7)) * 16)) = val;
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(slab), 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w2s + j * W2_SLAB_BYTES), 1024);
+          const int ksteps = (j == W2_SLABS - 1) ? 2 : 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(tmem_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
+          umma_commit(&bar_ring[slot]);
+          if (j == W2_SLABS - 1) umma_commit(bar_acc);
+        }
+      }
+      // ---- conv2 epilogue: acc (128 px x 64 ch) -> bias + ReLU -> act2 ----
+      mbar_wait(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      {
+        const int q = warp & 3, hh = warp >> 2;              // lane quarter, 32-column half
+        const int r = q * 32 + lane;                          // row = (f, y2, x2) of this pair
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_acc2 + (static_cast<uint32_t>(q * 32) << 16) + hh * 32, v);
+        tmem_ld_wait();
+        const int pixel = pair * 128 + r;                     // pixel index inside the 8-frame act2 block
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8));
+          const float4 bc = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8 + 4));
+          u.x = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 1]) + ba.y, 0.f));
+          u.y = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 3]) + ba.w, 0.f));
+          u.z = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 4]) + bc.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 5]) + bc.y, 0.f));
+          u.w = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 6]) + bc.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 7]) + bc.w, 0.f));
+          *reinterpret_cast<uint4*>(act2 + act2_chunk_off(pixel, hh * 4 + c)) = u;
+        }
+      }
+      tc_fence_before();
+      __syncthreads();     // act2 rows of this pair visible; acc2 drained; sIn/act1 reusable
+    }
+
+    // ---- conv3: one slab per tap, weights streamed by TMA ----
+    for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
+      const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+      if (use > 0) mbar_wait(&bar_ring[slot], (use - 1) & 1);
+      // the MMAs of tap t-2 have completed -> its W3 slot is free: refill it with tap t+1's slab (t+1 >= 3)
+      if (tid == 0 && t >= 2 && t + 1 < 9) {
+        const uint32_t ws = (n_w3 + 1) % 3;
+        mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
+        tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, (t + 1) * 128);
+      }
+      uint8_t* slab = ring + slot * SLAB_BYTES;
+      const int ky = t / 3, kx = t - ky * 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int id = tid + TC_THREADS * i;
+        const int r = id >> 3, c = id & 7;
+        const int g = r >> 4, y3 = (r >> 2) & 3, x3 = r & 3;
+        const int yy = 2 * y3 + ky - 1, xx = 2 * x3 + kx - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8)
+          val = *reinterpret_cast<const uint4*>(act2 + act2_chunk_off(g * 64 + yy * 8 + xx, c));
+        *reinterpret_cast<uint4*>(slab + r * 128 + ((c ^ (r & 7)) * 16)) = val;
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t ws = n_w3 % 3;
+        mbar_wait(&bar_w3[ws], (n_w3 / 3) & 1);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(slab), 1024);
+        const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, adesc + 2 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
+        umma_commit(&bar_ring[slot]);
+        if (t == 8) umma_commit(bar_acc);
+      }
+    }
+    // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
+    mbar_wait(bar_acc, acc_phase);
+    acc_phase ^= 1;
+    tc_fence_after();
+    {
+      const int q = warp & 3, hh = warp >> 2;                  // lane quarter (2 frames), 64-column half
+      const int fr = frame0 + q * 2 + (lane >> 4);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t v[32];
+        const int col0 = hh * 64 + cc * 32;
+        tmem_ld_32x32b_x32(tmem_acc3 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
+        tmem_ld_wait();
+        float keep0 = 0.f, keep1 = 0.f;
+#pragma unroll
+        for (int jx = 0; jx < 32; ++jx) {
+          float sv = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 8);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+          sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+          if ((lane & 15) == (jx & 15)) {       // lane l of each 16-lane half keeps columns l and 16 + l
+            if (jx < 16) keep0 = sv; else keep1 = sv;
+          }
+        }
+        if (fr < p.M) {
+          __nv_bfloat16* o = p.pooled + static_cast<size_t>(fr) * 128 + col0 + (lane & 15);
+          o[0] = __float2bfloat16_rn(keep0 * (1.f / 16.f));
+          o[16] = __float2bfloat16_rn(keep1 * (1.f / 16.f));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+inline uint16_t f2bf_tc(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+}  // namespace
+
+size_t visual_cnn_tc_w2_bytes() { return W2_SLABS * W2_SLAB_BYTES; }
+size_t visual_cnn_tc_w3_bytes() { return 9 * SLAB_BYTES; }
+
+// w2 [64][9*32], w3 [128][9*64] fp32, BN-folded, K index = tap*Cin + c  ->
+//   w2_slabs: 5 slabs [64 rows][64 k] bf16, k = (tap&1)*32 + c of taps (2j, 2j+1), 128B-swizzled (chunk ^= row&7)
+//   w3_rows : [9 taps][128 rows][64 k] bf16 row-major (TMA applies the swizzle)
+void visual_cnn_tc_pack(const float* w2, const float* w3, uint8_t* w2_slabs, uint8_t* w3_rows) {
+  memset(w2_slabs, 0, visual_cnn_tc_w2_bytes());
+  for (int j = 0; j < W2_SLABS; ++j)
+    for (int n = 0; n < 64; ++n)
+      for (int k = 0; k < 64; ++k) {
+        const int tap = 2 * j + (k >> 5), c = k & 31;
+        const float val = tap < 9 ? w2[static_cast<size_t>(n) * 288 + tap * 32 + c] : 0.f;
+        const int chunk = (k >> 3) ^ (n & 7);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(w2_slabs + j * W2_SLAB_BYTES + n * 128 + chunk * 16) + (k & 7);
+        *dst = f2bf_tc(val);
+      }
+  uint16_t* o = reinterpret_cast<uint16_t*>(w3_rows);
+  for (int t = 0; t < 9; ++t)
+    for (int n = 0; n < 128; ++n)
+      for (int c = 0; c < 64; ++c) o[(static_cast<size_t>(t) * 128 + n) * 64 + c] = f2bf_tc(w3[static_cast<size_t>(n) * 576 + t * 64 + c]);
+}
+
+const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
+                                 const uint8_t* w3_rows, void* pooled, int num_sms) {
+  if (M <= 0) return "visual_cnn_tc: empty problem";
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      return "visual_cnn_tc: cuTensorMapEncodeTiled entry point not found";
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {64, 9 * 128};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  if (encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint8_t*>(w3_rows), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return "visual_cnn_tc: cuTensorMapEncodeTiled failed";
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(visual_cnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess)
+      return "visual_cnn_tc: cudaFuncSetAttribute failed";
+    attr_done = true;
+  }
+  CnnTcDev d;
+  d.frames = frames; d.pooled = reinterpret_cast<__nv_bfloat16*>(pooled);
+  d.w1 = w.w1; d.b1 = w.b1; d.w2_slabs = w2_slabs; d.b2 = w.b2; d.b3 = w.b3;
+  d.M = M; d.num_groups = (M + GROUP - 1) / GROUP;
+  const int grid = d.num_groups < num_sms ? d.num_groups : num_sms;
+  visual_cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, d);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "visual_cnn_tc: launch failed";
+}
+
+}  // namespace avsep

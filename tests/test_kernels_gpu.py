@@ -163,8 +163,9 @@ def test_add_layernorm(eng, M, d):
     assert torch.equal(out2, x.bfloat16())
 
 
-@pytest.mark.parametrize("Hh,Ww,M", [(32, 32, 50), (16, 16, 21), (15, 18, 7), (32, 32, 601)])
-def test_visual_cnn(Hh, Ww, M):
+@pytest.mark.parametrize("Hh,Ww,M,tc", [(32, 32, 50, 1), (32, 32, 8, 1), (32, 32, 1203, 1), (32, 32, 50, 0), (16, 16, 21, 0),
+                                         (15, 18, 7, 0), (32, 32, 601, 0)])
+def test_visual_cnn(Hh, Ww, M, tc):
     from oracle.weights import CONFIGS, make_state_dict
     from avsep_b200.engine import Engine, EngineConfig
     cfg = CONFIGS["tiny"]
@@ -172,6 +173,7 @@ def test_visual_cnn(Hh, Ww, M):
     e = Engine(EngineConfig(**cfg.as_dict()), 0)
     try:
         e.load_state({k: v for k, v in P.items() if v.ndim > 0})
+        e.set_option("cnn_tc", tc)      # 1: tcgen05 kernel (32x32 only), 0: generic mma.sync kernel
         g = torch.Generator(device="cuda").manual_seed(M)
         frames = torch.rand(M, Hh, Ww, device="cuda", generator=g)
         pooled = torch.zeros(M, 128, device="cuda", dtype=torch.bfloat16)
