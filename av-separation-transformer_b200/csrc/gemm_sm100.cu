@@ -42,7 +42,8 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
 constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][2 halves] float2
-constexpr int SMEM_TOTAL = RED_OFFSET + 2 * 128 * 2 * 8 + 1024;
+constexpr int VEC_OFFSET = RED_OFFSET + 2 * 128 * 2 * 8;   // bias [2][256], gamma [256], beta [256] fp32
+constexpr int SMEM_TOTAL = VEC_OFFSET + 4 * BN_MAX * 4 + 1024;
 constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator stages
 
 struct GemmDev {
@@ -50,14 +51,27 @@ struct GemmDev {
   GemmEpilogue e;
 };
 
+// 32-byte (full-sector) global store: one request per thread writes a whole sector of its row.
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+__device__ __forceinline__ void store_f32_chunk(float* o, const float (&val)[32]) {   // 32 fp32, 32-byte aligned
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    st_global_v8(o + j, __float_as_uint(val[j]), __float_as_uint(val[j + 1]), __float_as_uint(val[j + 2]),
+                 __float_as_uint(val[j + 3]), __float_as_uint(val[j + 4]), __float_as_uint(val[j + 5]),
+                 __float_as_uint(val[j + 6]), __float_as_uint(val[j + 7]));
+}
+
 template <bool TF32>
 __device__ __forceinline__ void store_op_chunk(void* out_op, size_t off, const float (&val)[32], int ncols, bool vec) {
   if constexpr (TF32) {
     float* o = reinterpret_cast<float*>(out_op) + off;
     if (vec) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(o + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+      store_f32_chunk(o, val);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -67,14 +81,11 @@ __device__ __forceinline__ void store_op_chunk(void* out_op, size_t off, const f
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_op) + off;
     if (vec) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(val[j], val[j + 1]);
-        u.y = pack_bf16x2(val[j + 2], val[j + 3]);
-        u.z = pack_bf16x2(val[j + 4], val[j + 5]);
-        u.w = pack_bf16x2(val[j + 6], val[j + 7]);
-        *reinterpret_cast<uint4*>(o + j) = u;
-      }
+      for (int j = 0; j < 32; j += 16)
+        st_global_v8(o + j, pack_bf16x2(val[j], val[j + 1]), pack_bf16x2(val[j + 2], val[j + 3]),
+                     pack_bf16x2(val[j + 4], val[j + 5]), pack_bf16x2(val[j + 6], val[j + 7]),
+                     pack_bf16x2(val[j + 8], val[j + 9]), pack_bf16x2(val[j + 10], val[j + 11]),
+                     pack_bf16x2(val[j + 12], val[j + 13]), pack_bf16x2(val[j + 14], val[j + 15]));
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -112,24 +123,24 @@ __device__ __forceinline__ RowInfo row_info(const GemmEpilogue& e, int m, int M)
   return r;
 }
 
-// acc chunk -> value chunk: + bias, activation, + PE, halo zeroing.
+// acc chunk -> value chunk: (+ prior contents when ACCUM) + bias (shared memory), activation, + PE, halo zeroing.
+template <bool ACCUM>
 __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo& ri, const uint32_t (&v)[32],
-                                            float (&val)[32], int col0, int ncols, int N) {
+                                            float (&val)[32], const float* sbias_c0, int col0, int ncols, int N) {
   const bool full = (ncols == 32);
-  if (full && e.bias != nullptr && (N & 3) == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + j));
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sbias_c0 + j);     // zero beyond N
+    if constexpr (ACCUM) {
+      val[j] += __uint_as_float(v[j]) + b4.x;
+      val[j + 1] += __uint_as_float(v[j + 1]) + b4.y;
+      val[j + 2] += __uint_as_float(v[j + 2]) + b4.z;
+      val[j + 3] += __uint_as_float(v[j + 3]) + b4.w;
+    } else {
       val[j] = __uint_as_float(v[j]) + b4.x;
       val[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
       val[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
       val[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float bj = (e.bias != nullptr && j < ncols) ? __ldg(e.bias + col0 + j) : 0.0f;
-      val[j] = __uint_as_float(v[j]) + bj;
     }
   }
   if (e.act == ACT_RELU) {
@@ -170,6 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator stage drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* red = reinterpret_cast<float2*>(smem + RED_OFFSET);
+  float* sbias = reinterpret_cast<float*>(smem + VEC_OFFSET);       // [2][BN_MAX], double-buffered per tile
+  float* sgamma = sbias + 2 * BN_MAX;
+  float* sbeta = sgamma + BN_MAX;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,6 +210,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if constexpr (EPI == EPI_LN) {
+    if (p.e.ln_gamma != nullptr) {
+      for (int i = threadIdx.x; i < p.n_tile; i += NUM_THREADS) {
+        sgamma[i] = __ldg(p.e.ln_gamma + i);
+        sbeta[i] = __ldg(p.e.ln_beta + i);
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -267,52 +289,59 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = (tile % m_tiles) * BM;
       const int n0 = (tile / m_tiles) * p.n_tile;
       const int m = m0 + r;
+      // stage this tile's bias slice in shared memory while the main loop is still running
+      float* sb = sbias + (lt & 1) * BN_MAX;
+      {
+        const int i = threadIdx.x - 64;                       // 0..255 over the 8 epilogue warps
+        sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 5, 256;" ::: "memory");            // bias slice visible to all epilogue warps
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN_MAX);
 
       if constexpr (EPI == EPI_TAIL) {
-        // SeparationDecoder head (model.py:204-207,220): column c = s*F + f; lanes are consecutive t, so the
-        // (B,S,F,T) stores and the mixed_spec (B,F,T) loads are both contiguous across the warp.
+        // SeparationDecoder head (model.py:204-207,220): column c = s*F + f, so masks[b,s,f,t] sits at
+        // ((b*S*F + c)*T + t); lanes are consecutive t, so the (B,S,F,T) stores and the mixed_spec (B,F,T) loads are
+        // both contiguous across the warp.
         const bool valid = m < p.M;
         const int tb = m / e.T;
         const int tt = m - tb * e.T;
         const float* mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
+        const size_t out_base = static_cast<size_t>(tb) * e.S * e.F * e.T + tt;
         for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
           const int col0 = n0 + c0;
           if (col0 >= p.N) break;                      // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
           const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
-          const int s0 = col0 / e.F;
-          const int f0 = col0 - s0 * e.F;
+          int f = col0 % e.F;
           float mx[32];
           if (valid) {                                 // all mixed_spec loads in flight before any store
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              int f = f0 + j;
-              while (f >= e.F) f -= e.F;
               mx[j] = (j < ncols) ? __ldg(mixed_row + static_cast<size_t>(f) * e.T) : 0.f;
+              if (++f == e.F) f = 0;
             }
           }
           tmem_ld_wait();
           if (valid) {
-            int s = s0, f = f0;
+            float* mo = e.masks + out_base + static_cast<size_t>(col0) * e.T;
+            float* so = e.separated + out_base + static_cast<size_t>(col0) * e.T;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < ncols) {
-                const float z = __uint_as_float(v[j]) + __ldg(e.bias + col0 + j);
-                const float mk = 1.0f / (1.0f + __expf(-z));
-                const size_t o = ((static_cast<size_t>(tb) * e.S + s) * e.F + f) * e.T + tt;
-                __stcs(e.masks + o, mk);
-                __stcs(e.separated + o, mk * mx[j]);
-                if (++f == e.F) { f = 0; ++s; }
+                const float z = __uint_as_float(v[j]) + sb[c0 + j];
+                const float mk = __fdividef(1.0f, 1.0f + __expf(-z));
+                __stcs(mo + static_cast<size_t>(j) * e.T, mk);
+                __stcs(so + static_cast<size_t>(j) * e.T, mk * mx[j]);
               }
             }
           }
         }
       } else if constexpr (EPI == EPI_LN) {
-        // bias/act/PE value, + residual, fp32 residual-stream store, LayerNorm over the whole row, operand store.
+        // value = acc + bias (+act, +PE) + residual (already in val_ln), fp32 residual-stream store, LayerNorm over
+        // the whole row, operand store.
         const RowInfo ri = row_info(e, m, p.M);
         float val[4][32];
         float sum = 0.f;
@@ -324,24 +353,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
             tmem_ld_wait();
-            value_chunk(e, ri, v, val[ci], c0, 32, p.N);
-            if (ri.valid) {
-              if (e.resid != nullptr) {
-                const float4* rp = reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(ri.orow) * p.N + c0);
+            value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
+            if (ri.valid && e.resid != nullptr) {       // residual stream: written by the previous GEMM, L2-resident
+              const float4* rp = reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(ri.orow) * p.N + c0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 x4 = rp[j];
-                  val[ci][4 * j] += x4.x; val[ci][4 * j + 1] += x4.y;
-                  val[ci][4 * j + 2] += x4.z; val[ci][4 * j + 3] += x4.w;
-                }
-              }
-              if (e.out_f32 != nullptr) {
-                float4* op = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + c0);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  op[j] = make_float4(val[ci][4 * j], val[ci][4 * j + 1], val[ci][4 * j + 2], val[ci][4 * j + 3]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 x4 = rp[j];
+                val[ci][4 * j] += x4.x; val[ci][4 * j + 1] += x4.y;
+                val[ci][4 * j + 2] += x4.z; val[ci][4 * j + 3] += x4.w;
               }
             }
+            if (ri.valid && e.out_f32 != nullptr)
+              store_f32_chunk(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + c0, val[ci]);
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum += val[ci][j];
             cnt += 32;
@@ -382,8 +405,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (c0 < p.n_tile) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + c0 + j));
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + c0 + j));
+                const float4 g4 = *reinterpret_cast<const float4*>(sgamma + c0 + j);
+                const float4 b4 = *reinterpret_cast<const float4*>(sbeta + c0 + j);
                 val[ci][j] = (val[ci][j] - mean) * rstd * g4.x + b4.x;
                 val[ci][j + 1] = (val[ci][j + 1] - mean) * rstd * g4.y + b4.y;
                 val[ci][j + 2] = (val[ci][j + 2] - mean) * rstd * g4.z + b4.z;
@@ -412,14 +435,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
           if (!ri.valid) continue;
           float val[32];
-          value_chunk(e, ri, v, val, col0, ncols, p.N);
+          value_chunk<false>(e, ri, v, val, sb + c0, col0, ncols, p.N);
           const bool full = (ncols == 32);
           if (e.out_f32 != nullptr) {
             float* o = e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + col0;
-            if (full && (e.ld_f32 & 3) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+            if (full && (e.ld_f32 & 7) == 0) {
+              store_f32_chunk(o, val);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -427,7 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (e.out_op != nullptr) {
-            const bool vec = full && ((e.ld_op & 7) == 0);
+            const bool vec = full && ((e.ld_op & 15) == 0);
             store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + col0, val, ncols, vec);
           }
         }

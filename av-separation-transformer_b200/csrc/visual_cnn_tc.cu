@@ -121,6 +121,46 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   const int k0 = 2 * tig, k1 = 2 * tig + 1;
   const int off0 = (k0 / 3) * 34 + (k0 % 3), off1 = (k1 / 3) * 34 + (k1 % 3), off8 = 2 * 34 + 2;
 
+  // Input prefetch: each thread keeps the next pair's two float4 pieces (2 frames x 1024 px / 256 threads) in
+  // registers, so the global-load latency hides behind the current pair's conv1/conv2.
+  float4 pre[2];
+  auto prefetch_pair = [&](int first_frame) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int id = tid + TC_THREADS * i;
+      const int f = id >> 8, rem = id & 255;
+      const int fr = first_frame + f;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fr < p.M) pre[i] = __ldg(reinterpret_cast<const float4*>(p.frames + static_cast<size_t>(fr) * 1024) + rem);
+    }
+  };
+  // conv2 epilogue of one pair: acc (128 px x 64 ch) -> bias + ReLU -> act2
+  auto conv2_epilogue = [&](int pair_idx) {
+    mbar_wait(bar_acc, acc_phase);
+    acc_phase ^= 1;
+    tc_fence_after();
+    const int q = warp & 3, hh = warp >> 2;              // lane quarter, 32-column half
+    const int r = q * 32 + lane;                          // row = (f, y2, x2) of this pair
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_acc2 + (static_cast<uint32_t>(q * 32) << 16) + hh * 32, v);
+    tmem_ld_wait();
+    const int pixel = pair_idx * 128 + r;                 // pixel index inside the 8-frame act2 block
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 u;
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8));
+      const float4 bc = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8 + 4));
+      u.x = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 1]) + ba.y, 0.f));
+      u.y = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 3]) + ba.w, 0.f));
+      u.z = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 4]) + bc.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 5]) + bc.y, 0.f));
+      u.w = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 6]) + bc.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 7]) + bc.w, 0.f));
+      *reinterpret_cast<uint4*>(act2 + act2_chunk_off(pixel, hh * 4 + c)) = u;
+    }
+    tc_fence_before();
+    __syncthreads();     // act2 rows of this pair visible; acc2 drained
+  };
+  prefetch_pair(blockIdx.x * GROUP);
+
   for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
     const int frame0 = grp * GROUP;
     // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
@@ -133,17 +173,20 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     }
 
     for (int pair = 0; pair < GROUP / 2; ++pair) {
-      // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) ----
-      for (int i = tid; i < 2 * 256; i += TC_THREADS) {     // one float4 per thread-iteration: 2 frames x 1024 px
-        const int f = i >> 8, rem = i & 255;
+      // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) from the prefetch registers ----
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int id = tid + TC_THREADS * i;
+        const int f = id >> 8, rem = id & 255;
         const int y = rem >> 3, x4 = (rem & 7) * 4;
-        const int fr = frame0 + pair * 2 + f;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fr < p.M) v = __ldg(reinterpret_cast<const float4*>(p.frames + static_cast<size_t>(fr) * 1024 + y * 32 + x4));
         float* d = sIn + f * 34 * 34 + (y + 1) * 34 + (x4 + 1);
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
       }
       __syncthreads();
+      {
+        const int next_first = (pair + 1 < GROUP / 2) ? frame0 + (pair + 1) * 2 : (grp + static_cast<int>(gridDim.x)) * GROUP;
+        prefetch_pair(next_first);
+      }
 
       // ---- conv1: rows = 2 x 256 output pixels, K = 9 (padded to 16), N = 32 ----
       for (int t = warp; t < 32; t += TC_THREADS / 32) {
@@ -170,6 +213,9 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         }
       }
       __syncthreads();
+
+      // deferred epilogue of the previous pair: its MMAs had the staging + conv1 above to complete
+      if (pair > 0) conv2_epilogue(pair - 1);
 
       // ---- conv2: 5 slabs of two taps ----
       for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
@@ -205,32 +251,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
           if (j == W2_SLABS - 1) umma_commit(bar_acc);
         }
       }
-      // ---- conv2 epilogue: acc (128 px x 64 ch) -> bias + ReLU -> act2 ----
-      mbar_wait(bar_acc, acc_phase);
-      acc_phase ^= 1;
-      tc_fence_after();
-      {
-        const int q = warp & 3, hh = warp >> 2;              // lane quarter, 32-column half
-        const int r = q * 32 + lane;                          // row = (f, y2, x2) of this pair
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_acc2 + (static_cast<uint32_t>(q * 32) << 16) + hh * 32, v);
-        tmem_ld_wait();
-        const int pixel = pair * 128 + r;                     // pixel index inside the 8-frame act2 block
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8));
-          const float4 bc = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8 + 4));
-          u.x = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 1]) + ba.y, 0.f));
-          u.y = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 3]) + ba.w, 0.f));
-          u.z = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 4]) + bc.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 5]) + bc.y, 0.f));
-          u.w = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 6]) + bc.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 7]) + bc.w, 0.f));
-          *reinterpret_cast<uint4*>(act2 + act2_chunk_off(pixel, hh * 4 + c)) = u;
-        }
-      }
-      tc_fence_before();
-      __syncthreads();     // act2 rows of this pair visible; acc2 drained; sIn/act1 reusable
     }
+    conv2_epilogue(GROUP / 2 - 1);
 
     // ---- conv3: one slab per tap, weights streamed by TMA ----
     for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
