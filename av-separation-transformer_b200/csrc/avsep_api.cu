@@ -997,6 +997,29 @@ int avsep_test_gemm_ln(avsep_handle* h, const void* A, const void* W, const floa
   return 0;
 }
 
+// Debug: same GEMM as avsep_test_gemm / avsep_test_gemm_ln (ln != 0) with a per-CTA phase trace:
+// trace_dev[cta*8 + k] = globaltimer (ns) at k = 0 entry, 1 setup done, 2 first operands landed, 3 MMAs issued,
+// 4 accumulator ready, 5 accumulator drained (LN), 6 first tile's epilogue done, 7 CTA done.
+int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const float* bias, float* x_or_out,
+                          const float* gamma, const float* beta, void* out_op, int32_t M, int32_t N, int32_t K,
+                          int32_t ln, int32_t act, unsigned long long* trace_dev, void* cuda_stream) {
+  if (!h) return 1;
+  GemmProblem p{};
+  p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K; p.taps = 1;
+  GemmEpilogue e;
+  e.bias = bias; e.act = act;
+  if (ln) {
+    e.kind = EPI_LN;
+    e.resid = x_or_out; e.out_f32 = x_or_out; e.ld_f32 = N; e.ln_gamma = gamma; e.ln_beta = beta;
+    e.out_op = out_op; e.ld_op = N;
+  } else {
+    e.out_op = out_op; e.ld_op = N;
+    e.out_f32 = out_op ? nullptr : x_or_out; e.ld_f32 = N;
+  }
+  CK(launch_gemm(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, p, e, 0, trace_dev));
+  return 0;
+}
+
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }

@@ -33,7 +33,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BN_MAX = 256;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int TILE_K_BYTES = 128;            // one 128-byte swizzle span per row per stage
 constexpr int A_STAGE_BYTES = BM * TILE_K_BYTES;
 constexpr int B_STAGE_BYTES = BN_MAX * TILE_K_BYTES;
@@ -43,13 +43,23 @@ constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
 constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][2 halves] float2
 constexpr int VEC_OFFSET = RED_OFFSET + 2 * 128 * 2 * 8;   // bias [2][256], gamma [256], beta [256] fp32
-constexpr int SMEM_TOTAL = VEC_OFFSET + 4 * BN_MAX * 4 + 1024;
+constexpr int STG_OFFSET = (VEC_OFFSET + 4 * BN_MAX * 4 + 127) / 128 * 128;   // per-epilogue-warp 4 KB transpose buffers
+constexpr int SMEM_TOTAL = STG_OFFSET + NUM_EPI_WARPS * 4096 + 1024;
+static_assert(SMEM_TOTAL <= 227 * 1024, "gemm: shared memory budget exceeded");
 constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator stages
 
 struct GemmDev {
   int M, N, K, taps, tap_stride, row_shift, n_tile;
   GemmEpilogue e;
+  unsigned long long* trace;   // optional [grid][8] globaltimer stamps of the CTA's first tile (debug hook), else null
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if (p.trace != nullptr) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
 
 // 32-byte (full-sector) global store: one request per thread writes a whole sector of its row.
 __device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
@@ -91,6 +101,58 @@ __device__ __forceinline__ void store_op_chunk(void* out_op, size_t off, const f
       for (int j = 0; j < 32; ++j)
         if (j < ncols) o[j] = __float2bfloat16_rn(val[j]);
     }
+  }
+}
+
+// ---- per-warp transpose buffer: 32 rows x 128 B; 16-byte chunk c of row r lives at slot (c ^ (r & 7)) ----------
+// Thread-per-row accesses (lane = row) and row-contiguous cooperative accesses (8 lanes = one 128-byte row) are both
+// bank-conflict free, so the epilogue can read TMEM with thread = row and still move whole 128-byte lines to and
+// from global memory (4 rows per instruction instead of 32 partial lines).
+__device__ __forceinline__ uint32_t stg_off(int row, int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); }
+
+// global [32 rows x 128 B] -> buffer.  row_ptr = this lane's row base (already offset to the tile's first column) or 0.
+__device__ __forceinline__ void stg_load_rows(uint8_t* buf, unsigned long long row_ptr, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), c = lane & 7;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, row_ptr, row);
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (rp != 0) x = *reinterpret_cast<const uint4*>(rp + c * 16);
+    *reinterpret_cast<uint4*>(buf + stg_off(row, c)) = x;
+  }
+}
+// buffer -> global [32 rows x 128 B]
+__device__ __forceinline__ void stg_store_rows(const uint8_t* buf, unsigned long long row_ptr, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), c = lane & 7;
+    const unsigned long long rp = __shfl_sync(0xffffffffu, row_ptr, row);
+    if (rp != 0) *reinterpret_cast<uint4*>(rp + c * 16) = *reinterpret_cast<const uint4*>(buf + stg_off(row, c));
+  }
+}
+// own row (lane) <-> 32 fp32 registers
+__device__ __forceinline__ void stg_read_own_f32(const uint8_t* buf, int lane, float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v4 = *reinterpret_cast<const float4*>(buf + stg_off(lane, c));
+    x[4 * c] = v4.x; x[4 * c + 1] = v4.y; x[4 * c + 2] = v4.z; x[4 * c + 3] = v4.w;
+  }
+}
+__device__ __forceinline__ void stg_write_own_f32(uint8_t* buf, int lane, const float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(buf + stg_off(lane, c)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+// own row: 32 values as bf16 into chunk slots [slot0, slot0+4) (two calls fill one 128-byte row of 64 bf16)
+__device__ __forceinline__ void stg_write_own_bf16(uint8_t* buf, int lane, int slot0, const float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    u.x = pack_bf16x2(x[8 * c], x[8 * c + 1]);
+    u.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
+    u.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]);
+    u.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
+    *reinterpret_cast<uint4*>(buf + stg_off(lane, slot0 + c)) = u;
   }
 }
 
@@ -184,6 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* sbias = reinterpret_cast<float*>(smem + VEC_OFFSET);       // [2][BN_MAX], double-buffered per tile
   float* sgamma = sbias + 2 * BN_MAX;
   float* sbeta = sgamma + BN_MAX;
+  uint8_t* stg_all = smem + STG_OFFSET;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -195,6 +258,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int total_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
+    TRACE(0);                                  // kernel entry
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
 #pragma unroll
@@ -225,6 +289,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
+      TRACE(1);                                // setup done (barriers, TMEM alloc)
       // ---------------- TMA producer ----------------
       const uint32_t stage_bytes = A_STAGE_BYTES + static_cast<uint32_t>(p.n_tile) * TILE_K_BYTES;
       int it = 0;
@@ -261,6 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (lt == 0 && kt == 0) TRACE(2);    // first operands landed
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
@@ -274,6 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(&empty_bar[s]);      // smem stage reusable once these MMAs have read it
         }
         umma_commit(&tfull_bar[acc]);      // accumulator stage complete
+        if (lt == 0) TRACE(3);               // all MMAs of the first tile issued
       }
     }
   } else {
@@ -298,6 +365,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("bar.sync 5, 256;" ::: "memory");            // bias slice visible to all epilogue warps
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
+      if (lt == 0 && threadIdx.x == 64) TRACE(4);   // accumulator of the first tile ready
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN_MAX);
 
       if constexpr (EPI == EPI_TAIL) {
@@ -340,40 +408,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       } else if constexpr (EPI == EPI_LN) {
-        // value = acc + bias (+act, +PE) + residual (already in val_ln), fp32 residual-stream store, LayerNorm over
-        // the whole row, operand store.
+        // value = acc + bias (+act, +PE) + residual; fp32 residual-stream store; LayerNorm over the whole row;
+        // operand store.  Each warp owns 32 rows x (n_tile/2) contiguous columns; all global traffic goes through
+        // the warp's transpose buffer as whole 128-byte lines.
         const RowInfo ri = row_info(e, m, p.M);
+        uint8_t* stg = stg_all + (warp - 2) * 4096;
+        const int nch = p.n_tile >> 5;                       // 32-column chunks in the row (<= 8)
+        const int ch_first = half == 0 ? 0 : (nch + 1) >> 1;
+        const int ch_count = half == 0 ? (nch + 1) >> 1 : nch >> 1;
+        const unsigned long long resid_row =
+            (ri.valid && e.resid != nullptr) ? reinterpret_cast<unsigned long long>(e.resid + static_cast<size_t>(ri.orow) * p.N) : 0ull;
+        const unsigned long long xout_row =
+            (ri.valid && e.out_f32 != nullptr) ? reinterpret_cast<unsigned long long>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32) : 0ull;
+        const unsigned long long op_row =
+            (ri.valid && e.out_op != nullptr)
+                ? reinterpret_cast<unsigned long long>(e.out_op) + static_cast<size_t>(ri.orow) * e.ld_op * (TF32 ? 4 : 2) : 0ull;
         float val[4][32];
         float sum = 0.f;
-        int cnt = 0;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          const int c0 = (2 * ci + half) * 32;
-          if (c0 < p.n_tile) {                          // warp-uniform
+          if (ci < ch_count) {                          // warp-uniform
+            const int c0 = (ch_first + ci) * 32;
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+            if (e.resid != nullptr) stg_load_rows(stg, resid_row ? resid_row + c0 * 4 : 0ull, lane);
             tmem_ld_wait();
             value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
-            if (ri.valid && e.resid != nullptr) {       // residual stream: written by the previous GEMM, L2-resident
-              const float4* rp = reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(ri.orow) * p.N + c0);
+            __syncwarp();
+            if (e.resid != nullptr) {
+              float x[32];
+              stg_read_own_f32(stg, lane, x);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x4 = rp[j];
-                val[ci][4 * j] += x4.x; val[ci][4 * j + 1] += x4.y;
-                val[ci][4 * j + 2] += x4.z; val[ci][4 * j + 3] += x4.w;
-              }
+              for (int j = 0; j < 32; ++j) val[ci][j] += x[j];
             }
-            if (ri.valid && e.out_f32 != nullptr)
-              store_f32_chunk(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + c0, val[ci]);
+            if (e.out_f32 != nullptr) {
+              stg_write_own_f32(stg, lane, val[ci]);
+              __syncwarp();
+              stg_store_rows(stg, xout_row ? xout_row + c0 * 4 : 0ull, lane);
+            }
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum += val[ci][j];
-            cnt += 32;
           }
         }
         // accumulator fully read: hand the TMEM stage back before the statistics / stores
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lt == 0 && threadIdx.x == 64) TRACE(5);   // LN: accumulator drained, residual added, fp32 stream stored
+        const int cnt = ch_count * 32;
         if (e.ln_gamma != nullptr) {
           // exact two-pass statistics of this half, merged with the other half (Chan's parallel formula)
           const float n_h = static_cast<float>(cnt);
@@ -381,7 +464,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float m2 = 0.f;
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
-            if ((2 * ci + half) * 32 < p.n_tile) {
+            if (ci < ch_count) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float dlt = val[ci][j] - mean_h;
@@ -401,8 +484,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float rstd = rsqrtf(m2_all / n_all + 1e-5f);
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
-            const int c0 = (2 * ci + half) * 32;
-            if (c0 < p.n_tile) {
+            if (ci < ch_count) {
+              const int c0 = (ch_first + ci) * 32;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 g4 = *reinterpret_cast<const float4*>(sgamma + c0 + j);
@@ -415,41 +498,117 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (ri.valid && e.out_op != nullptr) {
+        if (e.out_op != nullptr) {
+          if constexpr (TF32) {
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
-            const int c0 = (2 * ci + half) * 32;
-            if (c0 < p.n_tile)
-              store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + c0, val[ci], 32, true);
+            for (int ci = 0; ci < 4; ++ci) {
+              if (ci < ch_count) {
+                stg_write_own_f32(stg, lane, val[ci]);
+                __syncwarp();
+                stg_store_rows(stg, op_row ? op_row + (ch_first + ci) * 128 : 0ull, lane);
+                __syncwarp();
+              }
+            }
+          } else {
+            // bf16: two chunks (64 columns) make one 128-byte row
+#pragma unroll
+            for (int cp = 0; cp < 2; ++cp) {
+              if (2 * cp + 1 < ch_count) {
+                stg_write_own_bf16(stg, lane, 0, val[2 * cp]);
+                stg_write_own_bf16(stg, lane, 4, val[2 * cp + 1]);
+                __syncwarp();
+                stg_store_rows(stg, op_row ? op_row + (ch_first + 2 * cp) * 64 : 0ull, lane);
+                __syncwarp();
+              } else if (2 * cp < ch_count) {          // odd trailing chunk: thread-per-row 32-byte stores
+                if (ri.valid)
+                  store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + (ch_first + 2 * cp) * 32,
+                                       val[2 * cp], 32, true);
+              }
+            }
           }
         }
+        if (lt == 0 && threadIdx.x == 64) TRACE(6);   // LN: first tile's epilogue done
         continue;   // tempty already signalled
       } else {
         const RowInfo ri = row_info(e, m, p.M);
-        for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
-          const int col0 = n0 + c0;
-          if (col0 >= p.N) break;                      // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
-          tmem_ld_wait();
-          const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
-          if (!ri.valid) continue;
-          float val[32];
-          value_chunk<false>(e, ri, v, val, sb + c0, col0, ncols, p.N);
-          const bool full = (ncols == 32);
-          if (e.out_f32 != nullptr) {
-            float* o = e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + col0;
-            if (full && (e.ld_f32 & 7) == 0) {
-              store_f32_chunk(o, val);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] = val[j];
+        uint8_t* stg = stg_all + (warp - 2) * 4096;
+        // Coalesced path: each warp owns a contiguous half of the tile's 64-column units, stages two chunks as one
+        // 128-byte bf16 row (or one chunk as a 128-byte fp32 row) and stores whole lines.
+        const bool coalesced = (p.N % 64 == 0) && (p.n_tile % 64 == 0) && (e.out_op == nullptr || (e.ld_op & 63) == 0) &&
+                               (e.out_f32 == nullptr || (e.ld_f32 & 31) == 0);
+        if (coalesced) {
+          const int npair = p.n_tile >> 6;
+          const int pr_first = half == 0 ? 0 : (npair + 1) >> 1;
+          const int pr_count = half == 0 ? (npair + 1) >> 1 : npair >> 1;
+          const unsigned long long f32_row =
+              (ri.valid && e.out_f32 != nullptr) ? reinterpret_cast<unsigned long long>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + n0) : 0ull;
+          const unsigned long long op_row =
+              (ri.valid && e.out_op != nullptr)
+                  ? reinterpret_cast<unsigned long long>(e.out_op) + (static_cast<size_t>(ri.orow) * e.ld_op + n0) * (TF32 ? 4 : 2) : 0ull;
+          for (int pi = 0; pi < pr_count; ++pi) {
+            const int c0 = (pr_first + pi) * 64;
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v0);
+            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0 + 32), v1);
+            tmem_ld_wait();
+            float a0[32], a1[32];
+            value_chunk<false>(e, ri, v0, a0, sb + c0, n0 + c0, 32, p.N);
+            value_chunk<false>(e, ri, v1, a1, sb + c0 + 32, n0 + c0 + 32, 32, p.N);
+            if (e.out_f32 != nullptr) {
+              stg_write_own_f32(stg, lane, a0);
+              __syncwarp();
+              stg_store_rows(stg, f32_row ? f32_row + c0 * 4 : 0ull, lane);
+              __syncwarp();
+              stg_write_own_f32(stg, lane, a1);
+              __syncwarp();
+              stg_store_rows(stg, f32_row ? f32_row + (c0 + 32) * 4 : 0ull, lane);
+              __syncwarp();
+            }
+            if (e.out_op != nullptr) {
+              if constexpr (TF32) {
+                stg_write_own_f32(stg, lane, a0);
+                __syncwarp();
+                stg_store_rows(stg, op_row ? op_row + c0 * 4 : 0ull, lane);
+                __syncwarp();
+                stg_write_own_f32(stg, lane, a1);
+                __syncwarp();
+                stg_store_rows(stg, op_row ? op_row + (c0 + 32) * 4 : 0ull, lane);
+                __syncwarp();
+              } else {
+                stg_write_own_bf16(stg, lane, 0, a0);
+                stg_write_own_bf16(stg, lane, 4, a1);
+                __syncwarp();
+                stg_store_rows(stg, op_row ? op_row + c0 * 2 : 0ull, lane);
+                __syncwarp();
+              }
             }
           }
-          if (e.out_op != nullptr) {
-            const bool vec = full && ((e.ld_op & 15) == 0);
-            store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + col0, val, ncols, vec);
+        } else {
+          for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
+            const int col0 = n0 + c0;
+            if (col0 >= p.N) break;                      // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+            tmem_ld_wait();
+            const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
+            if (!ri.valid) continue;
+            float val[32];
+            value_chunk<false>(e, ri, v, val, sb + c0, col0, ncols, p.N);
+            const bool full = (ncols == 32);
+            if (e.out_f32 != nullptr) {
+              float* o = e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + col0;
+              if (full && (e.ld_f32 & 7) == 0) {
+                store_f32_chunk(o, val);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) o[j] = val[j];
+              }
+            }
+            if (e.out_op != nullptr) {
+              const bool vec = full && ((e.ld_op & 15) == 0);
+              store_op_chunk<TF32>(e.out_op, static_cast<size_t>(ri.orow) * e.ld_op + col0, val, ncols, vec);
+            }
           }
         }
       }
@@ -457,11 +616,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lt == 0 && threadIdx.x == 64) TRACE(6);     // first tile's epilogue done
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(7);              // all tiles of this CTA done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -527,7 +688,8 @@ const char* gemm_init() {
 
 bool gemm_ln_fusable(int N) { return N <= BN_MAX && N >= 32 && (N % 32) == 0; }
 
-const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn) {
+const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn,
+                        unsigned long long* trace) {
   if (const char* err = gemm_init()) return err;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return "gemm: empty problem";
   const bool tf32 = (prec == PREC_TF32);
@@ -551,6 +713,7 @@ const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const Ge
   d.M = p.M; d.N = p.N; d.K = p.K; d.taps = p.taps; d.tap_stride = p.tap_stride; d.row_shift = p.row_shift;
   d.n_tile = n_tile;
   d.e = e;
+  d.trace = trace;
   CUtensorMap ta, tw;
   const uint32_t box_k = tf32 ? 32 : 64;
   if (const char* err = encode_2d(&ta, tf32, p.A, p.K, p.rowsA, p.lda, box_k, BM)) return err;

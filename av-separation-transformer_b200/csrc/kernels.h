@@ -57,7 +57,8 @@ struct GemmEpilogue {
 
 // Returns nullptr on success or a static error string.
 const char* gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
-const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn = 0);
+const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn = 0,
+                        unsigned long long* trace = nullptr);   // trace: [grid][8] globaltimer stamps (debug)
 bool gemm_ln_fusable(int N);   // EPI_LN usable for this row width
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).

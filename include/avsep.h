@@ -122,6 +122,9 @@ AVSEP_API int avsep_test_gemm(avsep_handle* h, const void* A, const void* W, con
 AVSEP_API int avsep_test_gemm_ln(avsep_handle* h, const void* A, const void* W, const float* bias, float* x_inout,
                                  const float* gamma, const float* beta, void* out_op, int32_t M, int32_t N, int32_t K,
                                  void* cuda_stream);
+AVSEP_API int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const float* bias, float* x_or_out,
+                                    const float* gamma, const float* beta, void* out_op, int32_t M, int32_t N, int32_t K,
+                                    int32_t ln, int32_t act, unsigned long long* trace_dev, void* cuda_stream);
 AVSEP_API int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
                       int32_t L, int32_t N, int32_t K, void* cuda_stream);
 AVSEP_API int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
