@@ -46,6 +46,31 @@ __global__ void interp_rows_kernel(const float* __restrict__ x, float* __restric
   for (int c = threadIdx.x; c < d; c += blockDim.x) o[c] = w0 * r0[c] + w1 * r1[c];
 }
 
+// Profiling aid: keeps the GPU busy while the host enqueues a whole forward, so that the per-kernel event pairs
+// measure device time and not host launch latency.
+__global__ void spin_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+
+struct GraphKey {
+  int B, T, N, Hh, Ww;
+  const void *mixed, *frames, *sep, *masks, *ws;
+  bool operator==(const GraphKey& o) const {
+    return B == o.B && T == o.T && N == o.N && Hh == o.Hh && Ww == o.Ww && mixed == o.mixed && frames == o.frames &&
+           sep == o.sep && masks == o.masks && ws == o.ws;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;
+  uint64_t last_use = 0;
+};
+
 struct HostTensor {
   std::vector<float> data;
   std::vector<int64_t> shape;
@@ -81,6 +106,11 @@ struct avsep_handle {
   std::map<std::string, HostTensor> host_w;
   bool finalized = false;
   bool fuse_ln = true;   // residual+LayerNorm in the GEMM epilogue when the row fits one tile
+  bool use_graph = true; // replay the forward as a CUDA graph (captured per shape + buffer set on its 2nd use)
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  int profile_spin_us = 3000;
   uint8_t* d_weights = nullptr;
   size_t weight_bytes = 0;
   // device views into d_weights
@@ -156,6 +186,12 @@ void prof_end(avsep_handle* h) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+void drop_graphs(avsep_handle* h) {   // cached graphs hold raw pointers to weights / workspace
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
 size_t op_size(const avsep_handle* h) { return h->cfg.precision == AVSEP_PREC_TF32 ? 4 : 2; }
 
 // ---- workspace -------------------------------------------------------------------------------
@@ -205,6 +241,7 @@ int get_workspace(avsep_handle* h, Workspace& w, void* user_ws, size_t user_byte
     base = static_cast<uint8_t*>(user_ws);
   } else {
     if (h->own_ws_bytes < need) {
+      drop_graphs(h);
       if (h->own_ws) cudaFree(h->own_ws);
       h->own_ws = nullptr;
       h->own_ws_bytes = 0;
@@ -420,6 +457,7 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   const int d = h->cfg.d_model;
   const int Ma = w.B * w.T, Mv = w.B * w.N;
   h->prof_stream = s;
+  if (h->profile && h->profile_spin_us > 0) spin_kernel<<<1, 1, 0, s>>>(1000ull * h->profile_spin_us);
   // --- audio branch ---
   if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
@@ -434,6 +472,54 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   // --- fusion + decoder ---
   if (fusion_stack(h, s, w, w.N)) return 1;
   return decoder_stage(h, s, w, mixed, separated, masks);
+}
+
+// Eager on the first use of a (shape, buffer set); captured into a CUDA graph on the second; replayed afterwards.
+// The graph bakes in the kernel parameters (tensor maps included), so a replay costs one host call.
+int forward_cached(avsep_handle* h, cudaStream_t s, Workspace& w, const void* ws_base, const float* mixed,
+                   const float* frames, float* separated, float* masks) {
+  if (!h->use_graph || h->profile || h->debug) return forward_device(h, s, w, mixed, frames, separated, masks);
+  const GraphKey key{w.B, w.T, w.N, w.Hh, w.Ww, mixed, frames, separated, masks, ws_base};
+  GraphEntry* ent = nullptr;
+  for (auto& g : h->graphs)
+    if (g.key == key) { ent = &g; break; }
+  if (ent == nullptr) {
+    if (h->graphs.size() >= 16) {          // evict the least recently used entry
+      size_t victim = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+      if (h->graphs[victim].exec) cudaGraphExecDestroy(h->graphs[victim].exec);
+      h->graphs.erase(h->graphs.begin() + victim);
+    }
+    GraphEntry g;
+    g.key = key;
+    g.last_use = ++h->graph_clock;
+    h->graphs.push_back(g);
+    return forward_device(h, s, w, mixed, frames, separated, masks);   // warm-up, also sets kernel attributes
+  }
+  ent->last_use = ++h->graph_clock;
+  if (ent->exec == nullptr) {
+    if (h->cap_stream == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = forward_device(h, h->cap_stream, w, mixed, frames, separated, masks);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc != 0) {
+      if (graph) cudaGraphDestroy(graph);
+      return 1;
+    }
+    if (ce != cudaSuccess) return fail(h, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const cudaError_t ci = cudaGraphInstantiate(&ent->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) {
+      ent->exec = nullptr;
+      return fail(h, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci));
+    }
+    ent->launches = h->launches;
+  }
+  h->launches = ent->launches;
+  CUDA_OK(cudaGraphLaunch(ent->exec, s));
+  return 0;
 }
 
 // ---- weight access helpers ---------------------------------------------------------------------
@@ -519,6 +605,9 @@ void avsep_destroy(avsep_handle* h) {
     if (kv.second.first) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (cudaEvent_t e : h->host_ev) cudaEventDestroy(e);
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int i = 0; i < 3; ++i)
     if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
   delete h;
@@ -706,6 +795,7 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   }
 #undef GETW
   // upload
+  drop_graphs(h);
   if (h->d_weights) cudaFree(h->d_weights);
   h->d_weights = nullptr;
   CUDA_OK(cudaMalloc(&h->d_weights, ar.bytes.size()));
@@ -762,7 +852,8 @@ int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_fra
   Workspace w;
   if (get_workspace(h, w, workspace, workspace_bytes, B, T, N, Hh, Ww)) return 1;
   h->launches = 0;
-  return forward_device(h, static_cast<cudaStream_t>(cuda_stream), w, mixed_spec, lip_frames, separated, masks);
+  return forward_cached(h, static_cast<cudaStream_t>(cuda_stream), w, workspace ? workspace : h->own_ws, mixed_spec,
+                        lip_frames, separated, masks);
 }
 
 int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
@@ -818,7 +909,7 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
     CUDA_OK(cudaStreamWaitEvent(s_comp, h->host_ev[2 * c], 0));
     Workspace wc = w;
     wc.B = bc;
-    if (forward_device(h, s_comp, wc, h->io_mixed + b0 * mixed_per, h->io_frames + b0 * frames_per,
+    if (forward_cached(h, s_comp, wc, h->own_ws, h->io_mixed + b0 * mixed_per, h->io_frames + b0 * frames_per,
                        h->io_sep + b0 * out_per, h->io_masks + b0 * out_per))
       return 1;
     CUDA_OK(cudaEventRecord(h->host_ev[2 * c + 1], s_comp));
@@ -1025,6 +1116,8 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
+  if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }
   return fail(h, std::string("unknown option ") + name);
 }
 
