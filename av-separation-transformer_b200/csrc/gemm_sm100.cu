@@ -38,11 +38,11 @@ constexpr int TILE_K_BYTES = 128;            // one 128-byte swizzle span per ro
 constexpr int A_STAGE_BYTES = BM * TILE_K_BYTES;
 constexpr int B_STAGE_BYTES = BN_MAX * TILE_K_BYTES;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][2 halves] float2
-constexpr int VEC_OFFSET = RED_OFFSET + 2 * 128 * 2 * 8;   // bias [2][256], gamma [256], beta [256] fp32
+constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][4 parts] float2
+constexpr int VEC_OFFSET = RED_OFFSET + 2 * 128 * 4 * 8;   // bias [2][256], gamma [256], beta [256] fp32
 constexpr int STG_OFFSET = (VEC_OFFSET + 4 * BN_MAX * 4 + 127) / 128 * 128;   // per-epilogue-warp 4 KB transpose buffers
 constexpr int SMEM_TOTAL = STG_OFFSET + NUM_EPI_WARPS * 4096 + 1024;
 static_assert(SMEM_TOTAL <= 227 * 1024, "gemm: shared memory budget exceeded");
@@ -51,15 +51,19 @@ constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator 
 struct GemmDev {
   int M, N, K, taps, tap_stride, row_shift, n_tile;
   GemmEpilogue e;
-  unsigned long long* trace;   // optional [grid][8] globaltimer stamps of the CTA's first tile (debug hook), else null
+  unsigned long long* trace;   // optional [grid][64] globaltimer stamps (debug hook), else null:
+                               //   [0] entry [1] setup done [7] CTA done; per local tile lt < 12 at 8 + 4*lt:
+                               //   +0 first operands of the tile landed, +1 tile's MMAs issued, +2 accumulator ready
+                               //   (epilogue), +3 epilogue done
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
   return t;
 }
-#define TRACE(slot) do { if (p.trace != nullptr) p.trace[blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+#define TRACE(slot) do { if (p.trace != nullptr) p.trace[blockIdx.x * 64 + (slot)] = gtime(); } while (0)
+#define TRACE_TILE(lt, k) do { if (p.trace != nullptr && (lt) < 12) p.trace[blockIdx.x * 64 + 8 + 4 * (lt) + (k)] = gtime(); } while (0)
 
 // 32-byte (full-sector) global store: one request per thread writes a whole sector of its row.
 __device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
@@ -136,6 +140,13 @@ __device__ __forceinline__ void stg_read_own_f32(const uint8_t* buf, int lane, f
   for (int c = 0; c < 8; ++c) {
     const float4 v4 = *reinterpret_cast<const float4*>(buf + stg_off(lane, c));
     x[4 * c] = v4.x; x[4 * c + 1] = v4.y; x[4 * c + 2] = v4.z; x[4 * c + 3] = v4.w;
+  }
+}
+__device__ __forceinline__ void stg_add_own_f32(const uint8_t* buf, int lane, float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 v4 = *reinterpret_cast<const float4*>(buf + stg_off(lane, c));
+    x[4 * c] += v4.x; x[4 * c + 1] += v4.y; x[4 * c + 2] += v4.z; x[4 * c + 3] += v4.w;
   }
 }
 __device__ __forceinline__ void stg_write_own_f32(uint8_t* buf, int lane, const float (&x)[32]) {
@@ -326,7 +337,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lt == 0 && kt == 0) TRACE(2);    // first operands landed
+          if (kt == 0) TRACE_TILE(lt, 0);      // first operands of this tile landed
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
           const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
@@ -340,13 +351,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           umma_commit(&empty_bar[s]);      // smem stage reusable once these MMAs have read it
         }
         umma_commit(&tfull_bar[acc]);      // accumulator stage complete
-        if (lt == 0) TRACE(3);               // all MMAs of the first tile issued
+        TRACE_TILE(lt, 1);                   // all MMAs of this tile issued
       }
     }
   } else {
-    // ---------------- epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----------------
+    // ---------------- epilogue: warps 2..17; TMEM lane quarter = warp % 4, column part = (warp - 2) / 4 ----------------
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;            // 0..3
     const int r = q * 32 + lane;
     const GemmEpilogue& e = p.e;
     int lt = 0;
@@ -359,13 +370,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // stage this tile's bias slice in shared memory while the main loop is still running
       float* sb = sbias + (lt & 1) * BN_MAX;
       {
-        const int i = threadIdx.x - 64;                       // 0..255 over the 8 epilogue warps
-        sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
+        const int i = threadIdx.x - 64;                       // 0..511 over the 16 epilogue warps
+        if (i < BN_MAX) sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
       }
-      asm volatile("bar.sync 5, 256;" ::: "memory");            // bias slice visible to all epilogue warps
+      asm volatile("bar.sync 5, 512;" ::: "memory");            // bias slice visible to all epilogue warps
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      if (lt == 0 && threadIdx.x == 64) TRACE(4);   // accumulator of the first tile ready
+      if (threadIdx.x == 64) TRACE_TILE(lt, 2);     // accumulator ready
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN_MAX);
 
       if constexpr (EPI == EPI_TAIL) {
@@ -377,7 +388,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tt = m - tb * e.T;
         const float* mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
         const size_t out_base = static_cast<size_t>(tb) * e.S * e.F * e.T + tt;
-        for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
+        for (int c0 = part * 32; c0 < p.n_tile; c0 += 128) {
           const int col0 = n0 + c0;
           if (col0 >= p.N) break;                      // warp-uniform
           uint32_t v[32];
@@ -414,8 +425,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const RowInfo ri = row_info(e, m, p.M);
         uint8_t* stg = stg_all + (warp - 2) * 4096;
         const int nch = p.n_tile >> 5;                       // 32-column chunks in the row (<= 8)
-        const int ch_first = half == 0 ? 0 : (nch + 1) >> 1;
-        const int ch_count = half == 0 ? (nch + 1) >> 1 : nch >> 1;
+        const int per = (nch + 3) >> 2;                      // chunks per column part (<= 2)
+        const int ch_first = part * per;
+        const int ch_count = max(0, min(per, nch - ch_first));
         const unsigned long long resid_row =
             (ri.valid && e.resid != nullptr) ? reinterpret_cast<unsigned long long>(e.resid + static_cast<size_t>(ri.orow) * p.N) : 0ull;
         const unsigned long long xout_row =
@@ -423,10 +435,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const unsigned long long op_row =
             (ri.valid && e.out_op != nullptr)
                 ? reinterpret_cast<unsigned long long>(e.out_op) + static_cast<size_t>(ri.orow) * e.ld_op * (TF32 ? 4 : 2) : 0ull;
-        float val[4][32];
+        float val[2][32];
         float sum = 0.f;
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
+        for (int ci = 0; ci < 2; ++ci) {
           if (ci < ch_count) {                          // warp-uniform
             const int c0 = (ch_first + ci) * 32;
             uint32_t v[32];
@@ -435,12 +447,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmem_ld_wait();
             value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
             __syncwarp();
-            if (e.resid != nullptr) {
-              float x[32];
-              stg_read_own_f32(stg, lane, x);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) val[ci][j] += x[j];
-            }
+            if (e.resid != nullptr) stg_add_own_f32(stg, lane, val[ci]);
             if (e.out_f32 != nullptr) {
               stg_write_own_f32(stg, lane, val[ci]);
               __syncwarp();
@@ -455,15 +462,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (lt == 0 && threadIdx.x == 64) TRACE(5);   // LN: accumulator drained, residual added, fp32 stream stored
         const int cnt = ch_count * 32;
         if (e.ln_gamma != nullptr) {
-          // exact two-pass statistics of this half, merged with the other half (Chan's parallel formula)
+          // exact two-pass statistics of this column part, merged across the four parts (Chan's parallel formula)
           const float n_h = static_cast<float>(cnt);
           const float mean_h = cnt > 0 ? sum / n_h : 0.f;
           float m2 = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
+          for (int ci = 0; ci < 2; ++ci) {
             if (ci < ch_count) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -472,18 +478,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          float2* slot = red + ((lt & 1) * 128 + r) * 2;
-          slot[half] = make_float2(mean_h, m2);
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-          const float2 other = slot[half ^ 1];
-          const float n_o = static_cast<float>(p.n_tile - cnt);
-          const float n_all = static_cast<float>(p.n_tile);
-          const float dm = other.x - mean_h;
-          const float mean = mean_h + dm * (n_o / n_all);
-          const float m2_all = m2 + other.y + dm * dm * (n_h * n_o / n_all);
-          const float rstd = rsqrtf(m2_all / n_all + 1e-5f);
+          float2* slot = red + ((lt & 1) * 128 + r) * 4;
+          slot[part] = make_float2(mean_h, m2);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+          float n_acc = 0.f, mean = 0.f, m2_all = 0.f;
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
+          for (int pp = 0; pp < 4; ++pp) {
+            const float n_p = static_cast<float>(max(0, min(per, nch - pp * per)) * 32);
+            if (n_p > 0.f) {
+              const float2 st = slot[pp];
+              const float n_new = n_acc + n_p;
+              const float dm = st.x - mean;
+              mean += dm * (n_p / n_new);
+              m2_all += st.y + dm * dm * (n_acc * n_p / n_new);
+              n_acc = n_new;
+            }
+          }
+          const float rstd = rsqrtf(m2_all / n_acc + 1e-5f);
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
             if (ci < ch_count) {
               const int c0 = (ch_first + ci) * 32;
 #pragma unroll
@@ -501,7 +514,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.out_op != nullptr) {
           if constexpr (TF32) {
 #pragma unroll
-            for (int ci = 0; ci < 4; ++ci) {
+            for (int ci = 0; ci < 2; ++ci) {
               if (ci < ch_count) {
                 stg_write_own_f32(stg, lane, val[ci]);
                 __syncwarp();
@@ -512,7 +525,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             // bf16: two chunks (64 columns) make one 128-byte row
 #pragma unroll
-            for (int cp = 0; cp < 2; ++cp) {
+            for (int cp = 0; cp < 1; ++cp) {
               if (2 * cp + 1 < ch_count) {
                 stg_write_own_bf16(stg, lane, 0, val[2 * cp]);
                 stg_write_own_bf16(stg, lane, 4, val[2 * cp + 1]);
@@ -527,7 +540,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (lt == 0 && threadIdx.x == 64) TRACE(6);   // LN: first tile's epilogue done
+        if (threadIdx.x == 64) TRACE_TILE(lt, 3);     // LN: epilogue done
         continue;   // tempty already signalled
       } else {
         const RowInfo ri = row_info(e, m, p.M);
@@ -538,53 +551,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                (e.out_f32 == nullptr || (e.ld_f32 & 31) == 0);
         if (coalesced) {
           const int npair = p.n_tile >> 6;
-          const int pr_first = half == 0 ? 0 : (npair + 1) >> 1;
-          const int pr_count = half == 0 ? (npair + 1) >> 1 : npair >> 1;
           const unsigned long long f32_row =
               (ri.valid && e.out_f32 != nullptr) ? reinterpret_cast<unsigned long long>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + n0) : 0ull;
           const unsigned long long op_row =
               (ri.valid && e.out_op != nullptr)
                   ? reinterpret_cast<unsigned long long>(e.out_op) + (static_cast<size_t>(ri.orow) * e.ld_op + n0) * (TF32 ? 4 : 2) : 0ull;
-          for (int pi = 0; pi < pr_count; ++pi) {
-            const int c0 = (pr_first + pi) * 64;
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v0);
-            tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0 + 32), v1);
-            tmem_ld_wait();
-            float a0[32], a1[32];
-            value_chunk<false>(e, ri, v0, a0, sb + c0, n0 + c0, 32, p.N);
-            value_chunk<false>(e, ri, v1, a1, sb + c0 + 32, n0 + c0 + 32, 32, p.N);
-            if (e.out_f32 != nullptr) {
-              stg_write_own_f32(stg, lane, a0);
-              __syncwarp();
-              stg_store_rows(stg, f32_row ? f32_row + c0 * 4 : 0ull, lane);
-              __syncwarp();
-              stg_write_own_f32(stg, lane, a1);
-              __syncwarp();
-              stg_store_rows(stg, f32_row ? f32_row + (c0 + 32) * 4 : 0ull, lane);
-              __syncwarp();
-            }
-            if (e.out_op != nullptr) {
-              if constexpr (TF32) {
-                stg_write_own_f32(stg, lane, a0);
+          for (int pi = part; pi < npair; pi += 4) {
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {             // the two 32-column chunks of this 64-column unit
+              const int c0 = pi * 64 + hc * 32;
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+              tmem_ld_wait();
+              float a[32];
+              value_chunk<false>(e, ri, v, a, sb + c0, n0 + c0, 32, p.N);
+              if (e.out_f32 != nullptr) {
+                stg_write_own_f32(stg, lane, a);
                 __syncwarp();
-                stg_store_rows(stg, op_row ? op_row + c0 * 4 : 0ull, lane);
+                stg_store_rows(stg, f32_row ? f32_row + c0 * 4 : 0ull, lane);
                 __syncwarp();
-                stg_write_own_f32(stg, lane, a1);
-                __syncwarp();
-                stg_store_rows(stg, op_row ? op_row + (c0 + 32) * 4 : 0ull, lane);
-                __syncwarp();
-              } else {
-                stg_write_own_bf16(stg, lane, 0, a0);
-                stg_write_own_bf16(stg, lane, 4, a1);
-                __syncwarp();
-                stg_store_rows(stg, op_row ? op_row + c0 * 2 : 0ull, lane);
-                __syncwarp();
+              }
+              if (e.out_op != nullptr) {
+                if constexpr (TF32) {
+                  stg_write_own_f32(stg, lane, a);
+                  __syncwarp();
+                  stg_store_rows(stg, op_row ? op_row + c0 * 4 : 0ull, lane);
+                  __syncwarp();
+                } else {
+                  stg_write_own_bf16(stg, lane, hc * 4, a);   // two chunks make one 128-byte bf16 row
+                  if (hc == 1) {
+                    __syncwarp();
+                    stg_store_rows(stg, op_row ? op_row + (pi * 64) * 2 : 0ull, lane);
+                    __syncwarp();
+                  }
+                }
               }
             }
           }
         } else {
-          for (int c0 = half * 32; c0 < p.n_tile; c0 += 64) {
+          for (int c0 = part * 32; c0 < p.n_tile; c0 += 128) {
             const int col0 = n0 + c0;
             if (col0 >= p.N) break;                      // warp-uniform
             uint32_t v[32];
@@ -616,7 +621,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (lt == 0 && threadIdx.x == 64) TRACE(6);     // first tile's epilogue done
+      if (threadIdx.x == 64) TRACE_TILE(lt, 3);       // epilogue done
     }
   }
 

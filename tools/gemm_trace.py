@@ -6,37 +6,32 @@ sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200"))
 from avsep_b200.engine import Engine, EngineConfig
 
 eng = Engine(EngineConfig(65, 64, 4, 1, 1, 2, "bf16"), 0)
-names = ["setup", "first_load", "mma_issue", "acc_ready", "acc_drained", "epi_done", "cta_done"]
 for (M, N, K, ln, act, tag) in [(16128, 256, 256, 1, 0, "out_proj+LN"), (16128, 256, 1024, 1, 0, "ffn2+LN"),
-                                (16128, 1024, 256, 0, 1, "ffn1 relu"), (16128, 768, 256, 0, 0, "qkv"),
-                                (12800, 256, 256, 1, 0, "out_proj+LN visual")]:
+                                (16128, 1024, 256, 0, 1, "ffn1 relu"), (16128, 768, 256, 0, 0, "qkv")]:
     A = torch.randn(M, K, device="cuda").bfloat16()
     W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
     bias = torch.randn(N, device="cuda")
     x = torch.randn(M, N, device="cuda")
     g = torch.randn(N, device="cuda"); b = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    trace = torch.zeros(148 * 8, device="cuda", dtype=torch.int64)
+    trace = torch.zeros(148 * 64, device="cuda", dtype=torch.int64)
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     for it in range(3):
         trace.zero_()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         rc = eng.lib.avsep_test_gemm_trace(eng.h, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(), g.data_ptr(),
                                            b.data_ptr(), out.data_ptr(), M, N, K, ln, act, trace.data_ptr(), s)
         assert rc == 0, eng.lib.avsep_last_error(eng.h)
-        e1.record(); torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(148, 8).astype(np.int64)
+        torch.cuda.synchronize()
+    t = trace.cpu().numpy().reshape(148, 64).astype(np.int64)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
-    rel = t - t0
-    print(f"== {tag}: M={M} N={N} K={K} ctas={len(t)} kernel {e0.elapsed_time(e1)*1e3:.1f} us (event)")
-    print("   entry spread (us): max", (rel[:, 0].max()) / 1e3)
-    prev = rel[:, 0]
-    for k, nm in enumerate(names, start=1):
-        col = rel[:, k]
-        ok = t[:, k] > 0
+    print(f"== {tag}: M={M} N={N} K={K} ctas={len(t)}; all times us since first CTA entry")
+    print(f"   setup done mean {(t[:,1]-t0).mean()/1e3:.2f}; CTA done mean {(t[:,7]-t0).mean()/1e3:.2f} max {(t[:,7]-t0).max()/1e3:.2f}")
+    for lt in range(6):
+        cols = t[:, 8 + 4 * lt: 12 + 4 * lt]
+        ok = cols[:, 3] > 0
         if not ok.any():
-            continue
-        print(f"   {nm:12s} at mean {col[ok].mean()/1e3:7.2f} us  max {col[ok].max()/1e3:7.2f} us")
+            break
+        r = (cols[ok] - t0) / 1e3
+        print(f"   tile {lt} (n={ok.sum():3d}): operands {r[:,0].mean():6.2f}  mma_issued {r[:,1].mean():6.2f}  acc_ready {r[:,2].mean():6.2f}  epi_done {r[:,3].mean():6.2f} (max {r[:,3].max():6.2f})")
