@@ -373,7 +373,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int i = threadIdx.x - 64;                       // 0..511 over the 16 epilogue warps
         if (i < BN_MAX) sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
       }
+      if (lt == 1 && threadIdx.x == 64) TRACE(2);               // [2] tile-1 epilogue entered (bias load issued)
       asm volatile("bar.sync 5, 512;" ::: "memory");            // bias slice visible to all epilogue warps
+      if (lt == 1 && threadIdx.x == 64) TRACE(3);               // [3] bias barrier passed
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
       if (threadIdx.x == 64) TRACE_TILE(lt, 2);     // accumulator ready
@@ -563,8 +565,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint32_t v[32];
               tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
               tmem_ld_wait();
+              if (lt == 1 && threadIdx.x == 64 && hc == 0) TRACE(4);   // [4] first TMEM chunk in registers
               float a[32];
               value_chunk<false>(e, ri, v, a, sb + c0, n0 + c0, 32, p.N);
+              if (lt == 1 && threadIdx.x == 64 && hc == 1) TRACE(5);   // [5] second chunk's values computed
               if (e.out_f32 != nullptr) {
                 stg_write_own_f32(stg, lane, a);
                 __syncwarp();
@@ -583,6 +587,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __syncwarp();
                     stg_store_rows(stg, op_row ? op_row + (pi * 64) * 2 : 0ull, lane);
                     __syncwarp();
+                    if (lt == 1 && threadIdx.x == 64) TRACE(6);        // [6] line stores issued
                   }
                 }
               }

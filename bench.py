@@ -127,6 +127,25 @@ def kernel_work(B):
     return flops, bytes_, n_ln
 
 
+def shard_bounds(rank, world, per_rank_batch):
+    """[lo, hi) utterance indices of this rank's shard of the global batch (weak scaling: fixed per-rank batch)."""
+    return rank * per_rank_batch, (rank + 1) * per_rank_batch
+
+
+def throughput(world, per_rank_batch, ms_per_step):
+    """Whole-job utterance-seconds per second from the slowest rank's step time."""
+    return world * per_rank_batch * CLIP_SECONDS / (ms_per_step * 1e-3)
+
+
+def max_over_ranks_cpu(x):
+    """MAX all-reduce of a host scalar on the default process group (gloo in tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def total_flops(B):
     return sum(kernel_work(B)[0].values())
 
@@ -235,7 +254,8 @@ def run_ours(args, rank, local_rank, world):
     # rotating input sets: inputs (69 MB) + outputs (133 MB) + activations (~350 MB) per step already exceed the
     # 126 MB L2; three distinct input sets make sure no step re-reads the previous step's inputs from L2.
     n_sets = 3
-    sets = [synthetic_batch(B, F, T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=1000 * rank + i, device=dev)
+    lo, hi = shard_bounds(rank, world, B)     # this rank's utterances of the global batch; seeds differ per shard
+    sets = [synthetic_batch(hi - lo, F, T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=100003 * i + lo, device=dev)
             for i in range(n_sets)]
     sep = torch.empty((B, S, F, T_FRAMES), device=dev)
     masks = torch.empty_like(sep)
@@ -267,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
-    value = world * B * CLIP_SECONDS / (ms_per_step * 1e-3)
+    value = throughput(world, B, ms_per_step)
 
     # ---- e2e: the public host-buffer call; pinned inputs H2D and results D2H every step -----------------
     h_sets = [(m.cpu().pin_memory(), f.cpu().pin_memory()) for m, f in sets[:2]]
