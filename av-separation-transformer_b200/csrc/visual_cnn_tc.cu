@@ -66,8 +66,11 @@ __device__ __forceinline__ int act2_chunk_off(int pixel, int c) {   // pixel = g
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p) {
-  extern __shared__ uint8_t smem_raw_cnn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_cnn) + 1023) & ~uintptr_t(1023));
+  // Dynamic shared memory is declared 1024-byte aligned (128B-swizzle atoms) and used directly: deriving the base
+  // through an integer round trip would make the compiler fall back to generic LD/ST for every access.
+  extern __shared__ __align__(1024) uint8_t smem_raw_cnn[];
+  uint8_t* const smem = smem_raw_cnn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* ring = smem + OFF_RING;
   uint8_t* w3s = smem + OFF_W3;
   uint8_t* w2s = smem + OFF_W2;

@@ -223,6 +223,9 @@ def run_reference(args, rank, world):
 
 
 def run_ours(args, rank, local_rank, world):
+    # Everything except the final JSON line goes to stderr (NCCL / torchrun print to stdout on their own).
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from avsep_b200.synth import synthetic_batch
@@ -373,7 +376,7 @@ def run_ours(args, rank, local_rank, world):
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"first {CPU_SAMPLE_B} utterances of the same batch, best of {reps} forwards "
                                          f"({best * 1e3:.0f} ms each), torch CPU ops, {cores} threads"}
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -381,8 +384,8 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
