@@ -274,9 +274,10 @@ int snapshot(avsep_handle* h, cudaStream_t s, const char* name, const void* ptr,
 }
 
 // ---- stage helpers -----------------------------------------------------------------------------
-const char* run_visual_cnn(avsep_handle* h, cudaStream_t s, const float* frames, int M, int Hh, int Ww, void* pooled) {
+const char* run_visual_cnn(avsep_handle* h, cudaStream_t s, const float* frames, int M, int Hh, int Ww, void* pooled,
+                           unsigned long long* trace = nullptr) {
   if (h->cnn_tc && Hh == 32 && Ww == 32 && h->cfg.precision == AVSEP_PREC_BF16)
-    return launch_visual_cnn_tc(s, frames, M, h->cnn, h->cnn_w2_slabs, h->cnn_w3_rows, pooled, h->num_sms);
+    return launch_visual_cnn_tc(s, frames, M, h->cnn, h->cnn_w2_slabs, h->cnn_w3_rows, pooled, h->num_sms, trace);
   return launch_visual_cnn(s, h->cfg.precision, frames, M, Hh, Ww, h->cnn, pooled, h->num_sms);
 }
 
@@ -1103,6 +1104,11 @@ int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const f
     e.kind = EPI_LN;
     e.resid = x_or_out; e.out_f32 = x_or_out; e.ld_f32 = N; e.ln_gamma = gamma; e.ln_beta = beta;
     e.out_op = out_op; e.ld_op = N;
+    if (ln == 2) e.resid = nullptr;            // ablations for the trace tool
+    if (ln == 3) e.out_f32 = nullptr;
+    if (ln == 4) e.out_op = nullptr;
+    if (ln == 5) { e.resid = nullptr; e.out_f32 = nullptr; }
+    if (ln == 6) { e.ln_gamma = nullptr; }
   } else {
     e.out_op = out_op; e.ld_op = N;
     e.out_f32 = out_op ? nullptr : x_or_out; e.ld_f32 = N;
@@ -1117,6 +1123,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  if (strcmp(name, "epilogue_tma") == 0) { gemm_set_epilogue_tma(value != 0); drop_graphs(h); return 0; }
   if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }
   return fail(h, std::string("unknown option ") + name);
 }
@@ -1156,6 +1163,15 @@ int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_t M, int32
   if (!h) return 1;
   if (!h->finalized) return fail(h, "weights not finalized");
   CK(run_visual_cnn(h, static_cast<cudaStream_t>(cuda_stream), frames, M, Hh, Ww, pooled));
+  return 0;
+}
+
+// Debug: tcgen05 CNN with a phase trace ([grid][64] globaltimer stamps of each CTA's second frame group).
+int avsep_test_visual_cnn_trace(avsep_handle* h, const float* frames, int32_t M, void* pooled,
+                                unsigned long long* trace_dev, void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "weights not finalized");
+  CK(run_visual_cnn(h, static_cast<cudaStream_t>(cuda_stream), frames, M, 32, 32, pooled, trace_dev));
   return 0;
 }
 

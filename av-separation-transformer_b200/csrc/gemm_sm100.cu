@@ -43,7 +43,7 @@ constexpr int NUM_THREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
 constexpr int RED_OFFSET = BAR_OFFSET + 256;                 // LN partial statistics: [2 parity][128 rows][4 parts] float2
 constexpr int VEC_OFFSET = RED_OFFSET + 2 * 128 * 4 * 8;   // bias [2][256], gamma [256], beta [256] fp32
-constexpr int STG_OFFSET = (VEC_OFFSET + 4 * BN_MAX * 4 + 127) / 128 * 128;   // per-epilogue-warp 4 KB transpose buffers
+constexpr int STG_OFFSET = (VEC_OFFSET + 4 * BN_MAX * 4 + 1023) / 1024 * 1024;   // 16 x 4 KB = four 128-row x 128-B slabs (one per column part)
 constexpr int SMEM_TOTAL = STG_OFFSET + NUM_EPI_WARPS * 4096 + 1024;
 static_assert(SMEM_TOTAL <= 227 * 1024, "gemm: shared memory budget exceeded");
 constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator stages
@@ -51,6 +51,7 @@ constexpr int TMEM_COLS = 2 * BN_MAX;                        // two accumulator 
 struct GemmDev {
   int M, N, K, taps, tap_stride, row_shift, n_tile;
   GemmEpilogue e;
+  int use_tma;                 // epilogue I/O through TMA slabs (ROW_IDENT, 64-column aligned)
   unsigned long long* trace;   // optional [grid][64] globaltimer stamps (debug hook), else null:
                                //   [0] entry [1] setup done [7] CTA done; per local tile lt < 12 at 8 + 4*lt:
                                //   +0 first operands of the tile landed, +1 tile's MMAs issued, +2 accumulator ready
@@ -245,7 +246,8 @@ __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo
 
 template <int EPI, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmDev p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmOp, const __grid_constant__ CUtensorMap tmF32, const GemmDev p) {
   // Dynamic shared memory is declared 1024-byte aligned (128B-swizzle atoms) and used directly: deriving the base
   // through an integer round trip would make the compiler fall back to generic LD/ST for every access.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -255,7 +257,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator stage complete
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator stage drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* resid_bar = tempty_bar + 2;         // [4] residual slab of column part p landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 4);
   float2* red = reinterpret_cast<float2*>(smem + RED_OFFSET);
   float* sbias = reinterpret_cast<float*>(smem + VEC_OFFSET);       // [2][BN_MAX], double-buffered per tile
   float* sgamma = sbias + 2 * BN_MAX;
@@ -285,10 +288,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) mbar_init(&resid_bar[a], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-  if constexpr (EPI == EPI_LN) {
+  if constexpr (EPI == EPI_LN || EPI == EPI_LN_TMA) {
     if (p.e.ln_gamma != nullptr) {
       for (int i = threadIdx.x; i < p.n_tile; i += NUM_THREADS) {
         sgamma[i] = __ldg(p.e.ln_gamma + i);
@@ -363,6 +368,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int part = (warp - 2) >> 2;            // 0..3
     const int r = q * 32 + lane;
     const GemmEpilogue& e = p.e;
+    uint8_t* const slab = stg_all + part * 16384;            // this column part's 128-row x 128-B slab (TMA box)
+    uint8_t* const slab_q = slab + q * 4096;                 // this warp's 32 rows of it
+    const bool elected = (warp == 2 + 4 * part) && (lane == 0);   // issues this part's TMA loads / stores
+    const int part_bar = 6 + part;                            // named barrier of the part's 4 warps (128 threads)
+    uint32_t rph = 0;                                         // parity of resid_bar[part]
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -375,6 +385,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       {
         const int i = threadIdx.x - 64;                       // 0..511 over the 16 epilogue warps
         if (i < BN_MAX) sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
+      }
+      if constexpr (EPI == EPI_LN_TMA) {
+        // TMA epilogue: fetch the residual slab of this part's first chunk while the main loop runs
+        if (e.resid != nullptr && elected) {
+          bulk_wait_read0();                                    // previous tile's stores have left the slab
+          mbar_arrive_expect_tx(&resid_bar[part], 16384);
+          tma_load_2d(slab, &tmF32, &resid_bar[part], part * 64, m0);
+        }
       }
       if (lt == 1 && threadIdx.x == 64) TRACE(2);               // [2] tile-1 epilogue entered (bias load issued)
       asm volatile("bar.sync 5, 512;" ::: "memory");            // bias slice visible to all epilogue warps
@@ -423,6 +441,106 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+      } else if constexpr (EPI == EPI_LN_TMA) {
+        // ---- LN epilogue with TMA I/O (n_tile == 256, ROW_IDENT): each column part owns 64 columns = 2 chunks.
+        // residual chunk: TMA-loaded slab -> own-row LDS; x' chunk: own-row STS into the same slab -> one TMA store;
+        // normalised bf16 row (64 columns = 128 B): own-row STS -> one TMA store.  No per-element address math.
+        const RowInfo ri = row_info(e, m, p.M);
+        float val[2][32];
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = part * 64 + ci * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+          if (e.resid != nullptr) {
+            mbar_wait(&resid_bar[part], rph);
+            rph ^= 1;
+          }
+          tmem_ld_wait();
+          value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
+          if (e.resid != nullptr) stg_add_own_f32(slab_q, lane, val[ci]);
+          if (e.out_f32 != nullptr) {
+            stg_write_own_f32(slab_q, lane, val[ci]);
+            fence_proxy_async_smem();
+          }
+          if (e.out_f32 != nullptr || (e.resid != nullptr && ci == 0)) named_bar_sync(part_bar, 128);
+          if (elected) {
+            if (e.out_f32 != nullptr) {
+              tma_store_2d(&tmF32, slab, c0, m0);
+              bulk_commit();
+            }
+            if (ci == 0 && e.resid != nullptr) {
+              bulk_wait_read0();                              // the store has read the slab: refill it
+              mbar_arrive_expect_tx(&resid_bar[part], 16384);
+              tma_load_2d(slab, &tmF32, &resid_bar[part], c0 + 32, m0);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sum += val[ci][j];
+            sq = fmaf(val[ci][j], val[ci][j], sq);
+          }
+        }
+        // accumulator fully read: hand the TMEM stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (e.ln_gamma != nullptr) {
+          // row statistics: this part's (sum, sum of squares about the part mean) merged over the 4 parts
+          const float mean_h = sum * (1.0f / 64.0f);
+          const float m2 = fmaxf(sq - sum * mean_h, 0.f);
+          float2* slot = red + ((lt & 1) * 128 + r) * 4;
+          slot[part] = make_float2(mean_h, m2);
+          named_bar_sync(1 + q, 128);
+          const float2 s0 = slot[0], s1 = slot[1], s2 = slot[2], s3 = slot[3];
+          const float mean = 0.25f * ((s0.x + s1.x) + (s2.x + s3.x));
+          const float d0 = s0.x - mean, d1 = s1.x - mean, d2 = s2.x - mean, d3 = s3.x - mean;
+          const float m2_all = (s0.y + s1.y) + (s2.y + s3.y) + 64.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+          const float rstd = rsqrtf(m2_all * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c0 = part * 64 + ci * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = *reinterpret_cast<const float4*>(sgamma + c0 + j);
+              const float4 b4 = *reinterpret_cast<const float4*>(sbeta + c0 + j);
+              val[ci][j] = (val[ci][j] - mean) * rstd * g4.x + b4.x;
+              val[ci][j + 1] = (val[ci][j + 1] - mean) * rstd * g4.y + b4.y;
+              val[ci][j + 2] = (val[ci][j + 2] - mean) * rstd * g4.z + b4.z;
+              val[ci][j + 3] = (val[ci][j + 3] - mean) * rstd * g4.w + b4.w;
+            }
+          }
+        }
+        if (e.out_op != nullptr) {
+          if (elected) bulk_wait_read0();                     // last x' store has read the slab
+          named_bar_sync(part_bar, 128);
+          if constexpr (TF32) {
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+              stg_write_own_f32(slab_q, lane, val[ci]);
+              fence_proxy_async_smem();
+              named_bar_sync(part_bar, 128);
+              if (elected) {
+                tma_store_2d(&tmOp, slab, part * 64 + ci * 32, m0);
+                bulk_commit();
+                bulk_wait_read0();
+              }
+              named_bar_sync(part_bar, 128);
+            }
+          } else {
+            stg_write_own_bf16(slab_q, lane, 0, val[0]);
+            stg_write_own_bf16(slab_q, lane, 4, val[1]);
+            fence_proxy_async_smem();
+            named_bar_sync(part_bar, 128);
+            if (elected) {
+              tma_store_2d(&tmOp, slab, part * 64, m0);
+              bulk_commit();
+            }
+          }
+        }
+        if (threadIdx.x == 64) TRACE_TILE(lt, 3);     // LN: epilogue done
+        continue;   // tempty already signalled
       } else if constexpr (EPI == EPI_LN) {
         // value = acc + bias (+act, +PE) + residual; fp32 residual-stream store; LayerNorm over the whole row;
         // operand store.  Each warp owns 32 rows x (n_tile/2) contiguous columns; all global traffic goes through
@@ -554,7 +672,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // 128-byte bf16 row (or one chunk as a 128-byte fp32 row) and stores whole lines.
         const bool coalesced = (p.N % 64 == 0) && (p.n_tile % 64 == 0) && (e.out_op == nullptr || (e.ld_op & 63) == 0) &&
                                (e.out_f32 == nullptr || (e.ld_f32 & 31) == 0);
-        if (coalesced) {
+        if (p.use_tma) {
+          // ---- TMA-store epilogue: each part stages one 64-column unit (128-B bf16 rows, or two 32-column fp32
+          // slabs) in its swizzled slab with thread-per-row STS; one elected thread stores the whole 128-row box.
+          const int npair = p.n_tile >> 6;
+          for (int pi = part; pi < npair; pi += 4) {
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              const int c0 = pi * 64 + hc * 32;
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
+              tmem_ld_wait();
+              float a[32];
+              value_chunk<false>(e, ri, v, a, sb + c0, n0 + c0, 32, p.N);
+              const bool f32_slab = (e.out_f32 != nullptr) || TF32;
+              if (f32_slab) {                                  // one 32-column fp32 slab per chunk
+                if (elected) bulk_wait_read0();
+                named_bar_sync(part_bar, 128);
+                stg_write_own_f32(slab_q, lane, a);
+                fence_proxy_async_smem();
+                named_bar_sync(part_bar, 128);
+                if (elected) {
+                  if (e.out_f32 != nullptr) tma_store_2d(&tmF32, slab, n0 + c0, m0);
+                  if (TF32 && e.out_op != nullptr) tma_store_2d(&tmOp, slab, n0 + c0, m0);
+                  bulk_commit();
+                }
+              }
+              if (!TF32 && e.out_op != nullptr) {
+                if (hc == 0) {
+                  if (elected) bulk_wait_read0();
+                  named_bar_sync(part_bar, 128);
+                }
+                stg_write_own_bf16(slab_q, lane, hc * 4, a);
+                if (hc == 1) {
+                  fence_proxy_async_smem();
+                  named_bar_sync(part_bar, 128);
+                  if (elected) {
+                    tma_store_2d(&tmOp, slab, n0 + pi * 64, m0);
+                    bulk_commit();
+                  }
+                }
+              }
+            }
+          }
+        } else if (coalesced) {
           const int npair = p.n_tile >> 6;
           const unsigned long long f32_row =
               (ri.valid && e.out_f32 != nullptr) ? reinterpret_cast<unsigned long long>(e.out_f32 + static_cast<size_t>(ri.orow) * e.ld_f32 + n0) : 0ull;
@@ -633,6 +794,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (p.use_tma && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) bulk_wait0();   // outstanding TMA stores
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TRACE(7);              // all tiles of this CTA done
@@ -647,10 +809,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_num_sms = 0;
+bool g_epi_tma = true;   // A/B switch (gemm_set_epilogue_tma)
 
 const char* encode_2d(CUtensorMap* map, bool tf32, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                       uint32_t box_inner, uint32_t box_outer) {
-  const uint64_t esz = tf32 ? 4 : 2;
+  const uint64_t esz = tf32 ? 4 : 2;   // tf32 == true also serves plain fp32 tensors (epilogue slabs)
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return "gemm: operand pointer not 16-byte aligned";
   if (((ld_elems * esz) & 15) != 0) return "gemm: operand leading dimension not a multiple of 16 bytes";
   cuuint64_t dims[2] = {inner, outer};
@@ -666,7 +829,8 @@ const char* encode_2d(CUtensorMap* map, bool tf32, const void* ptr, uint64_t inn
 }
 
 template <int EPI, bool TF32>
-const char* launch_cfg(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw, const GemmDev& d) {
+const char* launch_cfg(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& top,
+                       const CUtensorMap& tf32m, const GemmDev& d) {
   static bool attr_done = false;
   auto kern = gemm_tcgen05_kernel<EPI, TF32>;
   if (!attr_done) {
@@ -676,7 +840,7 @@ const char* launch_cfg(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap&
   }
   const int tiles = ((d.M + BM - 1) / BM) * ((d.N + d.n_tile - 1) / d.n_tile);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, SMEM_TOTAL, s>>>(ta, tw, d);
+  kern<<<grid, NUM_THREADS, SMEM_TOTAL, s>>>(ta, tw, top, tf32m, d);
   if (cudaGetLastError() != cudaSuccess) return "gemm: kernel launch failed";
   return nullptr;
 }
@@ -698,6 +862,8 @@ const char* gemm_init() {
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   return nullptr;
 }
+
+void gemm_set_epilogue_tma(bool on) { g_epi_tma = on; }
 
 bool gemm_ln_fusable(int N) { return N <= BN_MAX && N >= 32 && (N % 32) == 0; }
 
@@ -731,10 +897,29 @@ const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const Ge
   const uint32_t box_k = tf32 ? 32 : 64;
   if (const char* err = encode_2d(&ta, tf32, p.A, p.K, p.rowsA, p.lda, box_k, BM)) return err;
   if (const char* err = encode_2d(&tw, tf32, p.W, static_cast<uint64_t>(p.ldw), p.N, p.ldw, box_k, n_tile)) return err;
+  // Epilogue I/O through TMA slabs: rows map one-to-one (no Conv1d halo remap), columns in 64-wide units.
+  CUtensorMap top = ta, tf32m = ta;   // placeholders when unused
+  bool use_tma = g_epi_tma && e.kind != EPI_TAIL && e.rowmap == ROW_IDENT && (p.N % 64 == 0) && (n_tile % 64 == 0);
+  if (e.kind == EPI_STD && e.out_f32 != nullptr && e.out_op != nullptr && !tf32) use_tma = false;   // one slab, one output
+  if (e.kind == EPI_LN) {
+    use_tma = use_tma && n_tile == 256 && (e.resid == nullptr || e.resid == e.out_f32 || e.out_f32 == nullptr);
+    if (use_tma && e.resid != nullptr && e.out_f32 == nullptr) use_tma = false;   // residual map is the out_f32 map
+  }
+  if (use_tma) {
+    if (e.out_op != nullptr) {
+      if (encode_2d(&top, tf32, e.out_op, p.N, p.M, e.ld_op, tf32 ? 32 : 64, BM)) use_tma = false;
+    }
+    if (use_tma && e.out_f32 != nullptr) {
+      if (encode_2d(&tf32m, true, e.out_f32, p.N, p.M, e.ld_f32, 32, BM)) use_tma = false;
+    }
+  }
+  d.use_tma = use_tma ? 1 : 0;
   switch (e.kind) {
-    case EPI_STD: return tf32 ? launch_cfg<EPI_STD, true>(s, ta, tw, d) : launch_cfg<EPI_STD, false>(s, ta, tw, d);
-    case EPI_TAIL: return tf32 ? launch_cfg<EPI_TAIL, true>(s, ta, tw, d) : launch_cfg<EPI_TAIL, false>(s, ta, tw, d);
-    case EPI_LN: return tf32 ? launch_cfg<EPI_LN, true>(s, ta, tw, d) : launch_cfg<EPI_LN, false>(s, ta, tw, d);
+    case EPI_STD: return tf32 ? launch_cfg<EPI_STD, true>(s, ta, tw, top, tf32m, d) : launch_cfg<EPI_STD, false>(s, ta, tw, top, tf32m, d);
+    case EPI_TAIL: return tf32 ? launch_cfg<EPI_TAIL, true>(s, ta, tw, top, tf32m, d) : launch_cfg<EPI_TAIL, false>(s, ta, tw, top, tf32m, d);
+    case EPI_LN:
+      if (use_tma) return tf32 ? launch_cfg<EPI_LN_TMA, true>(s, ta, tw, top, tf32m, d) : launch_cfg<EPI_LN_TMA, false>(s, ta, tw, top, tf32m, d);
+      return tf32 ? launch_cfg<EPI_LN, true>(s, ta, tw, top, tf32m, d) : launch_cfg<EPI_LN, false>(s, ta, tw, top, tf32m, d);
     default: return "gemm: unknown epilogue";
   }
 }

@@ -15,7 +15,7 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 //                   the Conv1d zero padding); out row = m, halo rows are written as zeros
 //   ROW_PAD2COMPACT padded space in, compact (B*L) rows out; halo rows are dropped
 enum RowMap { ROW_IDENT = 0, ROW_PAD2PAD = 1, ROW_PAD2COMPACT = 2 };
-enum EpiKind { EPI_STD = 0, EPI_TAIL = 1, EPI_LN = 2 };
+enum EpiKind { EPI_STD = 0, EPI_TAIL = 1, EPI_LN = 2, EPI_LN_TMA = 3 };   // EPI_LN_TMA is selected internally by launch_gemm
 
 struct GemmProblem {
   const void* A;   // [rowsA, K] K-major activations (bf16 or fp32/tf32), leading dimension lda (elements)
@@ -60,6 +60,7 @@ const char* gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attribu
 const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const GemmEpilogue& e, int force_bn = 0,
                         unsigned long long* trace = nullptr);   // trace: [grid][8] globaltimer stamps (debug)
 bool gemm_ln_fusable(int N);   // EPI_LN usable for this row width
+void gemm_set_epilogue_tma(bool on);   // A/B switch: epilogue I/O through TMA slabs (default on)
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).
@@ -92,7 +93,8 @@ size_t visual_cnn_tc_w2_bytes();
 size_t visual_cnn_tc_w3_bytes();
 void visual_cnn_tc_pack(const float* w2, const float* w3, uint8_t* w2_slabs, uint8_t* w3_rows);
 const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
-                                 const uint8_t* w3_rows, void* pooled, int num_sms);
+                                 const uint8_t* w3_rows, void* pooled, int num_sms,
+                                 unsigned long long* trace = nullptr);
 size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint32)
 void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3);
 

@@ -44,7 +44,16 @@ struct CnnTcDev {
   const uint8_t* w2_slabs; const float* b2;
   const float* b3;
   int M, num_groups;
+  unsigned long long* trace;   // optional [grid][64] globaltimer stamps of the CTA's 2nd group (debug), else null
 };
+
+__device__ __forceinline__ unsigned long long cnn_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+#define CTRACE(slot) do { if (p.trace != nullptr && tid == 0 && grp == static_cast<int>(blockIdx.x + gridDim.x)) \
+    p.trace[blockIdx.x * 64 + (slot)] = cnn_gtime(); } while (0)
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
@@ -166,6 +175,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
 
   for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
     const int frame0 = grp * GROUP;
+    CTRACE(0);
     // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
     if (tid == 0) {
       for (int t = 0; t < 3; ++t) {
@@ -186,6 +196,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
       }
       __syncthreads();
+      CTRACE(1 + pair * 5);          // input staged
       {
         const int next_first = (pair + 1 < GROUP / 2) ? frame0 + (pair + 1) * 2 : (grp + static_cast<int>(gridDim.x)) * GROUP;
         prefetch_pair(next_first);
@@ -217,8 +228,10 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       }
       __syncthreads();
 
+      CTRACE(2 + pair * 5);          // conv1 done
       // deferred epilogue of the previous pair: its MMAs had the staging + conv1 above to complete
       if (pair > 0) conv2_epilogue(pair - 1);
+      CTRACE(3 + pair * 5);          // deferred conv2 epilogue done
 
       // ---- conv2: 5 slabs of two taps ----
       for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
@@ -254,8 +267,10 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
           if (j == W2_SLABS - 1) umma_commit(bar_acc);
         }
       }
+      CTRACE(4 + pair * 5);          // conv2 slabs built + MMAs issued
     }
     conv2_epilogue(GROUP / 2 - 1);
+    CTRACE(21);                      // last conv2 epilogue done
 
     // ---- conv3: one slab per tap, weights streamed by TMA ----
     for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
@@ -294,8 +309,10 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         if (t == 8) umma_commit(bar_acc);
       }
     }
+    CTRACE(22);                      // conv3 slabs built + MMAs issued
     // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
     mbar_wait(bar_acc, acc_phase);
+    CTRACE(23);                      // conv3 accumulator ready
     acc_phase ^= 1;
     tc_fence_after();
     {
@@ -328,6 +345,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     }
     tc_fence_before();
     __syncthreads();
+    CTRACE(24);                      // group done
   }
 
   tc_fence_before();
@@ -372,7 +390,7 @@ void visual_cnn_tc_pack(const float* w2, const float* w3, uint8_t* w2_slabs, uin
 }
 
 const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
-                                 const uint8_t* w3_rows, void* pooled, int num_sms) {
+                                 const uint8_t* w3_rows, void* pooled, int num_sms, unsigned long long* trace) {
   if (M <= 0) return "visual_cnn_tc: empty problem";
   static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (encode == nullptr) {
@@ -402,6 +420,7 @@ const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, con
   d.frames = frames; d.pooled = reinterpret_cast<__nv_bfloat16*>(pooled);
   d.w1 = w.w1; d.b1 = w.b1; d.w2_slabs = w2_slabs; d.b2 = w.b2; d.b3 = w.b3;
   d.M = M; d.num_groups = (M + GROUP - 1) / GROUP;
+  d.trace = trace;
   const int grid = d.num_groups < num_sms ? d.num_groups : num_sms;
   visual_cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, d);
   return cudaGetLastError() == cudaSuccess ? nullptr : "visual_cnn_tc: launch failed";

@@ -133,6 +133,8 @@ AVSEP_API int avsep_test_add_layernorm(avsep_handle* h, const float* x, const fl
                              float* x_out, void* out_op, int32_t M, int32_t d, void* cuda_stream);
 AVSEP_API int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_t M, int32_t Hh, int32_t Ww, void* pooled,
                           void* cuda_stream);
+AVSEP_API int avsep_test_visual_cnn_trace(avsep_handle* h, const float* frames, int32_t M, void* pooled,
+                                          unsigned long long* trace_dev, void* cuda_stream);
 
 #ifdef __cplusplus
 }
