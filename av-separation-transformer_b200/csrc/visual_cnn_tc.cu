@@ -22,7 +22,8 @@ namespace avsep {
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_BUILDERS = 256;          // 8 warps: gather im2col slabs, conv1, epilogues
+constexpr int TC_THREADS = TC_BUILDERS + 32;   // + 1 MMA-issuer warp
 constexpr int GROUP = 8;                 // frames per conv3 tile
 constexpr int SLAB_BYTES = 128 * 128;    // 128 rows x 128 B
 constexpr int W2_SLABS = 5, W2_SLAB_BYTES = 64 * 128;
@@ -86,26 +87,28 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   uint8_t* act2 = smem + OFF_ACT2;
   uint8_t* act1 = smem + OFF_ACT1;
   float* sIn = reinterpret_cast<float*>(smem + OFF_IN);
-  uint64_t* bar_ring = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [2] MMAs that read ring slot s have completed
-  uint64_t* bar_acc = bar_ring + 2;                               // accumulator complete
-  uint64_t* bar_w3 = bar_acc + 1;                                 // [3] W3 slab landed
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [2] slab written by all 8 builder warps
+  uint64_t* ring_free = ring_full + 2;                             // [2] MMAs that read the slab have completed
+  uint64_t* bar_acc = ring_free + 2;                               // accumulator complete
+  uint64_t* bar_w3 = bar_acc + 1;                                  // [3] W3 slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w3 + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gid = lane >> 2, tig = lane & 3;
 
   for (int i = tid; i < W2_SLABS * W2_SLAB_BYTES / 16; i += TC_THREADS)
     reinterpret_cast<uint4*>(w2s)[i] = reinterpret_cast<const uint4*>(p.w2_slabs)[i];
   for (int i = tid; i < 2 * 34 * 34; i += TC_THREADS) sIn[i] = 0.f;
   if (tid == 0) {
     tma_prefetch_desc(&tmW3);
-    mbar_init(&bar_ring[0], 1);
-    mbar_init(&bar_ring[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ring_full[i], TC_BUILDERS / 32);
+      mbar_init(&ring_free[i], 1);
+    }
     mbar_init(bar_acc, 1);
     for (int i = 0; i < 3; ++i) mbar_init(&bar_w3[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == TC_BUILDERS / 32) tmem_alloc(tmem_slot, 256);
   fence_proxy_async_smem();     // W2 slabs were written with generic stores, read by the tensor core
   tc_fence_before();
   __syncthreads();
@@ -113,244 +116,292 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc2 = tmem_base;          // 64 columns
   const uint32_t tmem_acc3 = tmem_base + 64;     // 128 columns
-  const uint32_t idesc2 = umma_idesc(1u, 128, 64);
-  const uint32_t idesc3 = umma_idesc(1u, 128, 128);
 
-  uint32_t n_slab = 0;      // slabs pushed through the ring so far (all threads keep the same count)
-  uint32_t acc_phase = 0;
-  uint32_t n_w3 = 0;        // W3 slabs consumed so far
-
-  // conv1 B fragments and bias (constant, registers)
-  uint32_t bw1[4][2];
-  float bias1[4][2];
+  if (warp == TC_BUILDERS / 32) {
+    // =========================== MMA issuer (one lane) ===========================
+    if (lane == 0) {
+      const uint32_t idesc2 = umma_idesc(1u, 128, 64);
+      const uint32_t idesc3 = umma_idesc(1u, 128, 128);
+      uint32_t n_slab = 0, n_w3 = 0;
+      for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+        for (int pair = 0; pair < GROUP / 2; ++pair) {
+          for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+            const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+            mbar_wait(&ring_full[slot], use & 1);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w2s + j * W2_SLAB_BYTES), 1024);
+            const int ksteps = (j == W2_SLABS - 1) ? 2 : 4;     // the last slab holds tap 8 only
+            for (int k = 0; k < ksteps; ++k)
+              umma_f16(tmem_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&ring_free[slot]);
+            if (j == W2_SLABS - 1) umma_commit(bar_acc);
+          }
+        }
+        for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
+          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          mbar_wait(&ring_full[slot], use & 1);
+          const uint32_t ws = n_w3 % 3;
+          mbar_wait(&bar_w3[ws], (n_w3 / 3) & 1);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) {
-    bw1[nt][0] = __ldg(p.w1 + nt * 64 + lane * 2);
-    bw1[nt][1] = __ldg(p.w1 + nt * 64 + lane * 2 + 1);
-    bias1[nt][0] = __ldg(p.b1 + nt * 8 + 2 * tig);
-    bias1[nt][1] = __ldg(p.b1 + nt * 8 + 2 * tig + 1);
-  }
-  const int k0 = 2 * tig, k1 = 2 * tig + 1;
-  const int off0 = (k0 / 3) * 34 + (k0 % 3), off1 = (k1 / 3) * 34 + (k1 % 3), off8 = 2 * 34 + 2;
-
-  // Input prefetch: each thread keeps the next pair's two float4 pieces (2 frames x 1024 px / 256 threads) in
-  // registers, so the global-load latency hides behind the current pair's conv1/conv2.
-  float4 pre[2];
-  auto prefetch_pair = [&](int first_frame) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int id = tid + TC_THREADS * i;
-      const int f = id >> 8, rem = id & 255;
-      const int fr = first_frame + f;
-      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (fr < p.M) pre[i] = __ldg(reinterpret_cast<const float4*>(p.frames + static_cast<size_t>(fr) * 1024) + rem);
-    }
-  };
-  // conv2 epilogue of one pair: acc (128 px x 64 ch) -> bias + ReLU -> act2
-  auto conv2_epilogue = [&](int pair_idx) {
-    mbar_wait(bar_acc, acc_phase);
-    acc_phase ^= 1;
-    tc_fence_after();
-    const int q = warp & 3, hh = warp >> 2;              // lane quarter, 32-column half
-    const int r = q * 32 + lane;                          // row = (f, y2, x2) of this pair
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem_acc2 + (static_cast<uint32_t>(q * 32) << 16) + hh * 32, v);
-    tmem_ld_wait();
-    const int pixel = pair_idx * 128 + r;                 // pixel index inside the 8-frame act2 block
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 u;
-      const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8));
-      const float4 bc = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + c * 8 + 4));
-      u.x = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 1]) + ba.y, 0.f));
-      u.y = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 3]) + ba.w, 0.f));
-      u.z = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 4]) + bc.x, 0.f), fmaxf(__uint_as_float(v[c * 8 + 5]) + bc.y, 0.f));
-      u.w = pack_bf16x2(fmaxf(__uint_as_float(v[c * 8 + 6]) + bc.z, 0.f), fmaxf(__uint_as_float(v[c * 8 + 7]) + bc.w, 0.f));
-      *reinterpret_cast<uint4*>(act2 + act2_chunk_off(pixel, hh * 4 + c)) = u;
-    }
-    tc_fence_before();
-    __syncthreads();     // act2 rows of this pair visible; acc2 drained
-  };
-  prefetch_pair(blockIdx.x * GROUP);
-
-  for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
-    const int frame0 = grp * GROUP;
-    CTRACE(0);
-    // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
-    if (tid == 0) {
-      for (int t = 0; t < 3; ++t) {
-        const uint32_t slot = (n_w3 + t) % 3;
-        mbar_arrive_expect_tx(&bar_w3[slot], SLAB_BYTES);
-        tma_load_2d(w3s + slot * SLAB_BYTES, &tmW3, &bar_w3[slot], 0, t * 128);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, adesc + 2 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
+          umma_commit(&ring_free[slot]);
+          if (t == 8) umma_commit(bar_acc);
+        }
       }
     }
+  } else {
+    // =========================== builders / epilogue (8 warps) ===========================
+    const int gid = lane >> 2, tig = lane & 3;
+    uint32_t n_slab = 0;      // slabs pushed through the ring so far
+    uint32_t acc_phase = 0;
+    uint32_t n_w3 = 0;        // W3 slabs requested so far (this thread mirrors the issuer's count)
 
-    for (int pair = 0; pair < GROUP / 2; ++pair) {
-      // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) from the prefetch registers ----
+    // ---- per-thread gather/scatter constants: thread handles chunk c of rows rb, rb+32, rb+64, rb+96 of every slab
+    const int c = tid & 7, rb = tid >> 3;
+    const uint32_t dst0 = static_cast<uint32_t>(rb * 128 + ((c ^ (rb & 7)) << 4));   // + i*4096
+    // conv2 (rows = (f, y2, x2) of a pair): x2 = rb&7, y2 = (rb>>3) + 4*(i&1), f = i>>1; source act1 (swizzled lines)
+    const int cc2 = c & 3, taphalf = c >> 2;
+    int xo2[3], rowbase2[4];
+    bool vx2[3], top2[4];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = 2 * (rb & 7) + kx - 1;
+      vx2[kx] = xx >= 0 && xx < 16;
+      xo2[kx] = (xx >> 1) * 128 + (((((xx & 1) << 2) | cc2) ^ ((xx >> 1) & 7)) << 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y2 = (rb >> 3) + 4 * (i & 1), f = i >> 1;
+      rowbase2[i] = (f * 256 + (2 * y2 - 1) * 16) * 64;     // + ky*1024 + xo2[kx]
+      top2[i] = (y2 == 0);                                   // tap row ky = 0 falls above the frame
+    }
+    // conv3 (rows = (g, y3, x3) of the group): x3 = rb&3, y3 = (rb>>2)&3, g = (rb>>4) + 2*i; source act2
+    int xo3[3], rowbase3[4];
+    bool vx3[3];
+    const bool top3 = ((rb >> 2) & 3) == 0;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = 2 * (rb & 3) + kx - 1;
+      vx3[kx] = xx >= 0 && xx < 8;
+      xo3[kx] = xx * 128 + ((c ^ (xx & 7)) << 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int g = (rb >> 4) + 2 * i, y3 = (rb >> 2) & 3;
+      rowbase3[i] = (g * 64 + (2 * y3 - 1) * 8) * 128;      // + ky*1024 + xo3[kx]
+    }
+
+    // conv1 B fragments and bias (constant, registers)
+    uint32_t bw1[4][2];
+    float bias1[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      bw1[nt][0] = __ldg(p.w1 + nt * 64 + lane * 2);
+      bw1[nt][1] = __ldg(p.w1 + nt * 64 + lane * 2 + 1);
+      bias1[nt][0] = __ldg(p.b1 + nt * 8 + 2 * tig);
+      bias1[nt][1] = __ldg(p.b1 + nt * 8 + 2 * tig + 1);
+    }
+    const int k0 = 2 * tig, k1 = 2 * tig + 1;
+    const int off0 = (k0 / 3) * 34 + (k0 % 3), off1 = (k1 / 3) * 34 + (k1 % 3), off8 = 2 * 34 + 2;
+
+    // Input prefetch: each thread keeps the next pair's two float4 pieces (2 frames x 1024 px / 256 threads) in
+    // registers, so the global-load latency hides behind the current pair's conv1/conv2.
+    float4 pre[2];
+    auto prefetch_pair = [&](int first_frame) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int id = tid + TC_THREADS * i;
+        const int id = tid + TC_BUILDERS * i;
         const int f = id >> 8, rem = id & 255;
-        const int y = rem >> 3, x4 = (rem & 7) * 4;
-        float* d = sIn + f * 34 * 34 + (y + 1) * 34 + (x4 + 1);
-        d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
+        const int fr = first_frame + f;
+        pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fr < p.M) pre[i] = __ldg(reinterpret_cast<const float4*>(p.frames + static_cast<size_t>(fr) * 1024) + rem);
       }
-      __syncthreads();
-      CTRACE(1 + pair * 5);          // input staged
-      {
-        const int next_first = (pair + 1 < GROUP / 2) ? frame0 + (pair + 1) * 2 : (grp + static_cast<int>(gridDim.x)) * GROUP;
-        prefetch_pair(next_first);
-      }
-
-      // ---- conv1: rows = 2 x 256 output pixels, K = 9 (padded to 16), N = 32 ----
-      for (int t = warp; t < 32; t += TC_THREADS / 32) {
-        uint32_t a[4] = {0, 0, 0, 0};
-        int pix[2];
+    };
+    // hand a finished slab to the MMA issuer
+    auto publish_slab = [&](uint32_t slot) {
+      fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
+      tc_fence_before();            // earlier tcgen05.ld of this thread are ordered before the MMAs this unblocks
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring_full[slot]);
+    };
+    // conv2 epilogue of one pair: acc (128 px x 64 ch) -> bias + ReLU -> act2
+    auto conv2_epilogue = [&](int pair_idx) {
+      mbar_wait(bar_acc, acc_phase);
+      acc_phase ^= 1;
+      tc_fence_after();
+      const int q = warp & 3, hh = warp >> 2;              // lane quarter, 32-column half
+      const int r = q * 32 + lane;                          // row = (f, y2, x2) of this pair
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_acc2 + (static_cast<uint32_t>(q * 32) << 16) + hh * 32, v);
+      tmem_ld_wait();
+      const int pixel = pair_idx * 128 + r;                 // pixel index inside the 8-frame act2 block
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int r = t * 16 + gid + 8 * hf;
-          const int f = r >> 8, rem = r & 255, y = rem >> 4, x = rem & 15;
-          pix[hf] = r;
-          const float* base = sIn + f * 34 * 34 + (2 * y) * 34 + 2 * x;
-          a[hf] = pack_bf16x2(base[off0], base[off1]);
-          if (tig == 0) a[2 + hf] = pack_bf16x2(base[off8], 0.f);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          float c[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c, a[0], a[1], a[2], a[3], bw1[nt][0], bw1[nt][1]);
-          const float bb0 = bias1[nt][0], bb1 = bias1[nt][1];
-          *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[0], nt) + tig * 4) =
-              pack_bf16x2(fmaxf(c[0] + bb0, 0.f), fmaxf(c[1] + bb1, 0.f));
-          *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[1], nt) + tig * 4) =
-              pack_bf16x2(fmaxf(c[2] + bb0, 0.f), fmaxf(c[3] + bb1, 0.f));
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 u;
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + ch * 8));
+        const float4 bc = __ldg(reinterpret_cast<const float4*>(p.b2 + hh * 32 + ch * 8 + 4));
+        u.x = pack_bf16x2(fmaxf(__uint_as_float(v[ch * 8 + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 1]) + ba.y, 0.f));
+        u.y = pack_bf16x2(fmaxf(__uint_as_float(v[ch * 8 + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 3]) + ba.w, 0.f));
+        u.z = pack_bf16x2(fmaxf(__uint_as_float(v[ch * 8 + 4]) + bc.x, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 5]) + bc.y, 0.f));
+        u.w = pack_bf16x2(fmaxf(__uint_as_float(v[ch * 8 + 6]) + bc.z, 0.f), fmaxf(__uint_as_float(v[ch * 8 + 7]) + bc.w, 0.f));
+        *reinterpret_cast<uint4*>(act2 + act2_chunk_off(pixel, hh * 4 + ch)) = u;
+      }
+      tc_fence_before();
+      named_bar_sync(1, TC_BUILDERS);     // act2 rows of this pair visible; acc2 drained
+    };
+    prefetch_pair(blockIdx.x * GROUP);
+
+    for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+      const int frame0 = grp * GROUP;
+      CTRACE(0);
+      // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
+      if (tid == 0) {
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t slot = (n_w3 + t) % 3;
+          mbar_arrive_expect_tx(&bar_w3[slot], SLAB_BYTES);
+          tma_load_2d(w3s + slot * SLAB_BYTES, &tmW3, &bar_w3[slot], 0, t * 128);
         }
       }
-      __syncthreads();
 
-      CTRACE(2 + pair * 5);          // conv1 done
-      // deferred epilogue of the previous pair: its MMAs had the staging + conv1 above to complete
-      if (pair > 0) conv2_epilogue(pair - 1);
-      CTRACE(3 + pair * 5);          // deferred conv2 epilogue done
+      for (int pair = 0; pair < GROUP / 2; ++pair) {
+        // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) from the prefetch registers ----
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int id = tid + TC_BUILDERS * i;
+          const int f = id >> 8, rem = id & 255;
+          const int y = rem >> 3, x4 = (rem & 7) * 4;
+          float* d = sIn + f * 34 * 34 + (y + 1) * 34 + (x4 + 1);
+          d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
+        }
+        named_bar_sync(1, TC_BUILDERS);
+        CTRACE(1 + pair * 5);          // input staged
+        {
+          const int next_first = (pair + 1 < GROUP / 2) ? frame0 + (pair + 1) * 2 : (grp + static_cast<int>(gridDim.x)) * GROUP;
+          prefetch_pair(next_first);
+        }
 
-      // ---- conv2: 5 slabs of two taps ----
-      for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+        // ---- conv1: rows = 2 x 256 output pixels, K = 9 (padded to 16), N = 32 ----
+        for (int t = warp; t < 32; t += TC_BUILDERS / 32) {
+          uint32_t a[4] = {0, 0, 0, 0};
+          int pix[2];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int r = t * 16 + gid + 8 * hf;
+            const int f = r >> 8, rem = r & 255, y = rem >> 4, x = rem & 15;
+            pix[hf] = r;
+            const float* base = sIn + f * 34 * 34 + (2 * y) * 34 + 2 * x;
+            a[hf] = pack_bf16x2(base[off0], base[off1]);
+            if (tig == 0) a[2 + hf] = pack_bf16x2(base[off8], 0.f);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float cacc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(cacc, a[0], a[1], a[2], a[3], bw1[nt][0], bw1[nt][1]);
+            const float bb0 = bias1[nt][0], bb1 = bias1[nt][1];
+            *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[0], nt) + tig * 4) =
+                pack_bf16x2(fmaxf(cacc[0] + bb0, 0.f), fmaxf(cacc[1] + bb1, 0.f));
+            *reinterpret_cast<uint32_t*>(act1 + act1_chunk_off(pix[1], nt) + tig * 4) =
+                pack_bf16x2(fmaxf(cacc[2] + bb0, 0.f), fmaxf(cacc[3] + bb1, 0.f));
+          }
+        }
+        named_bar_sync(1, TC_BUILDERS);
+        CTRACE(2 + pair * 5);          // conv1 done
+
+        // deferred epilogue of the previous pair: its MMAs had the staging + conv1 above to complete
+        if (pair > 0) conv2_epilogue(pair - 1);
+        CTRACE(3 + pair * 5);          // deferred conv2 epilogue done
+
+        // ---- conv2: 5 slabs of two taps, gathered from act1 ----
+        for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
+          uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
+          const int tap = 2 * j + taphalf;
+          const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;                 // tap / 3, tap % 3 for tap < 16
+          const bool okx = (tap < 9) && (kx == 0 ? vx2[0] : (kx == 1 ? vx2[1] : vx2[2]));
+          const int srcx = ky * 1024 + (kx == 0 ? xo2[0] : (kx == 1 ? xo2[1] : xo2[2]));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (okx && !(ky == 0 && top2[i])) val = *reinterpret_cast<const uint4*>(act1 + rowbase2[i] + srcx);
+            *reinterpret_cast<uint4*>(dst + i * 4096) = val;
+          }
+          publish_slab(slot);
+        }
+        CTRACE(4 + pair * 5);          // conv2 slabs built
+      }
+      conv2_epilogue(GROUP / 2 - 1);
+      CTRACE(21);                      // last conv2 epilogue done
+
+      // ---- conv3: one slab per tap gathered from act2; weights streamed by TMA ----
+      for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
         const uint32_t slot = n_slab & 1, use = n_slab >> 1;
-        if (use > 0) mbar_wait(&bar_ring[slot], (use - 1) & 1);
-        uint8_t* slab = ring + slot * SLAB_BYTES;
-        // 128 rows x 8 chunks; 8 consecutive lanes fill one row (conflict-free), 4 rows per thread
+        if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
+        // the MMAs of tap t-2 have completed -> its W3 slot is free: refill it with tap t+1's slab (t+1 >= 3)
+        if (tid == 0 && t >= 2 && t + 1 < 9) {
+          const uint32_t ws = (n_w3 + 1) % 3;
+          mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
+          tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, (t + 1) * 128);
+        }
+        uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
+        const int ky = (t * 11) >> 5, kx = t - 3 * ky;
+        const bool okx = (kx == 0 ? vx3[0] : (kx == 1 ? vx3[1] : vx3[2])) && !(ky == 0 && top3);
+        const int srcx = ky * 1024 + (kx == 0 ? xo3[0] : (kx == 1 ? xo3[1] : xo3[2]));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int id = tid + TC_THREADS * i;
-          const int r = id >> 3, c = id & 7;
-          const int tap = 2 * j + (c >> 2);
           uint4 val = make_uint4(0, 0, 0, 0);
-          if (tap < 9) {
-            const int f = r >> 6, y2 = (r >> 3) & 7, x2 = r & 7;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            const int yy = 2 * y2 + ky - 1, xx = 2 * x2 + kx - 1;
-            if (yy >= 0 && yy < 16 && xx >= 0 && xx < 16)
-              val = *reinterpret_cast<const uint4*>(act1 + act1_chunk_off(f * 256 + yy * 16 + xx, c & 3));
+          if (okx) val = *reinterpret_cast<const uint4*>(act2 + rowbase3[i] + srcx);
+          *reinterpret_cast<uint4*>(dst + i * 4096) = val;
+        }
+        publish_slab(slot);
+      }
+      CTRACE(22);                      // conv3 slabs built
+      // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
+      mbar_wait(bar_acc, acc_phase);
+      CTRACE(23);                      // conv3 accumulator ready
+      acc_phase ^= 1;
+      tc_fence_after();
+      {
+        const int q = warp & 3, hh = warp >> 2;                  // lane quarter (2 frames), 64-column half
+        const int fr = frame0 + q * 2 + (lane >> 4);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          const int col0 = hh * 64 + cc * 32;
+          tmem_ld_32x32b_x32(tmem_acc3 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
+          tmem_ld_wait();
+          float keep0 = 0.f, keep1 = 0.f;
+#pragma unroll
+          for (int jx = 0; jx < 32; ++jx) {
+            float sv = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 8);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+            if ((lane & 15) == (jx & 15)) {       // lane l of each 16-lane half keeps columns l and 16 + l
+              if (jx < 16) keep0 = sv; else keep1 = sv;
+            }
           }
-          *reinterpret_cast<uint4*>(slab + r * 128 + ((c ^ (r & 7)) * 16)) = val;
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(slab), 1024);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w2s + j * W2_SLAB_BYTES), 1024);
-          const int ksteps = (j == W2_SLABS - 1) ? 2 : 4;
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16(tmem_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&bar_ring[slot]);
-          if (j == W2_SLABS - 1) umma_commit(bar_acc);
-        }
-      }
-      CTRACE(4 + pair * 5);          // conv2 slabs built + MMAs issued
-    }
-    conv2_epilogue(GROUP / 2 - 1);
-    CTRACE(21);                      // last conv2 epilogue done
-
-    // ---- conv3: one slab per tap, weights streamed by TMA ----
-    for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
-      const uint32_t slot = n_slab & 1, use = n_slab >> 1;
-      if (use > 0) mbar_wait(&bar_ring[slot], (use - 1) & 1);
-      // the MMAs of tap t-2 have completed -> its W3 slot is free: refill it with tap t+1's slab (t+1 >= 3)
-      if (tid == 0 && t >= 2 && t + 1 < 9) {
-        const uint32_t ws = (n_w3 + 1) % 3;
-        mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
-        tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, (t + 1) * 128);
-      }
-      uint8_t* slab = ring + slot * SLAB_BYTES;
-      const int ky = t / 3, kx = t - ky * 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int id = tid + TC_THREADS * i;
-        const int r = id >> 3, c = id & 7;
-        const int g = r >> 4, y3 = (r >> 2) & 3, x3 = r & 3;
-        const int yy = 2 * y3 + ky - 1, xx = 2 * x3 + kx - 1;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8)
-          val = *reinterpret_cast<const uint4*>(act2 + act2_chunk_off(g * 64 + yy * 8 + xx, c));
-        *reinterpret_cast<uint4*>(slab + r * 128 + ((c ^ (r & 7)) * 16)) = val;
-      }
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        const uint32_t ws = n_w3 % 3;
-        mbar_wait(&bar_w3[ws], (n_w3 / 3) & 1);
-        tc_fence_after();
-        const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(slab), 1024);
-        const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, adesc + 2 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
-        umma_commit(&bar_ring[slot]);
-        if (t == 8) umma_commit(bar_acc);
-      }
-    }
-    CTRACE(22);                      // conv3 slabs built + MMAs issued
-    // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
-    mbar_wait(bar_acc, acc_phase);
-    CTRACE(23);                      // conv3 accumulator ready
-    acc_phase ^= 1;
-    tc_fence_after();
-    {
-      const int q = warp & 3, hh = warp >> 2;                  // lane quarter (2 frames), 64-column half
-      const int fr = frame0 + q * 2 + (lane >> 4);
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t v[32];
-        const int col0 = hh * 64 + cc * 32;
-        tmem_ld_32x32b_x32(tmem_acc3 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
-        tmem_ld_wait();
-        float keep0 = 0.f, keep1 = 0.f;
-#pragma unroll
-        for (int jx = 0; jx < 32; ++jx) {
-          float sv = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
-          sv += __shfl_xor_sync(0xffffffffu, sv, 8);
-          sv += __shfl_xor_sync(0xffffffffu, sv, 4);
-          sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-          sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-          if ((lane & 15) == (jx & 15)) {       // lane l of each 16-lane half keeps columns l and 16 + l
-            if (jx < 16) keep0 = sv; else keep1 = sv;
+          if (fr < p.M) {
+            __nv_bfloat16* o = p.pooled + static_cast<size_t>(fr) * 128 + col0 + (lane & 15);
+            o[0] = __float2bfloat16_rn(keep0 * (1.f / 16.f));
+            o[16] = __float2bfloat16_rn(keep1 * (1.f / 16.f));
           }
         }
-        if (fr < p.M) {
-          __nv_bfloat16* o = p.pooled + static_cast<size_t>(fr) * 128 + col0 + (lane & 15);
-          o[0] = __float2bfloat16_rn(keep0 * (1.f / 16.f));
-          o[16] = __float2bfloat16_rn(keep1 * (1.f / 16.f));
-        }
       }
+      tc_fence_before();
+      named_bar_sync(1, TC_BUILDERS);
+      CTRACE(24);                      // group done
     }
-    tc_fence_before();
-    __syncthreads();
-    CTRACE(24);                      // group done
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_BUILDERS / 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
