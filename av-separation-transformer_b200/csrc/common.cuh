@@ -28,8 +28,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() default (exact erf)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for our purposes), branch-free:
+// erf(|z|) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2), t = 1 / (1 + p |z|).
+__device__ __forceinline__ float erf_as(float z) {
+  const float az = fabsf(z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-az * az * 1.4426950408889634f);
+  return copysignf(fmaf(-poly, e, 1.0f), z);
+}
+__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() default (erf form)
+  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f));
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }

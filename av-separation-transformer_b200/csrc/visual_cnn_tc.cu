@@ -285,7 +285,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         }
 
         // ---- conv1: rows = 2 x 256 output pixels, K = 9 (padded to 16), N = 32 ----
-        for (int t = warp; t < 32; t += TC_BUILDERS / 32) {
+#pragma unroll
+        for (int t = warp; t < 32; t += TC_BUILDERS / 32) {   // 4 independent m-tiles per warp: unrolled for ILP
           uint32_t a[4] = {0, 0, 0, 0};
           int pix[2];
 #pragma unroll
@@ -374,22 +375,45 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
           const int col0 = hh * 64 + cc * 32;
           tmem_ld_32x32b_x32(tmem_acc3 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
           tmem_ld_wait();
-          float keep0 = 0.f, keep1 = 0.f;
+          // bias + ReLU, then sum the 16 pixel rows of each frame (lanes 0-15 / 16-31) with a transposing butterfly:
+          // every step halves the number of live columns per lane, 30 shuffles instead of 4 per column.
+          float x[32];
 #pragma unroll
-          for (int jx = 0; jx < 32; ++jx) {
-            float sv = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 8);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 4);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-            sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-            if ((lane & 15) == (jx & 15)) {       // lane l of each 16-lane half keeps columns l and 16 + l
-              if (jx < 16) keep0 = sv; else keep1 = sv;
-            }
+          for (int jx = 0; jx < 32; ++jx) x[jx] = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
+#pragma unroll
+          for (int jx = 0; jx < 16; ++jx) {            // lanes with bit3 clear keep columns 0-15, set keep 16-31
+            const bool up = (lane & 8) != 0;
+            const float send = up ? x[jx] : x[jx + 16];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            x[jx] = (up ? x[jx + 16] : x[jx]) + recv;
           }
+#pragma unroll
+          for (int jx = 0; jx < 8; ++jx) {
+            const bool up = (lane & 4) != 0;
+            const float send = up ? x[jx] : x[jx + 8];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            x[jx] = (up ? x[jx + 8] : x[jx]) + recv;
+          }
+#pragma unroll
+          for (int jx = 0; jx < 4; ++jx) {
+            const bool up = (lane & 2) != 0;
+            const float send = up ? x[jx] : x[jx + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            x[jx] = (up ? x[jx + 4] : x[jx]) + recv;
+          }
+#pragma unroll
+          for (int jx = 0; jx < 2; ++jx) {
+            const bool up = (lane & 1) != 0;
+            const float send = up ? x[jx] : x[jx + 2];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            x[jx] = (up ? x[jx + 2] : x[jx]) + recv;
+          }
+          // lane l (within its 16-lane half) now holds the frame sums of columns cbase, cbase+1 with
+          // cbase = 16*bit3 + 8*bit2 + 4*bit1 + 2*bit0
           if (fr < p.M) {
-            __nv_bfloat16* o = p.pooled + static_cast<size_t>(fr) * 128 + col0 + (lane & 15);
-            o[0] = __float2bfloat16_rn(keep0 * (1.f / 16.f));
-            o[16] = __float2bfloat16_rn(keep1 * (1.f / 16.f));
+            const int cbase = ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+            *reinterpret_cast<uint32_t*>(p.pooled + static_cast<size_t>(fr) * 128 + col0 + cbase) =
+                pack_bf16x2(x[0] * (1.f / 16.f), x[1] * (1.f / 16.f));
           }
         }
       }
