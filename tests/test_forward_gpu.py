@@ -144,3 +144,37 @@ def test_errors_are_loud():
         model(torch.zeros(1, 64, 8, device="cuda"), torch.zeros(1, 4, 16, 16, device="cuda"))   # wrong freq_bins
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 65, 5001, device="cuda"), torch.zeros(1, 4, 16, 16, device="cuda"))  # > PE table
+
+
+@pytest.mark.parametrize("option", ["fuse_ln", "epilogue_tma", "cnn_tc", "use_graph"])
+def test_alternative_execution_paths_agree(option):
+    """Every A/B switch of the library (unfused LayerNorm kernel, cooperative epilogue, generic mma.sync CNN, eager
+    launches) must stay parity-green: same golden case, same tolerance."""
+    z, meta = load_golden("c1_dataset")
+    cfg, P, mixed, frames = case_tensors(meta)
+    model = build_model(cfg, P, "bf16")
+    model.prepack()
+    model.engine.set_option(option, 0)
+    try:
+        for _ in range(3):                       # 3 calls: eager warm-up, graph capture, graph replay
+            sep, masks = _run(model, mixed, frames)
+        rep = err_report(sep, masks, z["separated"], z["masks"], mixed)
+        assert rep["masks"] < TOL["bf16"] and rep["separated_scaled"] < TOL["bf16"], (option, rep)
+    finally:
+        model.engine.set_option(option, 1)
+
+
+def test_graph_replay_is_bit_identical_to_eager():
+    cfg = CONFIGS["default"]
+    P = make_state_dict(cfg, seed=71, gain=2.0)
+    mixed, frames = make_inputs(cfg, 8, 63, 50, 32, 32, seed=71, kind="dataset")
+    model = build_model(cfg, P, "bf16")
+    m_t, f_t = torch.from_numpy(mixed).cuda(), torch.from_numpy(frames).cuda()
+    model.prepack()
+    model.engine.set_option("use_graph", 0)
+    sep_e, masks_e = model(m_t, f_t)
+    model.engine.set_option("use_graph", 1)
+    outs = [model(m_t, f_t) for _ in range(4)]
+    torch.cuda.synchronize()
+    for sep_g, masks_g in outs:
+        assert torch.equal(masks_g, masks_e) and torch.equal(sep_g, sep_e)
