@@ -342,16 +342,21 @@ def run_ours(args, rank, local_rank, world):
         breakdown[label] = entry
     top = next(iter(breakdown))
     te = breakdown[top]
+    traffic = None      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and B == 256:
+        with open(tpath) as f:
+            traffic = json.load(f).get(top, {}).get("traffic")
     n_top = max(1, te["launches_per_step"])
     if "tflops" in te:
         roofline = {"kernel": top, "bound": "tensor", "achieved": te["tflops"], "peak": peaks["tensor_sustained"],
-                    "unit": "TFLOP/s", "frac": round(te["tflops"] / peaks["tensor_sustained"], 4), "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(te["tflops"] / peaks["tensor_sustained"], 4), "traffic": traffic,
                     "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)",
                     "launch_ms": round(te["ms_per_step"] / n_top, 4),
                     "algorithmic_flops_per_launch": flops[top] / n_top}
     else:
         roofline = {"kernel": top, "bound": "hbm", "achieved": te["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                    "frac": round(te["gbs"] / peaks["hbm"], 4), "traffic": None, "peak_source": peaks["source"],
+                    "frac": round(te["gbs"] / peaks["hbm"], 4), "traffic": traffic, "peak_source": peaks["source"],
                     "launch_ms": round(te["ms_per_step"] / n_top, 4),
                     "algorithmic_bytes_per_launch": bytes_[top] / n_top}
 
