@@ -16,10 +16,10 @@ namespace avsep {
 namespace {
 
 struct AttnDev {
-  const __nv_bfloat16* q;
+  const void* q;      // bf16 rows, or fp32 rows on the split (fp32-grade) path
   const void* k;
   const void* v;
-  __nv_bfloat16* out;
+  void* out;          // bf16, or fp32 on the split path
   int ldq, ldkv, ldo;
   int H, Lq, Lk, nsrc;
   float scale_log2;
@@ -90,7 +90,50 @@ __device__ __forceinline__ void load_tile_lerp(__nv_bfloat16* dst, const float* 
   }
 }
 
-template <int HD, bool LERP>
+// fp32 source rows -> bf16 hi and lo tiles (x = hi + lo to ~2^-17 relative): the split operands of the fp32-grade
+// path.  nsrc > 0: rows are interpolated on load exactly as in load_tile_lerp.
+template <int HD>
+__device__ __forceinline__ void load_tile_split(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const float* src, int ld,
+                                                int row0, int nrows, int nsrc, float scale) {
+  constexpr int LDS = HD + 8;
+  constexpr int CH = HD / 8;
+  for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    const int t = row0 + r;
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (t < nrows) {
+      if (nsrc > 0) {
+        const float sp = fmaxf(scale * (static_cast<float>(t) + 0.5f) - 0.5f, 0.0f);
+        int i0 = static_cast<int>(sp);
+        if (i0 > nsrc - 1) i0 = nsrc - 1;
+        const int i1 = min(i0 + 1, nsrc - 1);
+        const float w1 = sp - static_cast<float>(i0), w0 = 1.0f - w1;
+        const float4* p0 = reinterpret_cast<const float4*>(src + static_cast<size_t>(i0) * ld + c * 8);
+        const float4* p1 = reinterpret_cast<const float4*>(src + static_cast<size_t>(i1) * ld + c * 8);
+        const float4 a0 = __ldg(p0), a1 = __ldg(p0 + 1), b0 = __ldg(p1), b1 = __ldg(p1 + 1);
+        x[0] = w0 * a0.x + w1 * b0.x; x[1] = w0 * a0.y + w1 * b0.y; x[2] = w0 * a0.z + w1 * b0.z; x[3] = w0 * a0.w + w1 * b0.w;
+        x[4] = w0 * a1.x + w1 * b1.x; x[5] = w0 * a1.y + w1 * b1.y; x[6] = w0 * a1.z + w1 * b1.z; x[7] = w0 * a1.w + w1 * b1.w;
+      } else {
+        const float4* p0 = reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * ld + c * 8);
+        const float4 a0 = __ldg(p0), a1 = __ldg(p0 + 1);
+        x[0] = a0.x; x[1] = a0.y; x[2] = a0.z; x[3] = a0.w; x[4] = a1.x; x[5] = a1.y; x[6] = a1.z; x[7] = a1.w;
+      }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * j]), h1 = __float2bfloat16_rn(x[2 * j + 1]);
+      hi[j] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+      lo[j] = pack_bf16x2(x[2 * j] - __bfloat162float(h0), x[2 * j + 1] - __bfloat162float(h1));
+    }
+    *reinterpret_cast<uint4*>(dst_hi + r * LDS + c * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst_lo + r * LDS + c * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// SPLIT = fp32-grade path: Q/K/V are fp32 in global memory and are staged as bf16 hi + lo tiles; every contraction is
+// three tensor-core products (hi*hi + hi*lo + lo*hi); P is split the same way; the output is fp32.
+template <int HD, bool LERP, bool SPLIT>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   constexpr int LDS = HD + 8;           // padded row (elements): 16-byte rows shifted by 4 banks -> conflict-free ldmatrix
   constexpr int KS = HD / 16;           // k-steps over the head dimension
@@ -99,6 +142,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + QT * LDS;
   __nv_bfloat16* sV = sK + KT * LDS;
+  __nv_bfloat16* sQl = sV + KT * LDS;      // lo tiles (SPLIT only)
+  __nv_bfloat16* sKl = sQl + QT * LDS;
+  __nv_bfloat16* sVl = sKl + KT * LDS;
 
   const int q0 = blockIdx.x * QT;
   const int h = blockIdx.y;
@@ -106,17 +152,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const __nv_bfloat16* qsrc = p.q + static_cast<size_t>(b) * p.Lq * p.ldq + h * HD;
-  load_tile_bf16<HD>(sQ, qsrc, p.ldq, q0, p.Lq);
+  if constexpr (SPLIT) {
+    const float* qsrc = reinterpret_cast<const float*>(p.q) + static_cast<size_t>(b) * p.Lq * p.ldq + h * HD;
+    load_tile_split<HD>(sQ, sQl, qsrc, p.ldq, q0, p.Lq, 0, 0.f);
+  } else {
+    const __nv_bfloat16* qsrc = reinterpret_cast<const __nv_bfloat16*>(p.q) + static_cast<size_t>(b) * p.Lq * p.ldq + h * HD;
+    load_tile_bf16<HD>(sQ, qsrc, p.ldq, q0, p.Lq);
+  }
   __syncthreads();
 
   // Q fragments stay in registers for the whole K/V sweep.
   uint32_t qf[KS][4];
+  uint32_t qfl[SPLIT ? KS : 1][4];
   {
     const int row = warp * 16 + (lane & 15);
     const int col = (lane >> 4) * 8;
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(qf[ks], smem_u32(sQ + row * LDS + ks * 16 + col));
+    for (int ks = 0; ks < KS; ++ks) {
+      ldmatrix_x4(qf[ks], smem_u32(sQ + row * LDS + ks * 16 + col));
+      if constexpr (SPLIT) ldmatrix_x4(qfl[ks], smem_u32(sQl + row * LDS + ks * 16 + col));
+    }
   }
 
   float o[NT_O][4];
@@ -129,7 +184,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   for (int jt = 0; jt < num_kv_tiles; ++jt) {
     const int kv0 = jt * KT;
     __syncthreads();   // previous tile fully consumed
-    if constexpr (LERP) {
+    if constexpr (SPLIT) {
+      const int src_rows = LERP ? p.nsrc : p.Lk;
+      const float* ksrc = reinterpret_cast<const float*>(p.k) + static_cast<size_t>(b) * src_rows * p.ldkv + h * HD;
+      const float* vsrc = reinterpret_cast<const float*>(p.v) + static_cast<size_t>(b) * src_rows * p.ldkv + h * HD;
+      load_tile_split<HD>(sK, sKl, ksrc, p.ldkv, kv0, p.Lk, LERP ? p.nsrc : 0, p.lerp_scale);
+      load_tile_split<HD>(sV, sVl, vsrc, p.ldkv, kv0, p.Lk, LERP ? p.nsrc : 0, p.lerp_scale);
+    } else if constexpr (LERP) {
       const float* ksrc = reinterpret_cast<const float*>(p.k) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
       const float* vsrc = reinterpret_cast<const float*>(p.v) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
       load_tile_lerp<HD>(sK, ksrc, p.ldkv, kv0, p.Lk, p.nsrc, p.lerp_scale);
@@ -158,6 +219,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
         ldmatrix_x4(bf, smem_u32(sK + row * LDS + col));
         mma_bf16_16816(s[2 * np], qf[ks], bf[0], bf[1]);
         mma_bf16_16816(s[2 * np + 1], qf[ks], bf[2], bf[3]);
+        if constexpr (SPLIT) {
+          mma_bf16_16816(s[2 * np], qfl[ks], bf[0], bf[1]);          // lo * hi
+          mma_bf16_16816(s[2 * np + 1], qfl[ks], bf[2], bf[3]);
+          uint32_t bl[4];
+          ldmatrix_x4(bl, smem_u32(sKl + row * LDS + col));
+          mma_bf16_16816(s[2 * np], qf[ks], bl[0], bl[1]);           // hi * lo
+          mma_bf16_16816(s[2 * np + 1], qf[ks], bl[2], bl[3]);
+        }
       }
     }
 
@@ -185,6 +254,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
       l_run[r] *= alpha[r];
     }
     uint32_t pf[4][4];   // P as A fragments for the 4 k-steps over this kv tile
+    uint32_t pfl[SPLIT ? 4 : 1][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float p0 = exp2f(s[nt][0] - m_run[0]);
@@ -195,6 +265,12 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
       l_run[1] += p2 + p3;
       pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
       pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      if constexpr (SPLIT) {
+        const float h0 = __bfloat162float(__float2bfloat16_rn(p0)), h1 = __bfloat162float(__float2bfloat16_rn(p1));
+        const float h2 = __bfloat162float(__float2bfloat16_rn(p2)), h3 = __bfloat162float(__float2bfloat16_rn(p3));
+        pfl[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0 - h0, p1 - h1);
+        pfl[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2 - h2, p3 - h3);
+      }
     }
 #pragma unroll
     for (int i = 0; i < NT_O; ++i) {
@@ -213,6 +289,14 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
         ldmatrix_x4_trans(bf, smem_u32(sV + row * LDS + col));
         mma_bf16_16816(o[2 * np], pf[ks], bf[0], bf[1]);
         mma_bf16_16816(o[2 * np + 1], pf[ks], bf[2], bf[3]);
+        if constexpr (SPLIT) {
+          mma_bf16_16816(o[2 * np], pfl[ks], bf[0], bf[1]);
+          mma_bf16_16816(o[2 * np + 1], pfl[ks], bf[2], bf[3]);
+          uint32_t bl[4];
+          ldmatrix_x4_trans(bl, smem_u32(sVl + row * LDS + col));
+          mma_bf16_16816(o[2 * np], pf[ks], bl[0], bl[1]);
+          mma_bf16_16816(o[2 * np + 1], pf[ks], bl[2], bl[3]);
+        }
       }
     }
   }
@@ -227,7 +311,18 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   const float inv1 = 1.0f / l_run[1];
   const int r0 = q0 + warp * 16 + (lane >> 2);
   const int r1 = r0 + 8;
-  __nv_bfloat16* obase = p.out + static_cast<size_t>(b) * p.Lq * p.ldo + h * HD + 2 * (lane & 3);
+  if constexpr (SPLIT) {
+    float* ob = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.Lq * p.ldo + h * HD + 2 * (lane & 3);
+#pragma unroll
+    for (int nt = 0; nt < NT_O; ++nt) {
+      if (r0 < p.Lq)
+        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r0) * p.ldo + nt * 8) = make_float2(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < p.Lq)
+        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r1) * p.ldo + nt * 8) = make_float2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+    return;
+  }
+  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.Lq * p.ldo + h * HD + 2 * (lane & 3);
 #pragma unroll
   for (int nt = 0; nt < NT_O; ++nt) {
     if (r0 < p.Lq)
@@ -239,11 +334,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   }
 }
 
-template <int HD, bool LERP>
+template <int HD, bool LERP, bool SPLIT>
 const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
-  constexpr int SMEM = 3 * 64 * (HD + 8) * 2;
+  constexpr int SMEM = (SPLIT ? 6 : 3) * 64 * (HD + 8) * 2;
   static bool attr_done = false;
-  auto kern = attention_kernel<HD, LERP>;
+  auto kern = attention_kernel<HD, LERP, SPLIT>;
   if (!attr_done && SMEM > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return "attention: cudaFuncSetAttribute failed";
@@ -257,25 +352,34 @@ const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
 }  // namespace
 
 const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p) {
-  if (prec != PREC_BF16) return "attention: only the bf16 path is implemented";
   if (p.B <= 0 || p.Lq <= 0 || p.Lk <= 0) return "attention: empty problem";
+  const bool split = (prec == PREC_TF32);     // fp32 operands, bf16 hi/lo split contractions, fp32 output
   AttnDev d;
-  d.q = reinterpret_cast<const __nv_bfloat16*>(p.q);
+  d.q = p.q;
   d.k = p.k; d.v = p.v;
-  d.out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  d.out = p.out;
   d.ldq = p.ldq; d.ldkv = p.ldkv; d.ldo = p.ldo;
   d.H = p.H; d.Lq = p.Lq; d.Lk = p.Lk; d.nsrc = p.lerp_src;
   d.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(p.hd));
   d.lerp_scale = p.lerp_src > 0 ? static_cast<float>(p.lerp_src) / static_cast<float>(p.Lk) : 0.f;
   const bool lerp = p.lerp_src > 0;
-  if ((p.ldq & 7) || (p.ldo & 1) || (lerp ? (p.ldkv & 3) : (p.ldkv & 7))) return "attention: misaligned leading dimension";
+  if (split) {
+    if ((p.ldq & 3) || (p.ldo & 1) || (p.ldkv & 3)) return "attention: misaligned leading dimension";
+  } else {
+    if ((p.ldq & 7) || (p.ldo & 1) || (lerp ? (p.ldkv & 3) : (p.ldkv & 7))) return "attention: misaligned leading dimension";
+  }
+#define AVSEP_ATTN_CASE(HDV)                                                                              \
+  case HDV:                                                                                               \
+    if (split) return lerp ? launch_t<HDV, true, true>(s, d, p.B, p.H, p.Lq) : launch_t<HDV, false, true>(s, d, p.B, p.H, p.Lq); \
+    return lerp ? launch_t<HDV, true, false>(s, d, p.B, p.H, p.Lq) : launch_t<HDV, false, false>(s, d, p.B, p.H, p.Lq);
   switch (p.hd) {
-    case 16: return lerp ? launch_t<16, true>(s, d, p.B, p.H, p.Lq) : launch_t<16, false>(s, d, p.B, p.H, p.Lq);
-    case 32: return lerp ? launch_t<32, true>(s, d, p.B, p.H, p.Lq) : launch_t<32, false>(s, d, p.B, p.H, p.Lq);
-    case 64: return lerp ? launch_t<64, true>(s, d, p.B, p.H, p.Lq) : launch_t<64, false>(s, d, p.B, p.H, p.Lq);
-    case 128: return lerp ? launch_t<128, true>(s, d, p.B, p.H, p.Lq) : launch_t<128, false>(s, d, p.B, p.H, p.Lq);
+    AVSEP_ATTN_CASE(16)
+    AVSEP_ATTN_CASE(32)
+    AVSEP_ATTN_CASE(64)
+    AVSEP_ATTN_CASE(128)
     default: return "attention: head dim must be 16, 32, 64 or 128";
   }
+#undef AVSEP_ATTN_CASE
 }
 
 }  // namespace avsep

@@ -735,6 +735,10 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     off["cw1"] = ar.add(p1.data(), p1.size() * 4);
     off["cw2"] = ar.add(p2.data(), p2.size() * 4);
     off["cw3"] = ar.add(p3.data(), p3.size() * 4);
+    visual_cnn_pack(folded[0].data(), folded[1].data(), folded[2].data(), p1.data(), p2.data(), p3.data(), true);
+    off["cw1l"] = ar.add(p1.data(), p1.size() * 4);
+    off["cw2l"] = ar.add(p2.data(), p2.size() * 4);
+    off["cw3l"] = ar.add(p3.data(), p3.size() * 4);
     off["cb1"] = ar.add_f32(fbias[0].data(), 32);
     off["cb2"] = ar.add_f32(fbias[1].data(), 64);
     off["cb3"] = ar.add_f32(fbias[2].data(), 128);
@@ -813,6 +817,9 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->cnn.w1 = reinterpret_cast<const uint32_t*>(P("cw1")); h->cnn.b1 = PF("cb1");
   h->cnn.w2 = reinterpret_cast<const uint32_t*>(P("cw2")); h->cnn.b2 = PF("cb2");
   h->cnn.w3 = reinterpret_cast<const uint32_t*>(P("cw3")); h->cnn.b3 = PF("cb3");
+  h->cnn.w1l = reinterpret_cast<const uint32_t*>(P("cw1l"));
+  h->cnn.w2l = reinterpret_cast<const uint32_t*>(P("cw2l"));
+  h->cnn.w3l = reinterpret_cast<const uint32_t*>(P("cw3l"));
   h->cnn_w2_slabs = static_cast<const uint8_t*>(P("tcw2"));
   h->cnn_w3_rows = static_cast<const uint8_t*>(P("tcw3"));
   h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();

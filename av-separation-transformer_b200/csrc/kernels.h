@@ -84,6 +84,7 @@ struct CnnWeights {                // BN-folded, fragment-ordered (see visual_cn
   const uint32_t* w1; const float* b1;
   const uint32_t* w2; const float* b2;
   const uint32_t* w3; const float* b3;
+  const uint32_t *w1l, *w2l, *w3l;   // lo parts (fp32-grade split path), fragment-ordered like w1/w2/w3
 };
 // frames (M,H,W) fp32 -> pooled (M,128) operand precision
 const char* launch_visual_cnn(cudaStream_t s, int prec, const float* frames, int M, int H, int W, const CnnWeights& w,
@@ -96,6 +97,7 @@ const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, con
                                  const uint8_t* w3_rows, void* pooled, int num_sms,
                                  unsigned long long* trace = nullptr);
 size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint32)
-void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3);
+void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3,
+                     bool lo_part = false);
 
 }  // namespace avsep

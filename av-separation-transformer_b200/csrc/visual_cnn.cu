@@ -13,6 +13,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 namespace avsep {
 
 namespace {
@@ -31,6 +33,7 @@ struct CnnDev {
   const uint32_t* w1; const float* b1;
   const uint32_t* w2; const float* b2;
   const uint32_t* w3; const float* b3;
+  const uint32_t *w1l, *w2l, *w3l;   // lo parts (w - bf16(w)) for the fp32-grade split path
   int M, H, W, H1, W1, H2, W2, H3, W3, G, num_groups;
 };
 
@@ -62,7 +65,11 @@ __device__ __forceinline__ RowRef make_rowref(int r, int rows_total, int Ho, int
   return rr;
 }
 
-template <bool TF32OUT>
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// SPLIT = fp32-grade path: activations and weights are carried as bf16 hi + lo pairs and every contraction is three
+// tensor-core products (hi*hi + lo*hi + hi*lo); the pooled output is fp32.
+template <bool SPLIT>
 __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev p) {
   extern __shared__ __align__(16) uint8_t smem_cnn[];
   const int Hp = p.H + 2, Wp = p.W + 2;
@@ -78,6 +85,11 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
   float* sIn = sPool + p.G * C3;                              // [G][Hp][Wp] fp32, zero border
   uint32_t* sA1 = reinterpret_cast<uint32_t*>(sIn + p.G * in_words);   // [G][H1][W1][18 words]
   uint32_t* sA2 = sA1 + p.G * a1_words;                        // [G][H2][W2][34 words]
+  // lo halves (SPLIT only)
+  uint32_t* sA1l = sA2 + p.G * a2_words;
+  uint32_t* sA2l = sA1l + p.G * a1_words;
+  uint32_t* sW2l = sA2l + p.G * a2_words;
+  uint32_t* sW1l = sW2l + W2_WORDS;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -85,6 +97,10 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
 
   for (int i = tid; i < W2_WORDS; i += CNN_THREADS) sW2[i] = p.w2[i];
   for (int i = tid; i < W1_WORDS; i += CNN_THREADS) sW1[i] = p.w1[i];
+  if constexpr (SPLIT) {
+    for (int i = tid; i < W2_WORDS; i += CNN_THREADS) sW2l[i] = p.w2l[i];
+    for (int i = tid; i < W1_WORDS; i += CNN_THREADS) sW1l[i] = p.w1l[i];
+  }
   for (int i = tid; i < C1; i += CNN_THREADS) sB1[i] = p.b1[i];
   for (int i = tid; i < C2; i += CNN_THREADS) sB2[i] = p.b2[i];
   for (int i = tid; i < C3; i += CNN_THREADS) sB3[i] = p.b3[i];
@@ -113,11 +129,13 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
 
     // ---- conv1: K = 9 taps padded to 16, N = 32 ----
     {
-      uint32_t bw[4][2];
+      uint32_t bw[4][2], bwl[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         bw[nt][0] = sW1[nt * 64 + lane * 2];
         bw[nt][1] = sW1[nt * 64 + lane * 2 + 1];
+        bwl[nt][0] = SPLIT ? sW1l[nt * 64 + lane * 2] : 0u;
+        bwl[nt][1] = SPLIT ? sW1l[nt * 64 + lane * 2 + 1] : 0u;
       }
       const int k0 = 2 * tig, k1 = 2 * tig + 1;           // taps handled by this lane (k < 8)
       const int off0 = (k0 / 3) * Wp + (k0 % 3);
@@ -125,7 +143,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
       const int off8 = 2 * Wp + 2;                         // tap 8
       const int tiles = (R1 + 15) / 16;
       for (int t = warp; t < tiles; t += CNN_THREADS / 32) {
-        uint32_t a[4] = {0, 0, 0, 0};
+        uint32_t a[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
         int pix[2];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -138,20 +156,36 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
             const int y = rem / p.W1, x = rem - y * p.W1;
             pix[hf] = r;
             const float* base = sIn + g * in_words + (2 * y) * Wp + 2 * x;
-            a[hf] = pack_bf16x2(base[off0], base[off1]);
-            if (tig == 0) a[2 + hf] = pack_bf16x2(base[off8], 0.f);
+            const float v0 = base[off0], v1 = base[off1];
+            a[hf] = pack_bf16x2(v0, v1);
+            if constexpr (SPLIT) al[hf] = pack_bf16x2(v0 - bf16_round(v0), v1 - bf16_round(v1));
+            if (tig == 0) {
+              const float v8 = base[off8];
+              a[2 + hf] = pack_bf16x2(v8, 0.f);
+              if constexpr (SPLIT) al[2 + hf] = pack_bf16x2(v8 - bf16_round(v8), 0.f);
+            }
           }
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           float c[4] = {0.f, 0.f, 0.f, 0.f};
           mma16816(c, a[0], a[1], a[2], a[3], bw[nt][0], bw[nt][1]);
+          if constexpr (SPLIT) {
+            mma16816(c, al[0], al[1], al[2], al[3], bw[nt][0], bw[nt][1]);
+            mma16816(c, a[0], a[1], a[2], a[3], bwl[nt][0], bwl[nt][1]);
+          }
           const int ch = nt * 8 + 2 * tig;
           const float bb0 = sB1[ch], bb1 = sB1[ch + 1];
-          if (pix[0] >= 0)
-            sA1[pix[0] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(fmaxf(c[0] + bb0, 0.f), fmaxf(c[1] + bb1, 0.f));
-          if (pix[1] >= 0)
-            sA1[pix[1] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(fmaxf(c[2] + bb0, 0.f), fmaxf(c[3] + bb1, 0.f));
+          const float o0 = fmaxf(c[0] + bb0, 0.f), o1 = fmaxf(c[1] + bb1, 0.f);
+          const float o2 = fmaxf(c[2] + bb0, 0.f), o3 = fmaxf(c[3] + bb1, 0.f);
+          if (pix[0] >= 0) {
+            sA1[pix[0] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o0, o1);
+            if constexpr (SPLIT) sA1l[pix[0] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o0 - bf16_round(o0), o1 - bf16_round(o1));
+          }
+          if (pix[1] >= 0) {
+            sA1[pix[1] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o2, o3);
+            if constexpr (SPLIT) sA1l[pix[1] * A1_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o2 - bf16_round(o2), o3 - bf16_round(o3));
+          }
         }
       }
     }
@@ -184,7 +218,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int ks = tap * 2 + half;
-            uint32_t af[2][4];
+            uint32_t af[2][4], afl[2][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               const int o0 = off[mt * 2], o1 = off[mt * 2 + 1];
@@ -192,12 +226,25 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
               af[mt][1] = o1 >= 0 ? sA1[o1 + half * 8] : 0u;
               af[mt][2] = o0 >= 0 ? sA1[o0 + half * 8 + 4] : 0u;
               af[mt][3] = o1 >= 0 ? sA1[o1 + half * 8 + 4] : 0u;
+              if constexpr (SPLIT) {
+                afl[mt][0] = o0 >= 0 ? sA1l[o0 + half * 8] : 0u;
+                afl[mt][1] = o1 >= 0 ? sA1l[o1 + half * 8] : 0u;
+                afl[mt][2] = o0 >= 0 ? sA1l[o0 + half * 8 + 4] : 0u;
+                afl[mt][3] = o1 >= 0 ? sA1l[o1 + half * 8 + 4] : 0u;
+              }
             }
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
               const uint2 bw = *reinterpret_cast<const uint2*>(sW2 + (ks * 8 + ng * 4 + n) * 64 + lane * 2);
               mma16816(acc[0][n], af[0][0], af[0][1], af[0][2], af[0][3], bw.x, bw.y);
               mma16816(acc[1][n], af[1][0], af[1][1], af[1][2], af[1][3], bw.x, bw.y);
+              if constexpr (SPLIT) {
+                const uint2 bl = *reinterpret_cast<const uint2*>(sW2l + (ks * 8 + ng * 4 + n) * 64 + lane * 2);
+                mma16816(acc[0][n], afl[0][0], afl[0][1], afl[0][2], afl[0][3], bw.x, bw.y);
+                mma16816(acc[1][n], afl[1][0], afl[1][1], afl[1][2], afl[1][3], bw.x, bw.y);
+                mma16816(acc[0][n], af[0][0], af[0][1], af[0][2], af[0][3], bl.x, bl.y);
+                mma16816(acc[1][n], af[1][0], af[1][1], af[1][2], af[1][3], bl.x, bl.y);
+              }
             }
           }
         }
@@ -208,12 +255,16 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
             const int ch = (ng * 4 + n) * 8 + 2 * tig;
             const float bb0 = sB2[ch], bb1 = sB2[ch + 1];
             const int r0 = mp * 32 + mt * 16 + gid, r1 = r0 + 8;
-            if (r0 < R2)
-              sA2[r0 * A2_PIX_WORDS + (ch >> 1)] =
-                  pack_bf16x2(fmaxf(acc[mt][n][0] + bb0, 0.f), fmaxf(acc[mt][n][1] + bb1, 0.f));
-            if (r1 < R2)
-              sA2[r1 * A2_PIX_WORDS + (ch >> 1)] =
-                  pack_bf16x2(fmaxf(acc[mt][n][2] + bb0, 0.f), fmaxf(acc[mt][n][3] + bb1, 0.f));
+            const float o0 = fmaxf(acc[mt][n][0] + bb0, 0.f), o1 = fmaxf(acc[mt][n][1] + bb1, 0.f);
+            const float o2 = fmaxf(acc[mt][n][2] + bb0, 0.f), o3 = fmaxf(acc[mt][n][3] + bb1, 0.f);
+            if (r0 < R2) {
+              sA2[r0 * A2_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o0, o1);
+              if constexpr (SPLIT) sA2l[r0 * A2_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o0 - bf16_round(o0), o1 - bf16_round(o1));
+            }
+            if (r1 < R2) {
+              sA2[r1 * A2_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o2, o3);
+              if constexpr (SPLIT) sA2l[r1 * A2_PIX_WORDS + (ch >> 1)] = pack_bf16x2(o2 - bf16_round(o2), o3 - bf16_round(o3));
+            }
           }
         }
       }
@@ -237,6 +288,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
 #pragma unroll
           for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
         const uint2* wbase = reinterpret_cast<const uint2*>(p.w3) + lane;
+        const uint2* wbase_l = reinterpret_cast<const uint2*>(SPLIT ? p.w3l : p.w3) + lane;
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
           int off[8];
@@ -264,6 +316,19 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
               const uint32_t a3 = o1 >= 0 ? sA2[o1 + q * 8 + 4] : 0u;
               mma16816(acc[mt][0], a0, a1, a2, a3, bw[q][0].x, bw[q][0].y);
               mma16816(acc[mt][1], a0, a1, a2, a3, bw[q][1].x, bw[q][1].y);
+              if constexpr (SPLIT) {
+                const uint32_t l0 = o0 >= 0 ? sA2l[o0 + q * 8] : 0u;
+                const uint32_t l1 = o1 >= 0 ? sA2l[o1 + q * 8] : 0u;
+                const uint32_t l2 = o0 >= 0 ? sA2l[o0 + q * 8 + 4] : 0u;
+                const uint32_t l3 = o1 >= 0 ? sA2l[o1 + q * 8 + 4] : 0u;
+                mma16816(acc[mt][0], l0, l1, l2, l3, bw[q][0].x, bw[q][0].y);
+                mma16816(acc[mt][1], l0, l1, l2, l3, bw[q][1].x, bw[q][1].y);
+                const int ksl = tap * 4 + q;
+                const uint2 wl0 = __ldg(wbase_l + (ksl * 16 + np * 2) * 32);
+                const uint2 wl1 = __ldg(wbase_l + (ksl * 16 + np * 2 + 1) * 32);
+                mma16816(acc[mt][0], a0, a1, a2, a3, wl0.x, wl0.y);
+                mma16816(acc[mt][1], a0, a1, a2, a3, wl1.x, wl1.y);
+              }
             }
           }
         }
@@ -314,7 +379,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
       const float val = sPool[i] * inv_pool;
       sPool[i] = 0.f;
       if (fr < p.M) {
-        if constexpr (TF32OUT) reinterpret_cast<float*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] = val;
+        if constexpr (SPLIT) reinterpret_cast<float*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] = val;
         else reinterpret_cast<__nv_bfloat16*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] =
             __float2bfloat16_rn(val);
       }
@@ -332,7 +397,19 @@ inline uint16_t f2bf(float f) {   // round-to-nearest-even, as __float2bfloat16_
 }
 
 // Pack a [N][K] fp32 matrix into mma.m16n8k16 B-fragment order: [k-step][n-tile][lane][2 words].
-void pack_frag(const float* w, int N, int K, int Kpad, uint32_t* out) {
+void pack_frag(const float* w_in, int N, int K, int Kpad, uint32_t* out, bool lo_part) {
+  std::vector<float> tmp;
+  const float* w = w_in;
+  if (lo_part) {      // residual after bf16 rounding
+    tmp.resize(static_cast<size_t>(N) * K);
+    for (size_t i = 0; i < tmp.size(); ++i) {
+      const uint32_t hb = static_cast<uint32_t>(f2bf(w_in[i])) << 16;
+      float hf;
+      memcpy(&hf, &hb, 4);
+      tmp[i] = w_in[i] - hf;
+    }
+    w = tmp.data();
+  }
   const int ksteps = Kpad / 16, ntiles = N / 8;
   for (int ks = 0; ks < ksteps; ++ks)
     for (int nt = 0; nt < ntiles; ++nt)
@@ -351,10 +428,11 @@ void pack_frag(const float* w, int N, int K, int Kpad, uint32_t* out) {
 size_t visual_cnn_pack_sizes(int which) { return which == 1 ? W1_WORDS : which == 2 ? W2_WORDS : W3_WORDS; }
 
 // w1 [32][9], w2 [64][9*32], w3 [128][9*64] fp32, already BN-folded, K index = tap*Cin + c.
-void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3) {
-  pack_frag(w1, C1, 9, 16, p1);
-  pack_frag(w2, C2, 9 * C1, 9 * C1, p2);
-  pack_frag(w3, C3, 9 * C2, 9 * C2, p3);
+void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3,
+                     bool lo_part) {
+  pack_frag(w1, C1, 9, 16, p1, lo_part);
+  pack_frag(w2, C2, 9 * C1, 9 * C1, p2, lo_part);
+  pack_frag(w3, C3, 9 * C2, 9 * C2, p3, lo_part);
 }
 
 const char* launch_visual_cnn(cudaStream_t s, int prec, const float* frames, int M, int H, int W, const CnnWeights& w,
@@ -363,13 +441,16 @@ const char* launch_visual_cnn(cudaStream_t s, int prec, const float* frames, int
   CnnDev d;
   d.frames = frames; d.pooled = pooled;
   d.w1 = w.w1; d.b1 = w.b1; d.w2 = w.w2; d.b2 = w.b2; d.w3 = w.w3; d.b3 = w.b3;
+  d.w1l = w.w1l; d.w2l = w.w2l; d.w3l = w.w3l;
+  const bool split = (prec == PREC_TF32);
+  const size_t mul = split ? 2 : 1;
   d.M = M; d.H = H; d.W = W;
   d.H1 = (H + 1) / 2; d.W1 = (W + 1) / 2;
   d.H2 = (d.H1 + 1) / 2; d.W2 = (d.W1 + 1) / 2;
   d.H3 = (d.H2 + 1) / 2; d.W3 = (d.W2 + 1) / 2;
-  const size_t fixed = (W2_WORDS + W1_WORDS + C1 + C2 + C3) * 4;
-  const size_t per_frame = static_cast<size_t>((H + 2) * (W + 2) + d.H1 * d.W1 * A1_PIX_WORDS +
-                                               d.H2 * d.W2 * A2_PIX_WORDS + C3) * 4;
+  const size_t fixed = (mul * (W2_WORDS + W1_WORDS) + C1 + C2 + C3) * 4;
+  const size_t per_frame = static_cast<size_t>((H + 2) * (W + 2) + mul * (d.H1 * d.W1 * A1_PIX_WORDS +
+                                               d.H2 * d.W2 * A2_PIX_WORDS) + C3) * 4;
   const size_t cap = 227 * 1024;
   if (fixed + per_frame > cap) return "visual_cnn: frame too large for the fused kernel (shared memory)";
   int G = static_cast<int>((cap - fixed) / per_frame);

@@ -48,6 +48,22 @@ def test_bf16_path_matches_reference_golden(name):
         assert v < 5e-2, (k, v)
 
 
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_tf32_path_matches_reference_golden(name):
+    """fp32/TF32 path (north star: 1e-3): GEMMs on tcgen05 kind::tf32 with fp32 operands in HBM, attention and the
+    CNN with bf16 hi/lo split contractions (fp32-grade), fp32 residual stream / LayerNorm / softmax."""
+    z, meta = load_golden(name)
+    cfg, P, mixed, frames = case_tensors(meta)
+    model = build_model(cfg, P, "tf32")
+    sep, masks = _run(model, mixed, frames)
+    sf, st = meta["stride_f"], meta["stride_t"]
+    rep = err_report(sep[:, :, ::sf, ::st], masks[:, :, ::sf, ::st], z["separated"], z["masks"], mixed[:, ::sf, ::st])
+    print("tf32", name, rep)
+    assert masks.min() >= 0.0 and masks.max() <= 1.0
+    assert rep["masks"] < TOL["tf32"], rep
+    assert rep["separated_scaled"] < TOL["tf32"], rep
+
+
 def test_against_live_oracle_other_seeds():
     cfg = CONFIGS["tiny2"]
     for seed in (21, 22):

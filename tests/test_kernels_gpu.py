@@ -56,6 +56,61 @@ def test_gemm_tcgen05(eng, M, N, K, act, bn):
     assert err < 2e-3, err
 
 
+@pytest.fixture(scope="module")
+def eng32():
+    from avsep_b200.engine import Engine, EngineConfig
+    e = Engine(EngineConfig(65, 64, 4, 1, 1, 2, "tf32"), 0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(128, 128, 32, 0), (1000, 768, 256, 0), (300, 192, 264, 1), (1000, 256, 1024, 2),
+                                       (77, 64, 64, 0)])
+def test_gemm_tcgen05_tf32(eng32, M, N, K, act):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _check(eng32, eng32.lib.avsep_test_gemm(eng32.h, A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                            M, N, K, act, 0, _s()))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + bias.double()
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 4e-3, err          # tf32 operands (10-bit mantissa), fp32 accumulation
+
+
+def test_attention_split_fp32_grade(eng32):
+    B, H, hd, T, N = 2, 4, 64, 63, 50
+    g = torch.Generator(device="cuda").manual_seed(5)
+    d = H * hd
+    q = torch.randn(B, T, d, device="cuda", generator=g)
+    k = torch.randn(B, N, d, device="cuda", generator=g)
+    v = torch.randn(B, N, d, device="cuda", generator=g)
+    out = torch.zeros(B, T, d, device="cuda")
+    _check(eng32, eng32.lib.avsep_test_attention(eng32.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                 B, H, hd, T, T, N, _s()))
+    torch.cuda.synchronize()
+    up = lambda t: torch.nn.functional.interpolate(t.permute(0, 2, 1), size=T, mode="linear",
+                                                   align_corners=False).permute(0, 2, 1)
+    qh = q.view(B, T, H, hd).transpose(1, 2)
+    kh = up(k).view(B, T, H, hd).transpose(1, 2)
+    vh = up(v).view(B, T, H, hd).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(hd), -1) @ vh).transpose(1, 2).reshape(B, T, d)
+    assert (out - ref).abs().max().item() < 2e-4
+    # self-attention (no interpolation), fp32 in / fp32 out
+    out2 = torch.zeros(B, T, d, device="cuda")
+    _check(eng32, eng32.lib.avsep_test_attention(eng32.h, q.data_ptr(), q.data_ptr(), q.data_ptr(), out2.data_ptr(),
+                                                 B, H, hd, T, T, 0, _s()))
+    torch.cuda.synchronize()
+    ref2 = (torch.softmax(qh @ qh.transpose(-1, -2) / math.sqrt(hd), -1) @ qh).transpose(1, 2).reshape(B, T, d)
+    assert (out2 - ref2).abs().max().item() < 2e-4
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (16128, 256, 1024), (77, 64, 64), (300, 128, 512), (130, 32, 64)])
 def test_gemm_fused_residual_layernorm(eng, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
