@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
 #pragma unroll
     for (int nt = 0; nt < NT_O; ++nt) {
       if (r0 < p.Lq)
-        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r0) * p.ldo + nt * 8) = make_float2(o[nt][0] * inv0, o[nt][1] * inv0);
+        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r0) * p.ldo + nt * 8) = make_float2(round_tf32(o[nt][0] * inv0), round_tf32(o[nt][1] * inv0));
       if (r1 < p.Lq)
-        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r1) * p.ldo + nt * 8) = make_float2(o[nt][2] * inv1, o[nt][3] * inv1);
+        *reinterpret_cast<float2*>(ob + static_cast<size_t>(r1) * p.ldo + nt * 8) = make_float2(round_tf32(o[nt][2] * inv1), round_tf32(o[nt][3] * inv1));
     }
     return;
   }

@@ -548,7 +548,16 @@ struct ArenaBuilder {
   }
   size_t add_f32(const float* src, size_t n) { return add(src, n * 4); }
   size_t add_op(const float* src, size_t n, bool tf32) {
-    if (tf32) return add(src, n * 4);
+    if (tf32) {   // round to tf32 (10-bit mantissa, nearest, ties away) so the tensor core's truncation is exact
+      std::vector<float> tmp(n);
+      for (size_t i = 0; i < n; ++i) {
+        uint32_t u;
+        memcpy(&u, &src[i], 4);
+        if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+        memcpy(&tmp[i], &u, 4);
+      }
+      return add(tmp.data(), n * 4);
+    }
     std::vector<uint16_t> tmp(n);
     for (size_t i = 0; i < n; ++i) tmp[i] = f2bf_host(src[i]);
     return add(tmp.data(), n * 2);

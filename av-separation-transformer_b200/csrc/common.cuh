@@ -47,6 +47,14 @@ __device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() defau
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// fp32 -> TF32 with round-to-nearest (the tensor core would otherwise truncate the low 13 mantissa bits, which
+// doubles the operand error and biases it towards zero).  Result is an fp32 bit pattern with a 10-bit mantissa.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -77,6 +77,7 @@ add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ y, c
         o.w = (o.w - mean) * rstd * g.w + b.w;
       }
       if constexpr (TF32) {
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
         reinterpret_cast<float4*>(reinterpret_cast<float*>(out_op) + static_cast<size_t>(row) * d)[c] = o;
       } else {
         uint2 u;
@@ -115,7 +116,7 @@ prep_audio_kernel(const float* __restrict__ mixed, void* __restrict__ xp, int F,
     if (t < T && f < Fp) {
       const float val = tile[tx][ty + 8 * i];
       const size_t o = base + static_cast<size_t>(t + 1) * Fp + f;
-      if constexpr (TF32) reinterpret_cast<float*>(xp)[o] = val;
+      if constexpr (TF32) reinterpret_cast<float*>(xp)[o] = round_tf32(val);
       else reinterpret_cast<__nv_bfloat16*>(xp)[o] = __float2bfloat16_rn(val);
     }
   }

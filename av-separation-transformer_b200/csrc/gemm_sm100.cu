@@ -85,12 +85,15 @@ template <bool TF32>
 __device__ __forceinline__ void store_op_chunk(void* out_op, size_t off, const float (&val)[32], int ncols, bool vec) {
   if constexpr (TF32) {
     float* o = reinterpret_cast<float*>(out_op) + off;
+    float rv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rv[j] = round_tf32(val[j]);
     if (vec) {
-      store_f32_chunk(o, val);
+      store_f32_chunk(o, rv);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ncols) o[j] = val[j];
+        if (j < ncols) o[j] = rv[j];
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_op) + off;
@@ -154,6 +157,12 @@ __device__ __forceinline__ void stg_write_own_f32(uint8_t* buf, int lane, const 
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<float4*>(buf + stg_off(lane, c)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+}
+__device__ __forceinline__ void stg_write_own_tf32(uint8_t* buf, int lane, const float (&x)[32]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(buf + stg_off(lane, c)) =
+        make_float4(round_tf32(x[4 * c]), round_tf32(x[4 * c + 1]), round_tf32(x[4 * c + 2]), round_tf32(x[4 * c + 3]));
 }
 // own row: 32 values as bf16 into chunk slots [slot0, slot0+4) (two calls fill one 128-byte row of 64 bf16)
 __device__ __forceinline__ void stg_write_own_bf16(uint8_t* buf, int lane, int slot0, const float (&x)[32]) {
@@ -518,7 +527,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (TF32) {
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
-              stg_write_own_f32(slab_q, lane, val[ci]);
+              stg_write_own_tf32(slab_q, lane, val[ci]);
               fence_proxy_async_smem();
               named_bar_sync(part_bar, 128);
               if (elected) {
@@ -639,7 +648,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
               if (ci < ch_count) {
-                stg_write_own_f32(stg, lane, val[ci]);
+                stg_write_own_tf32(stg, lane, val[ci]);
                 __syncwarp();
                 stg_store_rows(stg, op_row ? op_row + (ch_first + ci) * 128 : 0ull, lane);
                 __syncwarp();
@@ -685,16 +694,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tmem_ld_wait();
               float a[32];
               value_chunk<false>(e, ri, v, a, sb + c0, n0 + c0, 32, p.N);
-              const bool f32_slab = (e.out_f32 != nullptr) || TF32;
-              if (f32_slab) {                                  // one 32-column fp32 slab per chunk
+              if (e.out_f32 != nullptr) {                      // exact fp32 output: one 32-column slab per chunk
                 if (elected) bulk_wait_read0();
                 named_bar_sync(part_bar, 128);
                 stg_write_own_f32(slab_q, lane, a);
                 fence_proxy_async_smem();
                 named_bar_sync(part_bar, 128);
                 if (elected) {
-                  if (e.out_f32 != nullptr) tma_store_2d(&tmF32, slab, n0 + c0, m0);
-                  if (TF32 && e.out_op != nullptr) tma_store_2d(&tmOp, slab, n0 + c0, m0);
+                  tma_store_2d(&tmF32, slab, n0 + c0, m0);
+                  bulk_commit();
+                }
+              }
+              if (TF32 && e.out_op != nullptr) {               // tf32 operand output (rounded to nearest)
+                if (elected) bulk_wait_read0();
+                named_bar_sync(part_bar, 128);
+                stg_write_own_tf32(slab_q, lane, a);
+                fence_proxy_async_smem();
+                named_bar_sync(part_bar, 128);
+                if (elected) {
+                  tma_store_2d(&tmOp, slab, n0 + c0, m0);
                   bulk_commit();
                 }
               }
@@ -741,7 +759,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
               if (e.out_op != nullptr) {
                 if constexpr (TF32) {
-                  stg_write_own_f32(stg, lane, a);
+                  stg_write_own_tf32(stg, lane, a);
                   __syncwarp();
                   stg_store_rows(stg, op_row ? op_row + c0 * 4 : 0ull, lane);
                   __syncwarp();

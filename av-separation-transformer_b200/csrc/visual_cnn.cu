@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(CNN_THREADS, 1) visual_cnn_kernel(const CnnDev
       const float val = sPool[i] * inv_pool;
       sPool[i] = 0.f;
       if (fr < p.M) {
-        if constexpr (SPLIT) reinterpret_cast<float*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] = val;
+        if constexpr (SPLIT) reinterpret_cast<float*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] = round_tf32(val);
         else reinterpret_cast<__nv_bfloat16*>(p.pooled)[static_cast<size_t>(fr) * C3 + (i - g * C3)] =
             __float2bfloat16_rn(val);
       }
