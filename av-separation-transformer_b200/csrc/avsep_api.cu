@@ -107,6 +107,9 @@ struct avsep_handle {
   bool finalized = false;
   bool fuse_ln = true;   // residual+LayerNorm in the GEMM epilogue when the row fits one tile
   bool use_graph = true; // replay the forward as a CUDA graph (captured per shape + buffer set on its 2nd use)
+  bool two_stream = true; // audio and visual branches on two streams (fork/join), so partial waves overlap
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<GraphEntry> graphs;
   uint64_t graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
@@ -459,17 +462,35 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   const int Ma = w.B * w.T, Mv = w.B * w.N;
   h->prof_stream = s;
   if (h->profile && h->profile_spin_us > 0) spin_kernel<<<1, 1, 0, s>>>(1000ull * h->profile_spin_us);
+  // The audio and visual branches are independent until the fusion: run them on two streams (fork / join) unless
+  // per-kernel profiling or stage snapshots need a single ordered stream.
+  cudaStream_t sv = s;
+  const bool fork = h->two_stream && !h->profile && !h->debug;
+  if (fork) {
+    if (h->aux_stream == nullptr) {
+      CUDA_OK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    sv = h->aux_stream;
+    CUDA_OK(cudaEventRecord(h->ev_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(sv, h->ev_fork, 0));
+  }
+  // --- visual branch (enqueued first: its CNN is the longest kernel) ---
+  if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b)) return 1;
+  if (encoder_stack(h, sv, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
+    return 1;
+  if (snapshot(h, sv, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
   // --- audio branch ---
   if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b)) return 1;
   if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
                     h->fus[0].n1b))
     return 1;
   if (snapshot(h, s, "audio_enc", w.x_a, static_cast<size_t>(Ma) * d, false)) return 1;
-  // --- visual branch ---
-  if (visual_frontend(h, s, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b)) return 1;
-  if (encoder_stack(h, s, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
-    return 1;
-  if (snapshot(h, s, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
+  if (fork) {
+    CUDA_OK(cudaEventRecord(h->ev_join, sv));
+    CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+  }
   // --- fusion + decoder ---
   if (fusion_stack(h, s, w, w.N)) return 1;
   return decoder_stage(h, s, w, mixed, separated, masks);
@@ -618,6 +639,9 @@ void avsep_destroy(avsep_handle* h) {
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (int i = 0; i < 3; ++i)
     if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
   delete h;
@@ -1139,6 +1163,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "epilogue_tma") == 0) { gemm_set_epilogue_tma(value != 0); drop_graphs(h); return 0; }
   if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }
   return fail(h, std::string("unknown option ") + name);
