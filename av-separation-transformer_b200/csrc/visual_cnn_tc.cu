@@ -35,8 +35,7 @@ constexpr int OFF_ACT2 = OFF_W2 + W2_SLABS * W2_SLAB_BYTES;   // 8 frames x 64 p
 constexpr int OFF_ACT1 = OFF_ACT2 + GROUP * 64 * 128;     // 2 frames x 256 px x 64 B
 constexpr int OFF_IN = OFF_ACT1 + 2 * 256 * 64;           // 2 frames x 34 x 34 fp32
 constexpr int OFF_MISC = OFF_IN + 2 * 34 * 34 * 4;        // barriers, TMEM slot
-constexpr int NSLOT = 7;                                  // physical im2col slab slots (see kernel)
-constexpr int TC_SMEM = OFF_MISC + 256 + 1024;            // barriers + alignment slack (<= 227 KB)
+constexpr int TC_SMEM = OFF_MISC + 128 + 1024;            // + alignment slack (<= 227 KB)
 static_assert(TC_SMEM <= 227 * 1024, "visual_cnn_tc: shared memory budget exceeded");
 
 struct CnnTcDev {
@@ -75,24 +74,6 @@ __device__ __forceinline__ int act2_chunk_off(int pixel, int c) {   // pixel = g
   return pixel * 128 + ((c ^ (pixel & 7)) * 16);
 }
 
-// Slot schedule shared by the builders and the MMA issuer.
-//   conv2 of pair p, slab j : slots {0, 1, p+2 .. 4}  (2 + 3 - p of them), round robin
-//   conv3, tap t            : slots {0, 1, 5, 6}, round robin
-__device__ __forceinline__ int conv2_slot(int pair, int j) {
-  const int n = 5 - pair;                 // 5, 4, 3, 2 slots
-  const int k = j % n;
-  return k < 2 ? k : k + pair;            // k >= 2 -> act2 region of pair (k - 1 + pair) -> slot id k + pair
-}
-__device__ __forceinline__ int conv3_slot(int t) {
-  const int k = t & 3;
-  return k < 2 ? k : k + 3;               // 5, 6 = act1 halves
-}
-__device__ __forceinline__ uint32_t slot_offset(int slot) {
-  if (slot < 2) return OFF_RING + slot * SLAB_BYTES;
-  if (slot < 5) return OFF_ACT2 + (slot - 1) * SLAB_BYTES;      // act2 region of pair slot-1 (pairs 1..3)
-  return OFF_ACT1 + (slot - 5) * SLAB_BYTES;
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1)
 visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p) {
   // Dynamic shared memory is declared 1024-byte aligned (128B-swizzle atoms) and used directly: deriving the base
@@ -100,16 +81,15 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   extern __shared__ __align__(1024) uint8_t smem_raw_cnn[];
   uint8_t* const smem = smem_raw_cnn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* ring = smem + OFF_RING;
   uint8_t* w3s = smem + OFF_W3;
   uint8_t* w2s = smem + OFF_W2;
   uint8_t* act2 = smem + OFF_ACT2;
   uint8_t* act1 = smem + OFF_ACT1;
   float* sIn = reinterpret_cast<float*>(smem + OFF_IN);
-  // im2col slab slots: 0,1 = the ring; 2,3,4 = act2 regions of pairs 1,2,3 (free until that pair's conv2 epilogue);
-  // 5,6 = the two halves of act1 (dead during conv3).  Each has a full / free mbarrier pair.
-  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [7] slab written by all 8 builder warps
-  uint64_t* ring_free = ring_full + NSLOT;                         // [7] MMAs that read the slab have completed
-  uint64_t* bar_acc = ring_free + NSLOT;                           // accumulator complete
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [2] slab written by all 8 builder warps
+  uint64_t* ring_free = ring_full + 2;                             // [2] MMAs that read the slab have completed
+  uint64_t* bar_acc = ring_free + 2;                               // accumulator complete
   uint64_t* bar_w3 = bar_acc + 1;                                  // [3] W3 slab landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w3 + 3);
 
@@ -120,7 +100,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   for (int i = tid; i < 2 * 34 * 34; i += TC_THREADS) sIn[i] = 0.f;
   if (tid == 0) {
     tma_prefetch_desc(&tmW3);
-    for (int i = 0; i < NSLOT; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&ring_full[i], TC_BUILDERS / 32);
       mbar_init(&ring_free[i], 1);
     }
@@ -142,16 +122,14 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     if (lane == 0) {
       const uint32_t idesc2 = umma_idesc(1u, 128, 64);
       const uint32_t idesc3 = umma_idesc(1u, 128, 128);
-      uint32_t n_w3 = 0;
-      uint32_t full_par = 0;      // bit s = parity of the next completion of ring_full[s] this thread waits for
+      uint32_t n_slab = 0, n_w3 = 0;
       for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
         for (int pair = 0; pair < GROUP / 2; ++pair) {
-          for (int j = 0; j < W2_SLABS; ++j) {
-            const int slot = conv2_slot(pair, j);
-            mbar_wait(&ring_full[slot], (full_par >> slot) & 1);
-            full_par ^= 1u << slot;
+          for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+            const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+            mbar_wait(&ring_full[slot], use & 1);
             tc_fence_after();
-            const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + slot_offset(slot)), 1024);
+            const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
             const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w2s + j * W2_SLAB_BYTES), 1024);
             const int ksteps = (j == W2_SLABS - 1) ? 2 : 4;     // the last slab holds tap 8 only
             for (int k = 0; k < ksteps; ++k)
@@ -160,14 +138,13 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
             if (j == W2_SLABS - 1) umma_commit(bar_acc);
           }
         }
-        for (int t = 0; t < 9; ++t, ++n_w3) {
-          const int slot = conv3_slot(t);
-          mbar_wait(&ring_full[slot], (full_par >> slot) & 1);
-          full_par ^= 1u << slot;
+        for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
+          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          mbar_wait(&ring_full[slot], use & 1);
           const uint32_t ws = n_w3 % 3;
           mbar_wait(&bar_w3[ws], (n_w3 / 3) & 1);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + slot_offset(slot)), 1024);
+          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
           const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, adesc + 2 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
@@ -179,8 +156,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   } else {
     // =========================== builders / epilogue (8 warps) ===========================
     const int gid = lane >> 2, tig = lane & 3;
-    uint32_t free_par = 0;    // bit s = parity of the next completion of ring_free[s] to wait for
-    uint32_t used = 0;        // bit s = slot s has been filled at least once (its free barrier has a pending phase)
+    uint32_t n_slab = 0;      // slabs pushed through the ring so far
     uint32_t acc_phase = 0;
     uint32_t n_w3 = 0;        // W3 slabs requested so far (this thread mirrors the issuer's count)
 
@@ -246,15 +222,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       }
     };
     // hand a finished slab to the MMA issuer
-    // wait until the MMAs that read the previous contents of `slot` have completed, then claim it
-    auto acquire_slab = [&](int slot) {
-      if ((used >> slot) & 1) {
-        mbar_wait(&ring_free[slot], (free_par >> slot) & 1);
-        free_par ^= 1u << slot;
-      }
-      used |= 1u << slot;
-    };
-    auto publish_slab = [&](int slot) {
+    auto publish_slab = [&](uint32_t slot) {
       fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
       tc_fence_before();            // earlier tcgen05.ld of this thread are ordered before the MMAs this unblocks
       __syncwarp();
@@ -349,10 +317,10 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         CTRACE(3 + pair * 5);          // deferred conv2 epilogue done
 
         // ---- conv2: 5 slabs of two taps, gathered from act1 ----
-        for (int j = 0; j < W2_SLABS; ++j) {
-          const int slot = conv2_slot(pair, j);
-          acquire_slab(slot);
-          uint8_t* dst = smem + slot_offset(slot) + dst0;
+        for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
+          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
+          uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
           const int tap = 2 * j + taphalf;
           const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;                 // tap / 3, tap % 3 for tap < 16
           const bool okx = (tap < 9) && (kx == 0 ? vx2[0] : (kx == 1 ? vx2[1] : vx2[2]));
@@ -371,20 +339,16 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       CTRACE(21);                      // last conv2 epilogue done
 
       // ---- conv3: one slab per tap gathered from act2; weights streamed by TMA ----
-      for (int t = 0; t < 9; ++t, ++n_w3) {
-        const int slot = conv3_slot(t);
-        acquire_slab(slot);
-        // W3 slot of tap t-2 must be free before it is refilled with tap t+1's slab: wait for the MMAs of tap t-2
-        // (their completion is what ring_free of that tap's slab slot signals; with 4 slab slots it has not been
-        // waited for yet, so peek at it here without consuming the phase)
+      for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
+        const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+        if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
+        // the MMAs of tap t-2 have completed -> its W3 slot is free: refill it with tap t+1's slab (t+1 >= 3)
         if (tid == 0 && t >= 2 && t + 1 < 9) {
-          const int prev = conv3_slot(t - 2);
-          mbar_wait(&ring_free[prev], (free_par >> prev) & 1);
           const uint32_t ws = (n_w3 + 1) % 3;
           mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
           tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, (t + 1) * 128);
         }
-        uint8_t* dst = smem + slot_offset(slot) + dst0;
+        uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
         const int ky = (t * 11) >> 5, kx = t - 3 * ky;
         const bool okx = (kx == 0 ? vx3[0] : (kx == 1 ? vx3[1] : vx3[2])) && !(ky == 0 && top3);
         const int srcx = ky * 1024 + (kx == 0 ? xo3[0] : (kx == 1 ? xo3[1] : xo3[2]));
