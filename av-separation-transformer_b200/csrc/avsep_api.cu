@@ -107,6 +107,7 @@ struct avsep_handle {
   bool finalized = false;
   bool fuse_ln = true;   // residual+LayerNorm in the GEMM epilogue when the row fits one tile
   bool use_graph = true; // replay the forward as a CUDA graph (captured per shape + buffer set on its 2nd use)
+  bool fuse_ffn = true;   // linear1 -> act -> linear2 -> +residual -> LayerNorm in one kernel (d_model = 256, bf16)
   bool two_stream = true; // audio and visual branches on two streams (fork/join), so partial waves overlap
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -355,11 +356,15 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = L; ap.Lk = L; ap.lerp_src = 0;
     CKL("attn.self", launch_attention(s, prec, ap));
     if (linear_resid_ln(h, s, "gemm.out_proj", attn, M, d, w.wo, w.bo, d, x, w.n2g, w.n2b, a_op, y)) return 1;
-    if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
     const bool last = (l + 1 == layers.size());
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
-    if (linear_resid_ln(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, x, g, b, a_op, y)) return 1;
+    if (h->fuse_ffn && ffn_fusable(prec, d)) {
+      CKL("ffn.fused", launch_ffn_fused(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x, g, b, a_op, M, h->num_sms));
+    } else {
+      if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
+      if (linear_resid_ln(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, x, g, b, a_op, y)) return 1;
+    }
   }
   return 0;
 }
@@ -430,11 +435,16 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     CKL("attn.cross", launch_attention(s, prec, ap));
     if (linear_resid_ln(h, s, "gemm.out_proj", w.attn_a, Ma, d, fw.wo, fw.bo, d, w.x_a, fw.n2g, fw.n2b, w.a_op, w.y_a))
       return 1;
-    if (linear(h, s, "gemm.ffn1", w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
     const bool last = (l + 1 == Lf);
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
-    if (linear_resid_ln(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, w.x_a, g, b, w.a_op, w.y_a)) return 1;
+    if (h->fuse_ffn && ffn_fusable(prec, d)) {
+      CKL("ffn.fused", launch_ffn_fused(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU, w.x_a, w.x_a, g, b, w.a_op, Ma,
+                                        h->num_sms));
+    } else {
+      if (linear(h, s, "gemm.ffn1", w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
+      if (linear_resid_ln(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, w.x_a, g, b, w.a_op, w.y_a)) return 1;
+    }
   }
   return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
 }
@@ -1157,12 +1167,23 @@ int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const f
   return 0;
 }
 
+// Fused FFN sub-layer (d_model = 256, bf16): x (fp32, in place) += W2 act(W1 a + b1) + b2; out_op = LN(x) (bf16).
+int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const float* b1, const void* w2,
+                         const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
+                         void* out_op, int32_t M, void* cuda_stream) {
+  if (!h) return 1;
+  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act, x_inout, x_inout, gamma, beta,
+                      out_op, M, h->num_sms));
+  return 0;
+}
+
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
+  if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "epilogue_tma") == 0) { gemm_set_epilogue_tma(value != 0); drop_graphs(h); return 0; }
   if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }

@@ -62,6 +62,12 @@ const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const Ge
 bool gemm_ln_fusable(int N);   // EPI_LN usable for this row width
 void gemm_set_epilogue_tma(bool on);   // A/B switch: epilogue I/O through TMA slabs (default on)
 
+// Fused FFN sub-layer (d_model = 256, bf16): x += W2 act(W1 a + b1) + b2 ; out_op = LayerNorm(x)  (ffn_fused_sm100.cu)
+bool ffn_fusable(int prec, int d_model);
+const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, const float* b1, const void* w2,
+                             const float* b2, int act, const float* resid, float* x_out, const float* gamma,
+                             const float* beta, void* out_op, int M, int num_sms);
+
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).
 const char* launch_add_layernorm(cudaStream_t s, int prec, const float* x, const float* y, const float* gamma,

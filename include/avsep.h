@@ -112,6 +112,7 @@ AVSEP_API int avsep_profile_report(avsep_handle* h, char* buf, size_t capacity, 
 /* Kernel-level test hooks (DEVICE pointers; used by tests/ to check each kernel against a torch fp32 reference).
  *   gemm: out[M,N] = act(A[M,K] @ W[N,K]^T + bias), A/W in operand precision (bf16 or fp32), out fp32.
  *   gemm_ln: x += A W^T + bias (fp32, in place); out_op = LayerNorm(x) -- the fused sub-layer epilogue.
+ *   ffn_fused: x += W2 act(W1 a + b1) + b2 (fp32, in place); out_op = LayerNorm(x); d_model = 256, bf16 only.
  *   conv1d: taps=3 implicit GEMM over a zero-haloed activation: A [B*(L+2), K], W [N, 3*K] (k = tap*K + c),
  *           out fp32 [B*L, N] (ROW_PAD2COMPACT).
  *   attention: q [B*Lq, H*hd], k/v [B*Lk, H*hd] bf16 (lerp_src = 0) or fp32 [B*lerp_src, H*hd] (lerp on load).
@@ -125,6 +126,9 @@ AVSEP_API int avsep_test_gemm_ln(avsep_handle* h, const void* A, const void* W, 
 AVSEP_API int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const float* bias, float* x_or_out,
                                     const float* gamma, const float* beta, void* out_op, int32_t M, int32_t N, int32_t K,
                                     int32_t ln, int32_t act, unsigned long long* trace_dev, void* cuda_stream);
+AVSEP_API int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const float* b1, const void* w2,
+                                   const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
+                                   void* out_op, int32_t M, void* cuda_stream);
 AVSEP_API int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
                       int32_t L, int32_t N, int32_t K, void* cuda_stream);
 AVSEP_API int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,

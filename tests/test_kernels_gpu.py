@@ -56,6 +56,33 @@ def test_gemm_tcgen05(eng, M, N, K, act, bn):
     assert err < 2e-3, err
 
 
+@pytest.mark.parametrize("M,act", [(128, 1), (1000, 1), (16128, 1), (12800, 2), (77, 2), (148 * 128 + 300, 1)])
+def test_ffn_fused(eng, M, act):
+    """linear1 -> ReLU / GELU -> linear2 -> +residual -> LayerNorm in one kernel (hidden stays on chip)."""
+    g = torch.Generator(device="cuda").manual_seed(M + act)
+    d, hid = 256, 1024
+    a = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(hid, d, device="cuda", generator=g) / math.sqrt(d)).bfloat16()
+    b1 = torch.randn(hid, device="cuda", generator=g) * 0.5
+    w2 = (torch.randn(d, hid, device="cuda", generator=g) / math.sqrt(hid)).bfloat16()
+    b2 = torch.randn(d, device="cuda", generator=g)
+    x = torch.randn(M, d, device="cuda", generator=g) * 2 + 0.3
+    gamma = torch.randn(d, device="cuda", generator=g)
+    beta = torch.randn(d, device="cuda", generator=g)
+    hdn = a.float() @ w1.float().t() + b1
+    hdn = torch.relu(hdn) if act == 1 else torch.nn.functional.gelu(hdn)
+    x_ref = x + hdn.bfloat16().float() @ w2.float().t() + b2        # the hidden is rounded to bf16 between the GEMMs
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (d,), gamma, beta, 1e-5)
+    out = torch.zeros(M, d, device="cuda", dtype=torch.bfloat16)
+    _check(eng, eng.lib.avsep_test_ffn_fused(eng.h, a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                             act, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), M, _s()))
+    torch.cuda.synchronize()
+    assert (x - x_ref).abs().max().item() < 2e-2          # bf16 rounding of the hidden at a different point of the tie
+    assert (x - x_ref).abs().mean().item() < 2e-4
+    assert (out.float() - ln_ref).abs().max().item() < 6e-2
+    assert (out.float() - ln_ref).abs().mean().item() < 5e-3
+
+
 @pytest.fixture(scope="module")
 def eng32():
     from avsep_b200.engine import Engine, EngineConfig
