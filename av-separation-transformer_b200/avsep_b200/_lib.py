@@ -50,6 +50,7 @@ SIGNATURES = {
     "avsep_set_option": (C.c_int, [_P, C.c_char_p, _I]),
     "avsep_test_gemm_trace": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "avsep_test_ffn_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "avsep_test_ffn_fused_trace": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P]),
     "avsep_test_conv1d": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "avsep_test_attention": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "avsep_test_add_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),

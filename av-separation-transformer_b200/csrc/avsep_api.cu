@@ -1177,6 +1177,17 @@ int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const f
   return 0;
 }
 
+// Debug: the same with a phase trace ([grid][64] globaltimer stamps of each CTA's first tile: [0] entry, [1] A landed,
+// [2] acc2 complete, [3] epilogue-2 done, per chunk j at 8+4j: GEMM1 issued, GEMM2 issued, acc1 ready, H published).
+int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, const float* b1, const void* w2,
+                               const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
+                               void* out_op, int32_t M, unsigned long long* trace_dev, void* cuda_stream) {
+  if (!h) return 1;
+  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act, x_inout, x_inout, gamma, beta,
+                      out_op, M, h->num_sms, trace_dev));
+  return 0;
+}
+
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }

@@ -7,10 +7,10 @@
 // The 4d hidden activation never leaves the SM.
 //
 // One CTA per 128-row tile (persistent over tiles), 576 threads:
-//   warp 0 / lane 0 : TMA producer - A tile (4 k-slabs, loaded once per tile) and a 5-slot ring of 16 KB weight slabs
+//   warp 0 / lane 0 : TMA producer - A tile (4 k-slabs, loaded once per tile) and a 7-slot ring of 16 KB weight slabs
 //   warp 1 / lane 0 : MMA issuer   - per hidden chunk j (128 columns):
 //                        GEMM1_j : acc1[j&1] (TMEM, 128 cols)  = A (K=256) x W1[j]            (4 k-slabs, N=128)
-//                        GEMM2_j : acc2 (TMEM, 256 cols)      += H[j&1] (K=128) x W2[:, j]    (2 k-slabs x 2 halves)
+//                        GEMM2_j : acc2 (TMEM, 256 cols)      += H (K=128) x W2[:, j]         (2 k-slabs x 2 halves)
 //                     software-pipelined (G1_0, G1_1, G2_0, G1_2, G2_1, ...) so the tensor pipe stays busy while
 //                     the epilogue warps convert chunk j
 //   warps 2..17     : epilogue-1  - tcgen05.ld acc1 -> +b1 -> ReLU / erf-GELU -> bf16 -> swizzled K-major smem (H),
@@ -26,10 +26,10 @@ namespace {
 
 constexpr int D = 256, HID = 1024, CHUNK = 128, NCHUNK = HID / CHUNK;
 constexpr int SLAB = 128 * 128;                       // 128 rows x 128 B
-constexpr int WSLOTS = 5;
+constexpr int WSLOTS = 7;
 constexpr int OFF_A = 0;                              // 4 slabs  (A tile, K = 256)
-constexpr int OFF_H = OFF_A + 4 * SLAB;               // 2 x 2 slabs (hidden chunk, double-buffered); epilogue-2 staging
-constexpr int OFF_W = OFF_H + 4 * SLAB;               // 5 slabs (weight ring)
+constexpr int OFF_H = OFF_A + 4 * SLAB;               // 2 slabs (hidden chunk, one per 64-column k-slab, each with its own barriers)
+constexpr int OFF_W = OFF_H + 2 * SLAB;               // 7 slabs (weight ring)
 constexpr int OFF_BAR = OFF_W + WSLOTS * SLAB;        // barriers
 constexpr int OFF_RED = OFF_BAR + 256;                // LN partial statistics [128 rows][4 parts] float2
 constexpr int OFF_VEC = OFF_RED + 128 * 4 * 8;        // b1 [1024], b2 [256], gamma [256], beta [256]
@@ -42,7 +42,15 @@ struct FfnDev {
   const float* resid;     // == x_out (in place) or null
   int M, act;
   int has_xout, has_op;
+  unsigned long long* trace;   // optional [grid][64] globaltimer stamps of the CTA's first tile (debug), else null
 };
+
+__device__ __forceinline__ unsigned long long ffn_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+#define FTRACE(slot) do { if (p.trace != nullptr && lt == 0) p.trace[blockIdx.x * 64 + (slot)] = ffn_gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t soff(int row, int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); }
 
@@ -55,13 +63,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* a_full = bars;                 // A tile landed
-  uint64_t* a_empty = bars + 1;            // all GEMM1 of the tile issued and completed (A reusable)
+  uint64_t* a_empty = bars + 1;            // epilogue-2 (which stages in the A region) of the tile is done
   uint64_t* w_full = bars + 2;             // [5]
   uint64_t* w_empty = w_full + WSLOTS;     // [5]
   uint64_t* acc1_full = w_empty + WSLOTS;  // [2]
   uint64_t* acc1_empty = acc1_full + 2;    // [2] (16 warp arrivals)
-  uint64_t* h_full = acc1_empty + 2;       // [2] (16 warp arrivals)
-  uint64_t* h_empty = h_full + 2;          // [2]
+  uint64_t* h_full = acc1_empty + 2;       // [2] one per H k-slab (8 warp arrivals: the two column parts that write it)
+  uint64_t* h_empty = h_full + 2;          // [2] GEMM2 MMAs that read the k-slab have completed
   uint64_t* acc2_full = h_empty + 2;       // 1
   uint64_t* acc2_empty = acc2_full + 1;    // 1 (16 warp arrivals)
   uint64_t* resid_bar = acc2_empty + 1;    // [4]
@@ -74,6 +82,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + 127) / 128;
+  if (threadIdx.x == 0 && p.trace != nullptr) p.trace[blockIdx.x * 64] = ffn_gtime();
 
   for (int i = threadIdx.x; i < HID; i += FFN_THREADS) sb1[i] = __ldg(p.b1 + i);
   for (int i = threadIdx.x; i < D; i += FFN_THREADS) {
@@ -88,7 +97,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < WSLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 16);
-      mbar_init(&h_full[i], 16); mbar_init(&h_empty[i], 1);
+      mbar_init(&h_full[i], 8); mbar_init(&h_empty[i], 1);
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
@@ -147,6 +156,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(a_full, lt & 1);
         mbar_wait(acc2_empty, (lt & 1) ^ 1);          // epilogue-2 of the previous tile has drained acc2
         tc_fence_after();
+        FTRACE(1);                                     // A tile landed
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
             // GEMM1_j -> acc1[c1n & 1]
@@ -164,16 +174,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               umma_commit(&w_empty[slot]);
             }
             umma_commit(&acc1_full[st]);
-            if (j == NCHUNK - 1) umma_commit(a_empty);      // last read of the A tile
+            FTRACE(8 + 4 * j);                               // GEMM1_j issued
             ++c1n;
           }
           if (j >= 1) {
-            // GEMM2_{j-1}: acc2 += H[c2n & 1] x W2 chunk
-            const uint32_t hb = c2n & 1, use = c2n >> 1;
-            mbar_wait(&h_full[hb], use & 1);
-            tc_fence_after();
+            // GEMM2_{j-1}: acc2 += H x W2 chunk; each H k-slab is released as soon as its MMAs are issued
             for (int k = 0; k < 2; ++k) {
-              const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_H + (hb * 2 + k) * SLAB), 1024);
+              mbar_wait(&h_full[k], c2n & 1);
+              tc_fence_after();
+              const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_H + k * SLAB), 1024);
               for (int hf = 0; hf < 2; ++hf) {
                 const uint32_t slot = next_w();
                 const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_W + slot * SLAB), 1024);
@@ -182,8 +191,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   umma_f16(tm_acc2 + hf * 128, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((j - 1) | k | kk) != 0 ? 1u : 0u);
                 umma_commit(&w_empty[slot]);
               }
+              umma_commit(&h_empty[k]);
             }
-            umma_commit(&h_empty[hb]);
+            FTRACE(8 + 4 * (j - 1) + 1);                     // GEMM2_{j-1} issued
             ++c2n;
           }
         }
@@ -196,7 +206,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = q * 32 + lane;
     const bool elected = (warp == 2 + 4 * part) && (lane == 0);
     const int part_bar = 6 + part;
-    uint8_t* const slab = smem + OFF_H + part * SLAB;         // epilogue-2 staging (H is dead by then)
+    uint8_t* const slab = smem + OFF_A + part * SLAB;         // epilogue-2 staging: the A tile is dead once acc2 is complete
     uint8_t* const slab_q = slab + q * 4096;
     uint32_t c1n = 0;
     uint32_t rph = 0;
@@ -208,6 +218,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t st = c1n & 1, use = c1n >> 1;
         mbar_wait(&acc1_full[st], use & 1);
         tc_fence_after();
+        if (threadIdx.x == 64) FTRACE(8 + 4 * j + 2);        // acc1_j ready (epilogue-1 starts)
         uint32_t v[32];
         tmem_ld_32x32b_x32(tm_acc1 + st * CHUNK + (static_cast<uint32_t>(q * 32) << 16) + part * 32, v);
         tmem_ld_wait();
@@ -230,10 +241,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc1_empty[st]);
-        // H buffer st: wait until GEMM2 of chunk c1n-2 has consumed it
-        mbar_wait(&h_empty[st], (use & 1) ^ 1);
+        // H k-slab (part >> 1): wait until GEMM2 of the previous chunk has consumed it
+        mbar_wait(&h_empty[part >> 1], (c1n & 1) ^ 1);
         // this warp's 32 columns = half of the 64-column k-slab (part >> 1), chunk slots (part & 1) * 4 ..
-        uint8_t* hs = smem + OFF_H + (st * 2 + (part >> 1)) * SLAB;
+        uint8_t* hs = smem + OFF_H + (part >> 1) * SLAB;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 u;
@@ -245,11 +256,13 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&h_full[st]);
+        if (lane == 0) mbar_arrive(&h_full[part >> 1]);
+        if (threadIdx.x == 64) FTRACE(8 + 4 * j + 3);        // H_j published
       }
       // ---- epilogue-2: acc2 + b2 + residual -> x' ; LayerNorm -> operand ----
       mbar_wait(acc2_full, lt & 1);
       tc_fence_after();
+      if (threadIdx.x == 64) FTRACE(2);                      // acc2 complete
       const bool row_ok = (m0 + r) < p.M;
       (void)row_ok;
       if (p.resid != nullptr && elected) {
@@ -349,13 +362,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elected) {
           tma_store_2d(&tmOp, slab, part * 64, m0);
           bulk_commit();
-          bulk_wait_read0();          // the slab (H region) is rewritten by the next tile's epilogue-1
+          bulk_wait_read0();          // the slab (A region) is refilled by the producer for the next tile
         }
       } else {
         if (elected) bulk_wait_read0();
       }
-      // every part's staging slab aliases an H buffer that other parts' warps write in the next tile's epilogue-1
+      // all four staging slabs (= the A region) are drained: let the producer load the next tile's A
       named_bar_sync(5, 512);
+      if (threadIdx.x == 64) mbar_arrive(a_empty);
+      if (threadIdx.x == 64) FTRACE(3);                      // epilogue-2 done
     }
     if (elected) bulk_wait0();
   }
@@ -392,7 +407,7 @@ bool ffn_fusable(int prec, int d_model) { return prec == PREC_BF16 && d_model ==
 // residual with x_out; out_op [M,256] bf16 (LayerNorm(x') or cast when gamma == null).
 const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, const float* b1, const void* w2,
                              const float* b2, int act, const float* resid, float* x_out, const float* gamma,
-                             const float* beta, void* out_op, int M, int num_sms) {
+                             const float* beta, void* out_op, int M, int num_sms, unsigned long long* trace) {
   if (M <= 0) return "ffn_fused: empty problem";
   if (resid != nullptr && resid != x_out) return "ffn_fused: residual must be updated in place";
   if (g_enc == nullptr) {
@@ -421,6 +436,7 @@ const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, cons
   FfnDev d;
   d.b1 = b1; d.b2 = b2; d.gamma = gamma; d.beta = beta; d.resid = resid;
   d.M = M; d.act = act; d.has_xout = x_out != nullptr; d.has_op = out_op != nullptr;
+  d.trace = trace;
   const int m_tiles = (M + 127) / 128;
   const int grid = m_tiles < num_sms ? m_tiles : num_sms;
   ffn_fused_kernel<<<grid, FFN_THREADS, FFN_SMEM, s>>>(ta, tw1, tw2, tx, top, d);

@@ -66,7 +66,8 @@ void gemm_set_epilogue_tma(bool on);   // A/B switch: epilogue I/O through TMA s
 bool ffn_fusable(int prec, int d_model);
 const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, const float* b1, const void* w2,
                              const float* b2, int act, const float* resid, float* x_out, const float* gamma,
-                             const float* beta, void* out_op, int M, int num_sms);
+                             const float* beta, void* out_op, int M, int num_sms,
+                             unsigned long long* trace = nullptr);
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).

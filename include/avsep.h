@@ -129,6 +129,10 @@ AVSEP_API int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* 
 AVSEP_API int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const float* b1, const void* w2,
                                    const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
                                    void* out_op, int32_t M, void* cuda_stream);
+AVSEP_API int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, const float* b1, const void* w2,
+                                         const float* b2, int32_t act, float* x_inout, const float* gamma,
+                                         const float* beta, void* out_op, int32_t M, unsigned long long* trace_dev,
+                                         void* cuda_stream);
 AVSEP_API int avsep_test_conv1d(avsep_handle* h, const void* A_padded, const void* W3, const float* bias, float* out, int32_t B,
                       int32_t L, int32_t N, int32_t K, void* cuda_stream);
 AVSEP_API int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H,
