@@ -134,9 +134,7 @@ __device__ __forceinline__ void load_tile_split(__nv_bfloat16* dst_hi, __nv_bflo
 // SPLIT = fp32-grade path: Q/K/V are fp32 in global memory and are staged as bf16 hi + lo tiles; every contraction is
 // three tensor-core products (hi*hi + hi*lo + lo*hi); P is split the same way; the output is fp32.
 template <int HD, bool LERP, bool SPLIT>
-// bf16 variants with hd <= 64 are compiled for 7 resident CTAs per SM (<= 72 registers): at T <= 64 the kernel is one
-// tile per (utterance, head) and purely latency-bound, so all B*H CTAs should be resident in a single wave.
-__global__ void __launch_bounds__(128, (SPLIT || HD > 64) ? 2 : 7) attention_kernel(const AttnDev p) {
+__global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   constexpr int LDS = HD + 8;           // padded row (elements): 16-byte rows shifted by 4 banks -> conflict-free ldmatrix
   constexpr int KS = HD / 16;           // k-steps over the head dimension
   constexpr int NT_O = HD / 8;          // output n-tiles
@@ -349,12 +347,9 @@ const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
   constexpr int SMEM = (SPLIT ? 6 : 3) * 64 * (HD + 8) * 2;
   static bool attr_done = false;
   auto kern = attention_kernel<HD, LERP, SPLIT>;
-  if (!attr_done) {
-    if (SMEM > 48 * 1024 &&
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+  if (!attr_done && SMEM > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return "attention: cudaFuncSetAttribute failed";
-    // prefer shared memory over L1 so that 7 CTAs (7 x 27 KB at hd = 64) fit on one SM
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
   dim3 grid((Lq + QT - 1) / QT, H, B);
