@@ -108,6 +108,7 @@ struct avsep_handle {
   bool fuse_ln = true;   // residual+LayerNorm in the GEMM epilogue when the row fits one tile
   bool use_graph = true; // replay the forward as a CUDA graph (captured per shape + buffer set on its 2nd use)
   bool fuse_ffn = true;   // linear1 -> act -> linear2 -> +residual -> LayerNorm in one kernel (d_model = 256, bf16)
+  int ffn_fused_min_rows = 2048;   // below this the unfused pair spreads over more CTAs and wins
   bool two_stream = true; // audio and visual branches on two streams (fork/join), so partial waves overlap
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -359,7 +360,7 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     const bool last = (l + 1 == layers.size());
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
-    if (h->fuse_ffn && ffn_fusable(prec, d)) {
+    if (h->fuse_ffn && ffn_fusable(prec, d) && M >= h->ffn_fused_min_rows) {
       CKL("ffn.fused", launch_ffn_fused(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x, g, b, a_op, M, h->num_sms));
     } else {
       if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
@@ -438,7 +439,7 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     const bool last = (l + 1 == Lf);
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
-    if (h->fuse_ffn && ffn_fusable(prec, d)) {
+    if (h->fuse_ffn && ffn_fusable(prec, d) && Ma >= h->ffn_fused_min_rows) {
       CKL("ffn.fused", launch_ffn_fused(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU, w.x_a, w.x_a, g, b, w.a_op, Ma,
                                         h->num_sms));
     } else {
@@ -1195,6 +1196,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "epilogue_tma") == 0) { gemm_set_epilogue_tma(value != 0); drop_graphs(h); return 0; }
   if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }
