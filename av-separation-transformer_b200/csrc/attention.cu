@@ -359,8 +359,24 @@ const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
 
 }  // namespace
 
+namespace {
+int g_tc_mode = 1;
+int g_tc_min_len = 96;
+}  // namespace
+
+void attention_set_tc(int mode, int min_len) {
+  g_tc_mode = mode;
+  if (min_len > 0) g_tc_min_len = min_len;
+}
+
+bool attention_tc_wanted(int prec, const AttnProblem& p) {
+  if (g_tc_mode == 0 || !attention_tc_usable(prec, p)) return false;
+  return g_tc_mode == 2 || (p.Lq < p.Lk ? p.Lq : p.Lk) >= g_tc_min_len;
+}
+
 const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p) {
   if (p.B <= 0 || p.Lq <= 0 || p.Lk <= 0) return "attention: empty problem";
+  if (attention_tc_wanted(prec, p)) return launch_attention_tc(s, p);
   const bool split = (prec == PREC_TF32);     // fp32 operands, bf16 hi/lo split contractions, fp32 output
   AttnDev d;
   d.q = p.q;

@@ -433,6 +433,18 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     ap.ldkv = Lf * 2 * d;
     ap.out = w.attn_a; ap.ldo = d;
     ap.B = B; ap.H = H; ap.hd = d / H; ap.Lq = T; ap.Lk = T; ap.lerp_src = L_src;
+    {
+      // Long sequences: materialise the interpolated K/V rows once (bf16, in the unused 2d columns' worth of the
+      // Q buffer) so the tcgen05 kernel can stage them by TMA; short ones interpolate on load inside the kernel.
+      AttnProblem tp = ap;
+      tp.lerp_src = 0;
+      __nv_bfloat16* kvi = static_cast<__nv_bfloat16*>(w.qkv_a) + static_cast<size_t>(Ma) * d;
+      tp.k = kvi; tp.v = kvi + d; tp.ldkv = 2 * d;
+      if (attention_tc_wanted(prec, tp)) {
+        CKL("lerp_kv", launch_lerp_rows(s, w.kvn + static_cast<size_t>(l) * 2 * d, Lf * 2 * d, B, L_src, T, 2 * d, kvi, 2 * d));
+        ap = tp;
+      }
+    }
     CKL("attn.cross", launch_attention(s, prec, ap));
     if (linear_resid_ln(h, s, "gemm.out_proj", w.attn_a, Ma, d, fw.wo, fw.bo, d, w.x_a, fw.n2g, fw.n2b, w.a_op, w.y_a))
       return 1;
@@ -1198,6 +1210,8 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "attn_tc") == 0) { attention_set_tc(value, 0); drop_graphs(h); return 0; }
+  if (strcmp(name, "attn_tc_min_len") == 0) { attention_set_tc(1, value); drop_graphs(h); return 0; }
   if (strcmp(name, "epilogue_tma") == 0) { gemm_set_epilogue_tma(value != 0); drop_graphs(h); return 0; }
   if (strcmp(name, "profile_spin_us") == 0) { h->profile_spin_us = value; return 0; }
   return fail(h, std::string("unknown option ") + name);
@@ -1222,7 +1236,23 @@ int avsep_test_attention(avsep_handle* h, const void* q, const void* k, const vo
   AttnProblem ap{};
   ap.q = q; ap.ldq = H * hd; ap.k = k; ap.v = v; ap.ldkv = H * hd; ap.out = out; ap.ldo = H * hd;
   ap.B = B; ap.H = H; ap.hd = hd; ap.Lq = Lq; ap.Lk = Lk; ap.lerp_src = lerp_src;
-  CK(launch_attention(static_cast<cudaStream_t>(cuda_stream), h->cfg.precision, ap));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  void* scratch = nullptr;
+  if (lerp_src > 0) {   // same routing as fusion_stack: K then V columns side by side in one interpolated buffer
+    AttnProblem tp = ap;
+    tp.lerp_src = 0; tp.ldkv = 2 * H * hd;
+    if (attention_tc_wanted(h->cfg.precision, tp)) {
+      const int dm = H * hd;
+      if (cudaMalloc(&scratch, static_cast<size_t>(B) * Lk * 2 * dm * 2) != cudaSuccess) return fail(h, "test_attention: cudaMalloc failed");
+      tp.k = scratch; tp.v = static_cast<__nv_bfloat16*>(scratch) + dm;
+      CK(launch_lerp_rows(s, static_cast<const float*>(k), dm, B, lerp_src, Lk, dm, scratch, 2 * dm));
+      CK(launch_lerp_rows(s, static_cast<const float*>(v), dm, B, lerp_src, Lk, dm, static_cast<__nv_bfloat16*>(scratch) + dm, 2 * dm));
+      ap = tp;
+    }
+  }
+  const char* err = launch_attention(s, h->cfg.precision, ap);
+  if (scratch) { cudaStreamSynchronize(s); cudaFree(scratch); }
+  if (err) return fail(h, err);
   return 0;
 }
 

@@ -101,6 +101,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, but each probe may suspend the thread in hardware for up to ~1 us (suspend-time hint) instead of spinning:
+// for single-thread producer / MMA-issuer roles that share an SM sub-partition with compute warps, so that their
+// polling does not take issue slots.  The watchdog is then checked about once per microsecond.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 1000u)) {
+    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) {
+      printf("avsep: mbarrier watchdog fired (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), completion on an mbarrier
 // ------------------------------------------------------------------------------------------

@@ -86,6 +86,15 @@ struct AttnProblem {
   int lerp_src;                    // 0 = plain; >0 = K/V hold lerp_src source rows per utterance, interpolated to Lk rows
 };
 const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p);
+// tcgen05 flash attention (attention_tc.cu): bf16, head dim 64, materialised K/V rows.  launch_attention dispatches
+// to it by itself; mode 0 = never, 1 = when min(Lq, Lk) >= min_len, 2 = whenever usable.
+bool attention_tc_usable(int prec, const AttnProblem& p);
+bool attention_tc_wanted(int prec, const AttnProblem& p);      // usable and selected by the current mode
+const char* launch_attention_tc(cudaStream_t s, const AttnProblem& p);
+void attention_set_tc(int mode, int min_len);                  // min_len <= 0 keeps the current value
+// dst[b*L + t, 0:cols] (bf16) = linear interpolation (align_corners=False) of src rows [b*nsrc + i, 0:cols] (fp32)
+const char* launch_lerp_rows(cudaStream_t s, const float* src, int ld_src, int B, int nsrc, int L, int cols,
+                             void* dst_bf16, int ld_dst);
 
 struct CnnWeights {                // BN-folded, fragment-ordered (see visual_cnn.cu)
   const uint32_t* w1; const float* b1;

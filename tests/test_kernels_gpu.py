@@ -278,3 +278,56 @@ def test_visual_cnn(Hh, Ww, M, tc):
         assert err < 2e-2 * max(1.0, scale), (err, scale)
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 4, 63, 63), (1, 4, 128, 128), (2, 2, 300, 300), (1, 4, 1251, 1251),
+                                       (3, 4, 129, 257), (2, 4, 500, 500), (1, 1, 5, 5), (2, 4, 200, 77)])
+def test_attention_tcgen05_self(eng, B, H, Lq, Lk):
+    """tcgen05 flash-attention kernel (attention_tc.cu), forced on for every shape, against fp32 softmax attention."""
+    hd = 64
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Lq + Lk)
+    d = H * hd
+    q = torch.randn(B, Lq, d, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Lk, d, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, d, device="cuda", generator=g).bfloat16()
+    out = torch.full((B, Lq, d), 7.0, device="cuda", dtype=torch.bfloat16)
+    guard = out.clone()
+    eng.set_option("attn_tc", 2)
+    try:
+        _check(eng, eng.lib.avsep_test_attention(eng.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                 B, H, hd, Lq, Lk, 0, _s()))
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("attn_tc", 1)
+    qh, kh, vh = (t.float().view(B, -1, H, hd).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(hd), -1) @ vh
+    ref = ref.transpose(1, 2).reshape(B, Lq, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err
+    assert not torch.equal(out, guard)
+
+
+@pytest.mark.parametrize("B,H,T,N", [(2, 4, 63, 50), (1, 4, 300, 120), (2, 4, 1251, 500), (1, 2, 640, 64)])
+def test_attention_tcgen05_cross_materialised_lerp(eng, B, H, T, N):
+    hd = 64
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + N)
+    d = H * hd
+    q = torch.randn(B, T, d, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, N, d, device="cuda", generator=g)
+    v = torch.randn(B, N, d, device="cuda", generator=g)
+    out = torch.zeros(B, T, d, device="cuda", dtype=torch.bfloat16)
+    eng.set_option("attn_tc", 2)
+    try:
+        _check(eng, eng.lib.avsep_test_attention(eng.h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                 B, H, hd, T, T, N, _s()))
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("attn_tc", 1)
+    up = lambda t: torch.nn.functional.interpolate(t.permute(0, 2, 1), size=T, mode="linear",
+                                                   align_corners=False).permute(0, 2, 1)
+    qh = q.float().view(B, T, H, hd).transpose(1, 2)
+    kh = up(k).view(B, T, H, hd).transpose(1, 2)
+    vh = up(v).view(B, T, H, hd).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(hd), -1) @ vh).transpose(1, 2).reshape(B, T, d)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err
