@@ -115,6 +115,7 @@ def kernel_work(B):
         "visual_cnn": Mv * cnn_per_frame, "gemm.frame_proj": Mv * 2 * 128 * d,
         "gemm.dec0": Ma * 2 * 2 * d * d, "gemm.dec3_tail": Ma * 2 * S * F * 2 * d,
     }
+    flops["ffn.fused"] = flops["gemm.ffn1"] + flops["gemm.ffn2"]     # linear1 + act + linear2 + residual + LN in one kernel
     n_ln = 2 + 2 * Le * 2 + 2 * Lf            # launches per forward
     ln_rows = (1 + 2 * Le) * Ma + (1 + 2 * Le) * Mv + 2 * Lf * Ma
     bytes_ = {
@@ -147,7 +148,7 @@ def max_over_ranks_cpu(x):
 
 
 def total_flops(B):
-    return sum(kernel_work(B)[0].values())
+    return sum(v for k, v in kernel_work(B)[0].items() if k != "ffn.fused")   # ffn.fused = ffn1 + ffn2, counted once
 
 
 # ----------------------------------------------------------------------------------------------
