@@ -5,6 +5,7 @@ Host-side mirror of the reference interface (``model.py``) over the C ABI of lib
 from .model import (AudioEncoder, VisualEncoder, CrossModalFusion, CrossAttentionLayer, SeparationDecoder,
                     AVSeparationTransformer, PositionalEncoding)
 from .engine import Engine, EngineConfig, STAGE_NAMES
+from .dataset import SyntheticAVDataset, evaluate_separation
 
 __all__ = ["AudioEncoder", "VisualEncoder", "CrossModalFusion", "CrossAttentionLayer", "SeparationDecoder",
-           "AVSeparationTransformer", "PositionalEncoding", "Engine", "EngineConfig", "STAGE_NAMES"]
+           "AVSeparationTransformer", "PositionalEncoding", "Engine", "EngineConfig", "STAGE_NAMES", "SyntheticAVDataset", "evaluate_separation"]

@@ -23,6 +23,13 @@ class AvsepConfig(C.Structure):
     ]
 
 
+class AvsepSynthConfig(C.Structure):
+    _fields_ = [
+        ("num_samples_audio", C.c_int32), ("duration", C.c_double), ("n_fft", C.c_int32), ("hop_length", C.c_int32),
+        ("num_frames", C.c_int32), ("frame_h", C.c_int32), ("frame_w", C.c_int32), ("num_speakers", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 
@@ -56,6 +63,8 @@ SIGNATURES = {
     "avsep_test_add_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "avsep_test_visual_cnn": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
     "avsep_test_visual_cnn_trace": (C.c_int, [_P, _P, _I, _P, _P, _P]),
+    "avsep_synth_batch": (C.c_int, [_P, C.POINTER(AvsepSynthConfig), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "avsep_eval_snr": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -229,6 +229,60 @@ class Engine:
         self._check(rc, "avsep_decoder")
         return sep, masks
 
+    # ---- rows either side of the path --------------------------------------------------------------
+    def synth_batch(self, geom: dict, amps, freqs, phases, noise=None, want_clean: bool = True):
+        """avsep_synth_batch: device tensors amps/freqs/phases (B,S) float64, noise (B,S,nf,ph,pw) float32 or None.
+
+        geom keys: num_samples_audio, duration, n_fft, hop_length, num_frames, frame_h, frame_w, num_speakers.
+        Returns mixed_spec (B,F,T), lip_frames (B,S*nf,H,W), clean_specs (B,S,F,T) or None."""
+        dev = torch.device("cuda", self.device)
+        for t, dt in ((amps, torch.float64), (freqs, torch.float64), (phases, torch.float64)):
+            if t.device != dev or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("synth_batch: amps/freqs/phases must be contiguous float64 tensors on the engine device")
+        B, S = amps.shape
+        if S != geom["num_speakers"] or freqs.shape != amps.shape or phases.shape != amps.shape:
+            raise ValueError("synth_batch: amps/freqs/phases must be (B, num_speakers)")
+        cfg = _lib.AvsepSynthConfig(geom["num_samples_audio"], float(geom["duration"]), geom["n_fft"],
+                                    geom["hop_length"], geom["num_frames"], geom["frame_h"], geom["frame_w"], S)
+        F, T = geom["n_fft"] // 2 + 1, 1 + geom["num_samples_audio"] // geom["hop_length"]
+        nf, Hh, Ww = geom["num_frames"], geom["frame_h"], geom["frame_w"]
+        if noise is not None:
+            want = (B, S, nf, 3 * Hh // 4 - Hh // 4, 3 * Ww // 4 - Ww // 4)
+            if tuple(noise.shape) != want or noise.dtype != torch.float32 or noise.device != dev or not noise.is_contiguous():
+                raise ValueError(f"synth_batch: noise must be a contiguous float32 device tensor of shape {want}")
+        mixed = torch.empty(B, F, T, device=dev)
+        frames = torch.empty(B, S * nf, Hh, Ww, device=dev)
+        clean = torch.empty(B, S, F, T, device=dev) if want_clean else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_synth_batch(self.h, C.byref(cfg), B, amps.data_ptr(), freqs.data_ptr(), phases.data_ptr(),
+                                            noise.data_ptr() if noise is not None else None, mixed.data_ptr(),
+                                            frames.data_ptr(), clean.data_ptr() if clean is not None else None,
+                                            self._stream())
+        self._check(rc, "avsep_synth_batch")
+        return mixed, frames, clean
+
+    def eval_snr(self, separated, targets, mixed=None):
+        """avsep_eval_snr: per-utterance input SNRs (B,S), best-permutation output SNR (B), permutation code (B),
+        SI-SNR (B); float64 dB, device tensors."""
+        dev = torch.device("cuda", self.device)
+        for t in (separated, targets) + ((mixed,) if mixed is not None else ()):
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("eval_snr: tensors must be contiguous float32 on the engine device")
+        B, S, F, T = separated.shape
+        if targets.shape != separated.shape or (mixed is not None and tuple(mixed.shape) != (B, F, T)):
+            raise ValueError("eval_snr: shape mismatch")
+        in_snr = torch.empty(B, S, device=dev, dtype=torch.float64) if mixed is not None else None
+        out_snr = torch.empty(B, device=dev, dtype=torch.float64)
+        perm = torch.empty(B, device=dev, dtype=torch.int32)
+        si = torch.empty(B, device=dev, dtype=torch.float64)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_eval_snr(self.h, separated.data_ptr(), targets.data_ptr(),
+                                         mixed.data_ptr() if mixed is not None else None, B, S, F, T,
+                                         in_snr.data_ptr() if in_snr is not None else None, out_snr.data_ptr(),
+                                         perm.data_ptr(), si.data_ptr(), self._stream())
+        self._check(rc, "avsep_eval_snr")
+        return in_snr, out_snr, perm, si
+
     def set_option(self, name: str, value: int):
         """Execution options: 'fuse_ln' (0/1), 'host_chunk' (utterances per pipeline chunk of forward_host)."""
         self._check(self.lib.avsep_set_option(self.h, name.encode(), int(value)), "avsep_set_option")

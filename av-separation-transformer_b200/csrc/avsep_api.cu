@@ -133,6 +133,8 @@ struct avsep_handle {
   // host-path staging
   float *io_mixed = nullptr, *io_frames = nullptr, *io_sep = nullptr, *io_masks = nullptr;
   size_t io_cap[4] = {0, 0, 0, 0};
+  float* synth_waves = nullptr;   // scratch of avsep_synth_batch
+  size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> host_ev;
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
@@ -655,6 +657,7 @@ void avsep_destroy(avsep_handle* h) {
   if (h->io_frames) cudaFree(h->io_frames);
   if (h->io_sep) cudaFree(h->io_sep);
   if (h->io_masks) cudaFree(h->io_masks);
+  if (h->synth_waves) cudaFree(h->synth_waves);
   for (auto& kv : h->snaps)
     if (kv.second.first) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -987,6 +990,46 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
   CUDA_OK(cudaEventRecord(ev_end, s_out));
   CUDA_OK(cudaStreamWaitEvent(s, ev_end, 0));
   CUDA_OK(cudaStreamSynchronize(s_out));
+  return 0;
+}
+
+int avsep_synth_batch(avsep_handle* h, const avsep_synth_config* cfg, int32_t B, const double* amps, const double* freqs,
+                      const double* phases, const float* noise, float* mixed_spec, float* lip_frames,
+                      float* clean_specs, void* cuda_stream) {
+  if (!h) return 1;
+  if (!cfg || !amps || !freqs || !phases || !mixed_spec || !lip_frames) return fail(h, "avsep_synth_batch: null argument");
+  if (B < 1) return fail(h, "avsep_synth_batch: empty batch");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  SynthProblem p{};
+  p.B = B; p.S = cfg->num_speakers; p.n = cfg->num_samples_audio; p.nfft = cfg->n_fft; p.hop = cfg->hop_length;
+  p.nf = cfg->num_frames; p.Hh = cfg->frame_h; p.Ww = cfg->frame_w; p.duration = cfg->duration;
+  p.amps = amps; p.freqs = freqs; p.phases = phases; p.noise = noise;
+  p.mixed_spec = mixed_spec; p.lip_frames = lip_frames; p.clean_specs = clean_specs;
+  if (p.S < 1 || p.n < 1) return fail(h, "avsep_synth_batch: bad geometry");
+  const size_t need = static_cast<size_t>(B) * (p.S + 1) * p.n;
+  if (h->synth_cap < need) {
+    if (h->synth_waves) cudaFree(h->synth_waves);
+    h->synth_waves = nullptr; h->synth_cap = 0;
+    CUDA_OK(cudaMalloc(&h->synth_waves, need * sizeof(float)));
+    h->synth_cap = need;
+  }
+  p.waves = h->synth_waves;
+  h->launches = 0;
+  CK(launch_synth(static_cast<cudaStream_t>(cuda_stream), p));
+  h->launches = 3;
+  return 0;
+}
+
+int avsep_eval_snr(avsep_handle* h, const float* separated, const float* targets, const float* mixed, int32_t B,
+                   int32_t S, int32_t F, int32_t T, double* input_snr, double* output_snr, int32_t* best_perm,
+                   double* si_snr, void* cuda_stream) {
+  if (!h) return 1;
+  if (!separated || !targets) return fail(h, "avsep_eval_snr: null argument");
+  if (B < 1 || F < 1 || T < 1) return fail(h, "avsep_eval_snr: empty problem");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  CK(launch_eval_snr(static_cast<cudaStream_t>(cuda_stream), separated, targets, mixed, B, S, F * T, input_snr,
+                     output_snr, best_perm, si_snr));
+  h->launches = 1;
   return 0;
 }
 

@@ -138,14 +138,7 @@ __device__ __forceinline__ void stg_store_rows(const uint8_t* buf, unsigned long
     if (rp != 0) *reinterpret_cast<uint4*>(rp + c * 16) = *reinterpret_cast<const uint4*>(buf + stg_off(row, c));
   }
 }
-// own row (lane) <-> 32 fp32 registers
-__device__ __forceinline__ void stg_read_own_f32(const uint8_t* buf, int lane, float (&x)[32]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float4 v4 = *reinterpret_cast<const float4*>(buf + stg_off(lane, c));
-    x[4 * c] = v4.x; x[4 * c + 1] = v4.y; x[4 * c + 2] = v4.z; x[4 * c + 3] = v4.w;
-  }
-}
+// own row (lane) += 32 fp32 values of the slab
 __device__ __forceinline__ void stg_add_own_f32(const uint8_t* buf, int lane, float (&x)[32]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {

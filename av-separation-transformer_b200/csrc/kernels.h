@@ -116,4 +116,17 @@ size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint3
 void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3,
                      bool lo_part = false);
 
+// ---- rows either side of the path (synth.cu) ----
+struct SynthProblem {
+  int B, S, n, nfft, hop, nf, Hh, Ww;
+  double duration;
+  const double *amps, *freqs, *phases;   // (B,S)
+  const float* noise;                    // (B,S,nf,ph,pw) or null
+  float* waves;                          // scratch (B, S+1, n)
+  float *mixed_spec, *lip_frames, *clean_specs;
+};
+const char* launch_synth(cudaStream_t s, const SynthProblem& p);
+const char* launch_eval_snr(cudaStream_t s, const float* separated, const float* targets, const float* mixed, int B,
+                            int S, int FT, double* input_snr, double* output_snr, int* best_perm, double* si_snr);
+
 }  // namespace avsep

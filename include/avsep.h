@@ -144,6 +144,40 @@ AVSEP_API int avsep_test_visual_cnn(avsep_handle* h, const float* frames, int32_
 AVSEP_API int avsep_test_visual_cnn_trace(avsep_handle* h, const float* frames, int32_t M, void* pooled,
                                           unsigned long long* trace_dev, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The rows either side of the path.  All pointers are DEVICE pointers.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Geometry of the reference's SyntheticAVDataset (reference src/av_separation/dataset.py:33-65). */
+typedef struct avsep_synth_config {
+  int32_t num_samples_audio;  /* int(sample_rate * duration), dataset.py:59 */
+  double duration;            /* seconds (t = linspace(0, duration, n, endpoint=False), dataset.py:60) */
+  int32_t n_fft;              /* power of two, <= 2048; freq_bins = n_fft/2 + 1 */
+  int32_t hop_length;         /* T = 1 + num_samples_audio / hop_length, dataset.py:65 */
+  int32_t num_frames;         /* video frames per speaker; the item holds num_speakers * num_frames frames */
+  int32_t frame_h, frame_w;
+  int32_t num_speakers;
+} avsep_synth_config;
+
+/* Replaces SyntheticAVDataset.__getitem__ for a batch (dataset.py:70-119, _stft :122-135, _make_lip_frame :137-147).
+ * The reference's random draws are inputs (consume numpy's default_rng(idx) in the reference's order on the host):
+ *   amps, freqs (already jittered), phases : (B, S) float64;  noise : (B, S, num_frames, H/2-ish, W/2-ish) float32
+ *   patch noise N(0, 0.05), or NULL for none.
+ * Outputs: mixed_spec (B, F, T), lip_frames (B, S*num_frames, H, W), clean_specs (B, S, F, T) or NULL, float32. */
+AVSEP_API int avsep_synth_batch(avsep_handle* h, const avsep_synth_config* cfg, int32_t B, const double* amps,
+                                const double* freqs, const double* phases, const float* noise, float* mixed_spec,
+                                float* lip_frames, float* clean_specs, void* cuda_stream);
+
+/* Replaces the per-utterance SNR evaluation after the path: snr_db / _permutation_snr of evaluate_separation
+ * (reference demo.py:25-29,55-62,67-80) and the per-row value of si_snr (src/av_separation/losses.py:14-42).
+ *   separated, targets : (B, S, F, T) float32;  mixed : (B, F, T) float32 or NULL
+ * Outputs (any may be NULL): input_snr (B, S) float64 dB; output_snr (B) float64 dB = best-permutation mean;
+ * best_perm (B) int32 = the chosen permutation as base-4 digits (digit t = index of the separated channel matched
+ * with target t, most significant first); si_snr (B) float64 dB over the flattened (S, F, T) row.  S <= 4. */
+AVSEP_API int avsep_eval_snr(avsep_handle* h, const float* separated, const float* targets, const float* mixed,
+                             int32_t B, int32_t S, int32_t F, int32_t T, double* input_snr, double* output_snr,
+                             int32_t* best_perm, double* si_snr, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
