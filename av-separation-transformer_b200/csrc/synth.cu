@@ -40,17 +40,20 @@ __global__ void synth_wave_kernel(const double* __restrict__ amps, const double*
   waves[static_cast<size_t>(b) * (S + 1) * n + i] = mix;
 }
 
-// One CTA = TG consecutive STFT frames of one signal.  N/2 threads (one butterfly per stage).
+// One CTA = TG consecutive STFT frames of one signal, N/2 threads (one butterfly per stage).  Two real frames share
+// one complex transform (frame A in the real part, frame B in the imaginary part; A[k] = (Z[k] + conj Z[N-k]) / 2,
+// B[k] = (Z[k] - conj Z[N-k]) / 2i), the fp64 Hann window is evaluated once per CTA.
 constexpr int TG = 8;
 
 __global__ void stft_mag_kernel(const float* __restrict__ waves, int n, int nfft, int log2n, int hop, int T, int F,
                                 int S, float* __restrict__ mixed_spec, float* __restrict__ clean_specs) {
-  extern __shared__ float sm[];
-  float* re = sm;                 // [nfft]
-  float* im = re + nfft;          // [nfft]
-  float* twr = im + nfft;         // [nfft/2]
-  float* twi = twr + nfft / 2;    // [nfft/2]
-  float* stage = twi + nfft / 2;  // [F][TG]
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* win = reinterpret_cast<double*>(sm_raw);          // [nfft]
+  float* re = reinterpret_cast<float*>(win + nfft);         // [nfft]
+  float* im = re + nfft;                                    // [nfft]
+  float* twr = im + nfft;                                   // [nfft/2]
+  float* twi = twr + nfft / 2;                              // [nfft/2]
+  float* stage = twi + nfft / 2;                            // [F][TG]
   const int sig = blockIdx.y;     // b * (S+1) + j
   const int b = sig / (S + 1), j = sig - b * (S + 1);
   const int t0 = blockIdx.x * TG;
@@ -60,22 +63,30 @@ __global__ void stft_mag_kernel(const float* __restrict__ waves, int n, int nfft
     float sv, cv;
     sincospif(-2.0f * static_cast<float>(tid) / static_cast<float>(nfft), &sv, &cv);
     twr[tid] = cv; twi[tid] = sv;
-  }
-  for (int g = 0; g < TG; ++g) {
-    const int t = t0 + g;
-    if (t >= T) break;                                 // uniform across the CTA
-    __syncthreads();
-    // window (np.hanning: 0.5 + 0.5*cos(pi*(1-M+2k)/(M-1)), fp64), product rounded to fp32 (in-place `frame *= window`
-    // on a float32 array, dataset.py:131), bit-reversed placement for the in-place DIT FFT
+    // np.hanning(M): 0.5 + 0.5*cos(pi*(1-M+2k)/(M-1)), fp64
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int k = tid + h * (nfft / 2);
-      const int src = t * hop + k;
-      const float v = src < n ? x[src] : 0.f;
-      const double w = 0.5 + 0.5 * cos(kPi * static_cast<double>(1 - nfft + 2 * k) / static_cast<double>(nfft - 1));
+      win[k] = 0.5 + 0.5 * cos(kPi * static_cast<double>(1 - nfft + 2 * k) / static_cast<double>(nfft - 1));
+    }
+  }
+  const int ng = min(TG, T - t0);
+  for (int g = 0; g < ng; g += 2) {
+    const int ta = t0 + g;
+    const bool has_b = g + 1 < ng;
+    __syncthreads();
+    // windowed product rounded to fp32 (in-place `frame *= window` on a float32 array, dataset.py:131), frames
+    // zero-padded past the end of the signal, bit-reversed placement for the in-place DIT transform
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = tid + h * (nfft / 2);
+      const int sa = ta * hop + k, sb = sa + hop;
+      const float va = sa < n ? x[sa] : 0.f;
+      const float vb = (has_b && sb < n) ? x[sb] : 0.f;
+      const double w = win[k];
       const int r = static_cast<int>(__brev(static_cast<unsigned>(k)) >> (32 - log2n));
-      re[r] = static_cast<float>(static_cast<double>(v) * w);
-      im[r] = 0.f;
+      re[r] = static_cast<float>(static_cast<double>(va) * w);
+      im[r] = static_cast<float>(static_cast<double>(vb) * w);
     }
     for (int s = 1; s <= log2n; ++s) {
       __syncthreads();
@@ -92,13 +103,17 @@ __global__ void stft_mag_kernel(const float* __restrict__ waves, int n, int nfft
       re[i1] = ar - pr; im[i1] = ai - pi;
     }
     __syncthreads();
-    for (int f = tid; f < F; f += blockDim.x) stage[f * TG + g] = hypotf(re[f], im[f]);
+    for (int f = tid; f < F; f += blockDim.x) {
+      const int fn = (nfft - f) & (nfft - 1);
+      const float zr = re[f], zi = im[f], yr = re[fn], yi = im[fn];
+      stage[f * TG + g] = 0.5f * hypotf(zr + yr, zi - yi);
+      if (has_b) stage[f * TG + g + 1] = 0.5f * hypotf(zi + yi, yr - zr);
+    }
   }
   __syncthreads();
   float* out = j == 0 ? mixed_spec + static_cast<size_t>(b) * F * T
                       : (clean_specs ? clean_specs + (static_cast<size_t>(b) * S + (j - 1)) * F * T : nullptr);
   if (out == nullptr) return;
-  const int ng = min(TG, T - t0);
   for (int e = tid; e < F * TG; e += blockDim.x) {
     const int f = e / TG, g = e - f * TG;
     if (g < ng) out[static_cast<size_t>(f) * T + t0 + g] = stage[e];
@@ -284,7 +299,8 @@ const char* launch_synth(cudaStream_t s, const SynthProblem& p) {
   const int T = 1 + p.n / p.hop, F = p.nfft / 2 + 1;
   synth_wave_kernel<<<dim3((p.n + 255) / 256, p.B), 256, 0, s>>>(p.amps, p.freqs, p.phases, p.S, p.n,
                                                                  p.duration / static_cast<double>(p.n), p.waves);
-  const size_t smem = (3 * static_cast<size_t>(p.nfft) + static_cast<size_t>(F) * TG) * sizeof(float);
+  const size_t smem = static_cast<size_t>(p.nfft) * sizeof(double) +
+                      (3 * static_cast<size_t>(p.nfft) + static_cast<size_t>(F) * TG) * sizeof(float);
   stft_mag_kernel<<<dim3((T + TG - 1) / TG, p.B * (p.S + 1)), p.nfft / 2, smem, s>>>(
       p.waves, p.n, p.nfft, log2n, p.hop, T, F, p.S, p.mixed_spec, p.clean_specs);
   lip_frames_kernel<<<dim3(p.nf, p.S, p.B), 256, 0, s>>>(p.waves, p.noise, p.S, p.n, p.nf, p.Hh, p.Ww, p.lip_frames);
