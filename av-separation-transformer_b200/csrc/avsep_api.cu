@@ -138,6 +138,10 @@ struct avsep_handle {
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> host_ev;
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
+  int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
+  void* host_ws = nullptr;
+  size_t host_ws_bytes = 0;
+  cudaStream_t host_comp[3] = {nullptr, nullptr, nullptr};
   // debug
   bool debug = false;
   std::map<std::string, std::pair<float*, size_t>> snaps;
@@ -658,6 +662,7 @@ void avsep_destroy(avsep_handle* h) {
   if (h->io_sep) cudaFree(h->io_sep);
   if (h->io_masks) cudaFree(h->io_masks);
   if (h->synth_waves) cudaFree(h->synth_waves);
+  if (h->host_ws) cudaFree(h->host_ws);
   for (auto& kv : h->snaps)
     if (kv.second.first) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -949,36 +954,59 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
     for (int i = 0; i < 3; ++i) CUDA_OK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
   }
   const int Bc = h->host_chunk > 0 && h->host_chunk < B ? h->host_chunk : B;
-  const int nchunks = (B + Bc - 1) / Bc;
+  std::vector<int> starts, sizes;
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    starts.push_back(b0);
+    sizes.push_back((B - b0) < Bc ? (B - b0) : Bc);
+  }
+  const int nchunks = static_cast<int>(starts.size());
   while (static_cast<int>(h->host_ev.size()) < 2 * nchunks + 2) {
     cudaEvent_t e;
     CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->host_ev.push_back(e);
   }
-  Workspace w;
-  if (get_workspace(h, w, nullptr, 0, Bc, T, N, Hh, Ww)) return 1;
-  cudaStream_t s_in = h->hs[0], s_comp = h->hs[1], s_out = h->hs[2];
+  // one workspace + compute stream per lane: with small chunks a single forward cannot fill the GPU, so the kernels
+  // of consecutive chunks are allowed to overlap
+  const int lanes = h->host_lanes < 1 ? 1 : (h->host_lanes > 3 ? 3 : h->host_lanes);
+  Workspace wl[3];
+  const size_t per_lane = carve_workspace(h, wl[0], nullptr, Bc, T, N, Hh, Ww);
+  if (h->host_ws_bytes < per_lane * lanes) {
+    drop_graphs(h);
+    if (h->host_ws) cudaFree(h->host_ws);
+    h->host_ws = nullptr;
+    h->host_ws_bytes = 0;
+    CUDA_OK(cudaMalloc(&h->host_ws, per_lane * lanes));
+    h->host_ws_bytes = per_lane * lanes;
+  }
+  for (int l = 0; l < lanes; ++l) {
+    carve_workspace(h, wl[l], static_cast<uint8_t*>(h->host_ws) + l * per_lane, Bc, T, N, Hh, Ww);
+    if (h->host_comp[l] == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&h->host_comp[l], cudaStreamNonBlocking));
+  }
+  cudaStream_t s_in = h->hs[0], s_out = h->hs[2];
   // order after whatever the caller queued on its stream
   cudaEvent_t ev_start = h->host_ev[2 * nchunks];
   CUDA_OK(cudaEventRecord(ev_start, s));
   CUDA_OK(cudaStreamWaitEvent(s_in, ev_start, 0));
-  CUDA_OK(cudaStreamWaitEvent(s_comp, ev_start, 0));
+  for (int l = 0; l < lanes; ++l) CUDA_OK(cudaStreamWaitEvent(h->host_comp[l], ev_start, 0));
   CUDA_OK(cudaStreamWaitEvent(s_out, ev_start, 0));
-  h->launches = 0;
+  int64_t launches = 0;
   for (int c = 0; c < nchunks; ++c) {
-    const int b0 = c * Bc;
-    const int bc = (B - b0) < Bc ? (B - b0) : Bc;
+    const size_t b0 = starts[c];
+    const int bc = sizes[c];
+    const int lane = c % lanes;
+    cudaStream_t s_comp = h->host_comp[lane];
     CUDA_OK(cudaMemcpyAsync(h->io_mixed + b0 * mixed_per, mixed_spec + b0 * mixed_per, bc * mixed_per * 4,
                             cudaMemcpyHostToDevice, s_in));
     CUDA_OK(cudaMemcpyAsync(h->io_frames + b0 * frames_per, lip_frames + b0 * frames_per, bc * frames_per * 4,
                             cudaMemcpyHostToDevice, s_in));
     CUDA_OK(cudaEventRecord(h->host_ev[2 * c], s_in));
     CUDA_OK(cudaStreamWaitEvent(s_comp, h->host_ev[2 * c], 0));
-    Workspace wc = w;
+    Workspace wc = wl[lane];
     wc.B = bc;
-    if (forward_cached(h, s_comp, wc, h->own_ws, h->io_mixed + b0 * mixed_per, h->io_frames + b0 * frames_per,
-                       h->io_sep + b0 * out_per, h->io_masks + b0 * out_per))
+    if (forward_cached(h, s_comp, wc, static_cast<uint8_t*>(h->host_ws) + lane * per_lane, h->io_mixed + b0 * mixed_per,
+                       h->io_frames + b0 * frames_per, h->io_sep + b0 * out_per, h->io_masks + b0 * out_per))
       return 1;
+    launches += h->launches;
     CUDA_OK(cudaEventRecord(h->host_ev[2 * c + 1], s_comp));
     CUDA_OK(cudaStreamWaitEvent(s_out, h->host_ev[2 * c + 1], 0));
     CUDA_OK(cudaMemcpyAsync(separated + b0 * out_per, h->io_sep + b0 * out_per, bc * out_per * 4,
@@ -986,6 +1014,7 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
     CUDA_OK(cudaMemcpyAsync(masks + b0 * out_per, h->io_masks + b0 * out_per, bc * out_per * 4,
                             cudaMemcpyDeviceToHost, s_out));
   }
+  h->launches = launches;
   cudaEvent_t ev_end = h->host_ev[2 * nchunks + 1];
   CUDA_OK(cudaEventRecord(ev_end, s_out));
   CUDA_OK(cudaStreamWaitEvent(s, ev_end, 0));
@@ -1009,6 +1038,7 @@ int avsep_synth_batch(avsep_handle* h, const avsep_synth_config* cfg, int32_t B,
   const size_t need = static_cast<size_t>(B) * (p.S + 1) * p.n;
   if (h->synth_cap < need) {
     if (h->synth_waves) cudaFree(h->synth_waves);
+  if (h->host_ws) cudaFree(h->host_ws);
     h->synth_waves = nullptr; h->synth_cap = 0;
     CUDA_OK(cudaMalloc(&h->synth_waves, need * sizeof(float)));
     h->synth_cap = need;
@@ -1248,6 +1278,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
+  if (strcmp(name, "host_lanes") == 0) { h->host_lanes = value; return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }

@@ -1,0 +1,35 @@
+"""End-to-end (host buffers in, host buffers out) throughput of avsep_forward_host vs chunk size / lanes, next to the
+raw pinned-copy times of the same bytes."""
+import json, os, sys, time
+import torch
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200")); sys.path.insert(0, ROOT)
+from avsep_b200 import AVSeparationTransformer
+from avsep_b200.synth import synthetic_batch
+
+B = 256
+m = AVSeparationTransformer().eval(); m.prepack("cuda")
+eng = m.engine
+mixed, frames = synthetic_batch(B, device="cpu")
+mixed, frames = mixed.pin_memory(), frames.pin_memory()
+sep = torch.empty(B, 2, 257, 63).pin_memory(); masks = torch.empty_like(sep).pin_memory()
+dm, df = mixed.cuda(), frames.cuda(); ds, dk = sep.cuda(), masks.cuda()
+def timed(fn, n=10):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def h2d():
+    dm.copy_(mixed, non_blocking=True); df.copy_(frames, non_blocking=True)
+def d2h():
+    sep.copy_(ds, non_blocking=True); masks.copy_(dk, non_blocking=True)
+def both():
+    with torch.cuda.stream(s1): h2d()
+    with torch.cuda.stream(s2): d2h()
+print(json.dumps({"h2d_ms": timed(h2d), "d2h_ms": timed(d2h), "both_ms": timed(both),
+                  "h2d_MB": (mixed.numel() + frames.numel()) * 4 / 1e6, "d2h_MB": 2 * sep.numel() * 4 / 1e6}), flush=True)
+for chunk, lanes in [(64, 1), (64, 2), (64, 3), (48, 2), (32, 2), (32, 3), (96, 2), (128, 2), (256, 1)]:
+    eng.set_option("host_chunk", chunk); eng.set_option("host_lanes", lanes)
+    for _ in range(3): eng.forward_host(mixed, frames, sep, masks)
+    ms = timed(lambda: eng.forward_host(mixed, frames, sep, masks), 20)
+    print(json.dumps({"chunk": chunk, "lanes": lanes, "ms": round(ms, 3), "utt_s_per_s": round(B / ms * 1e3)}), flush=True)
