@@ -7,13 +7,17 @@
 // The 4d hidden activation never leaves the SM.
 //
 // One CTA per 128-row tile (persistent over tiles), 576 threads:
-//   warp 0 / lane 0 : TMA producer - A tile (4 k-slabs, loaded once per tile) and a 7-slot ring of 16 KB weight slabs
+//   warp 0 / lane 0 : TMA producer - A tile (4 k-slabs, loaded once per tile) and an 8-slot ring of 16 KB weight slabs
 //   warp 1 / lane 0 : MMA issuer   - per hidden chunk j (128 columns):
 //                        GEMM1_j : acc1[j&1] (TMEM, 128 cols)  = A (K=256) x W1[j]            (4 k-slabs, N=128)
-//                        GEMM2_j : acc2 (TMEM, 256 cols)      += H (K=128) x W2[:, j]         (2 k-slabs x 2 halves)
+//                        GEMM2_j : acc2 (TMEM, 256 cols)      += H_j (K=128, A operand read from TMEM) x W2[:, j]
+//                                                                                             (2 k-slabs, N=256)
 //                     software-pipelined (G1_0, G1_1, G2_0, G1_2, G2_1, ...) so the tensor pipe stays busy while
 //                     the epilogue warps convert chunk j
-//   warps 2..17     : epilogue-1  - tcgen05.ld acc1 -> +b1 -> ReLU / erf-GELU -> bf16 -> swizzled K-major smem (H),
+//   warps 2..17     : epilogue-1  - tcgen05.ld acc1 -> +b1 -> ReLU / erf-GELU -> bf16 pairs -> tcgen05.st back into
+//                                   the first 64 columns of the same accumulator stage (H never touches shared
+//                                   memory: the kernel is bound by shared-memory bandwidth - UMMA operand reads plus
+//                                   TMA fills - so GEMM2 reads only its weights from smem),
 //                     epilogue-2  - acc2 + b2 + residual (TMA slab) -> x' (TMA store) -> LayerNorm -> bf16 (TMA store)
 #include "common.cuh"
 #include "kernels.h"
@@ -26,10 +30,9 @@ namespace {
 
 constexpr int D = 256, HID = 1024, CHUNK = 128, NCHUNK = HID / CHUNK;
 constexpr int SLAB = 128 * 128;                       // 128 rows x 128 B
-constexpr int WSLOTS = 7;
+constexpr int WSLOTS = 8;                             // even: the two 128-row halves of a W2 k-slab sit in adjacent slots
 constexpr int OFF_A = 0;                              // 4 slabs  (A tile, K = 256)
-constexpr int OFF_H = OFF_A + 4 * SLAB;               // 2 slabs (hidden chunk, one per 64-column k-slab, each with its own barriers)
-constexpr int OFF_W = OFF_H + 2 * SLAB;               // 7 slabs (weight ring)
+constexpr int OFF_W = OFF_A + 4 * SLAB;               // 8 slabs (weight ring)
 constexpr int OFF_BAR = OFF_W + WSLOTS * SLAB;        // barriers
 constexpr int OFF_RED = OFF_BAR + 256;                // LN partial statistics [128 rows][4 parts] float2
 constexpr int OFF_VEC = OFF_RED + 128 * 4 * 8;        // b1 [1024], b2 [256], gamma [256], beta [256]
@@ -67,10 +70,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* w_full = bars + 2;             // [5]
   uint64_t* w_empty = w_full + WSLOTS;     // [5]
   uint64_t* acc1_full = w_empty + WSLOTS;  // [2]
-  uint64_t* acc1_empty = acc1_full + 2;    // [2] (16 warp arrivals)
-  uint64_t* h_full = acc1_empty + 2;       // [2] one per H k-slab (8 warp arrivals: the two column parts that write it)
-  uint64_t* h_empty = h_full + 2;          // [2] GEMM2 MMAs that read the k-slab have completed
-  uint64_t* acc2_full = h_empty + 2;       // 1
+  uint64_t* h_full = acc1_full + 2;        // [2] H_j written into accumulator stage j&1 (16 warp arrivals); the stage is
+                                           //     reused by GEMM1_{j+2}, which the in-order tensor pipe runs after GEMM2_j
+  uint64_t* acc2_full = h_full + 2;        // 1
   uint64_t* acc2_empty = acc2_full + 1;    // 1 (16 warp arrivals)
   uint64_t* resid_bar = acc2_empty + 1;    // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 4);
@@ -96,8 +98,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(a_empty, 1);
     for (int i = 0; i < WSLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 16);
-      mbar_init(&h_full[i], 8); mbar_init(&h_empty[i], 1);
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&h_full[i], 16);
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
@@ -141,6 +143,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = umma_idesc(1u, 128, 128);
+      const uint32_t idesc2 = umma_idesc(1u, 128, 256);
       uint32_t wn = 0;
       uint32_t c1n = 0;      // GEMM1 chunks issued so far (acc1 stage = c1n & 1)
       uint32_t c2n = 0;      // GEMM2 chunks issued so far (H buffer = c2n & 1)
@@ -160,9 +163,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
             // GEMM1_j -> acc1[c1n & 1]
-            const uint32_t st = c1n & 1, use = c1n >> 1;
-            mbar_wait(&acc1_empty[st], (use & 1) ^ 1);
-            tc_fence_after();
+            const uint32_t st = c1n & 1;
             const uint32_t d_tmem = tm_acc1 + st * CHUNK;
             for (int k = 0; k < 4; ++k) {
               const uint32_t slot = next_w();
@@ -178,20 +179,20 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ++c1n;
           }
           if (j >= 1) {
-            // GEMM2_{j-1}: acc2 += H x W2 chunk; each H k-slab is released as soon as its MMAs are issued
+            // GEMM2_{j-1}: acc2 += H x W2 chunk, H read from TMEM (accumulator stage of chunk j-1)
+            const uint32_t st2 = c2n & 1;
+            mbar_wait(&h_full[st2], (c2n >> 1) & 1);
+            tc_fence_after();
             for (int k = 0; k < 2; ++k) {
-              mbar_wait(&h_full[k], c2n & 1);
-              tc_fence_after();
-              const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_H + k * SLAB), 1024);
-              for (int hf = 0; hf < 2; ++hf) {
-                const uint32_t slot = next_w();
-                const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_W + slot * SLAB), 1024);
+              const uint32_t slot0 = next_w();
+              const uint32_t slot1 = next_w();            // rows 128..255: the adjacent slot (slot0 is even)
+              const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_W + slot0 * SLAB), 1024);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_f16(tm_acc2 + hf * 128, adesc + 2 * kk, bdesc + 2 * kk, idesc, ((j - 1) | k | kk) != 0 ? 1u : 0u);
-                umma_commit(&w_empty[slot]);
-              }
-              umma_commit(&h_empty[k]);
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ts(tm_acc2, tm_acc1 + st2 * CHUNK + (k * 4 + kk) * 8, bdesc + 2 * kk, idesc2,
+                            ((j - 1) | k | kk) != 0 ? 1u : 0u);
+              umma_commit(&w_empty[slot0]);
+              umma_commit(&w_empty[slot1]);
             }
             FTRACE(8 + 4 * (j - 1) + 1);                     // GEMM2_{j-1} issued
             ++c2n;
@@ -237,26 +238,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) h[i] = gelu_erf(h[i]);
         }
-        // accumulator stage drained
+        // bf16 pairs back into the same accumulator stage: columns [16*part, +16) of the stage hold this warp's 32
+        // hidden columns.  They alias fp32 columns other parts are still reading, hence the quarter-wide barrier.
+        uint32_t hp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hp[i] = pack_bf16x2(h[2 * i], h[2 * i + 1]);
+        tc_fence_before();
+        named_bar_sync(10 + q, 128);
+        tc_fence_after();
+        tmem_st_32x32b_x16(tm_acc1 + st * CHUNK + (static_cast<uint32_t>(q * 32) << 16) + part * 16, hp);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc1_empty[st]);
-        // H k-slab (part >> 1): wait until GEMM2 of the previous chunk has consumed it
-        mbar_wait(&h_empty[part >> 1], (c1n & 1) ^ 1);
-        // this warp's 32 columns = half of the 64-column k-slab (part >> 1), chunk slots (part & 1) * 4 ..
-        uint8_t* hs = smem + OFF_H + (part >> 1) * SLAB;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16x2(h[8 * c], h[8 * c + 1]);
-          u.y = pack_bf16x2(h[8 * c + 2], h[8 * c + 3]);
-          u.z = pack_bf16x2(h[8 * c + 4], h[8 * c + 5]);
-          u.w = pack_bf16x2(h[8 * c + 6], h[8 * c + 7]);
-          *reinterpret_cast<uint4*>(hs + soff(r, (part & 1) * 4 + c)) = u;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&h_full[part >> 1]);
+        if (lane == 0) mbar_arrive(&h_full[st]);
         if (threadIdx.x == 64) FTRACE(8 + 4 * j + 3);        // H_j published
       }
       // ---- epilogue-2: acc2 + b2 + residual -> x' ; LayerNorm -> operand ----

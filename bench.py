@@ -223,6 +223,25 @@ def run_reference(args, rank, world):
     }))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads (and therefore its first-touch pinned host buffers) to the CPU cores local to its GPU,
+    so that the e2e host<->device copies of 8 ranks do not all cross one socket.  Returns the core count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {w * 64 + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:                                   # affinity is an optimisation, never a requirement
+        sys.stderr.write(f"bench.py: NUMA binding skipped ({e})\n")
+    return None
+
+
 def run_ours(args, rank, local_rank, world):
     # Everything except the final JSON line goes to stderr (NCCL / torchrun print to stdout on their own).
     real_stdout = os.dup(1)
@@ -235,6 +254,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cores = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -365,7 +385,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(B), "global_batch": world * B, "parallelism": f"batch-sharded x{world}",
+        "config": {"workload": workload_name(B), "global_batch": world * B, "parallelism": f"batch-sharded x{world}", "rank_cpu_affinity_cores": numa_cores,
                    "l2": f"{n_sets} rotating input sets; per-step footprint (inputs+outputs+activations) > 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
