@@ -4,9 +4,11 @@
 //   for each pair of frames:
 //     conv1 (K = 9 taps, tensor cores via mma.sync, 3 % of the FLOPs)        -> act1 (bf16, smem, 16x16x32 / frame)
 //     conv2 as an implicit GEMM  M = 128 (2 frames x 64 px), N = 64, K = 9x32:
-//       im2col slabs [128 rows x 128 B] (two taps each) are gathered from act1 into a 2-slot ring in the canonical
-//       K-major 128B-swizzle layout, tcgen05.mma accumulates all 18 k-steps in TMEM; the ring lets the gather of
-//       slab j+1 overlap the MMAs of slab j.  Epilogue: tcgen05.ld -> bias(BN-folded)+ReLU -> act2 (bf16, smem)
+//       im2col slabs [128 rows x 64 k] (two taps each) are gathered from act1 straight into TENSOR MEMORY (an 8-slot
+//       ring of 32 columns: thread = row, tcgen05.st) and fed to tcgen05.mma as the A operand from TMEM, so the slab
+//       costs no shared-memory store and no shared-memory operand read (the kernel was bound by shared-memory
+//       bandwidth and by the build -> MMA -> free round trip of a 2-slot smem ring); all 18 k-steps accumulate in
+//       TMEM.  Epilogue: tcgen05.ld -> bias(BN-folded)+ReLU -> act2 (bf16, smem)
 //   conv3 as an implicit GEMM  M = 128 (8 frames x 16 px), N = 128, K = 9x64: one slab per tap gathered from act2,
 //       the matching 16 KB weight slab streamed by TMA (3-slot ring, L2-resident), 36 tcgen05.mma k-steps;
 //       epilogue: tcgen05.ld -> bias+ReLU -> 16-pixel mean by warp shuffles -> pooled (M,128) bf16.
@@ -23,19 +25,20 @@ namespace avsep {
 namespace {
 
 constexpr int TC_BUILDERS = 256;          // 8 warps: gather im2col slabs, conv1, epilogues
-constexpr int TC_THREADS = TC_BUILDERS + 32;   // + 1 MMA-issuer warp
+constexpr int TC_THREADS = TC_BUILDERS + 64;   // + 1 MMA-issuer warp + 1 TMA-producer warp (conv3 weights)
+constexpr int W3S = 4;                    // conv3 weight ring slots
 constexpr int GROUP = 8;                 // frames per conv3 tile
 constexpr int SLAB_BYTES = 128 * 128;    // 128 rows x 128 B
 constexpr int W2_SLABS = 5, W2_SLAB_BYTES = 64 * 128;
 // shared memory map (bytes, all tensor-core regions 1024-aligned)
-constexpr int OFF_RING = 0;                               // 2 x 16 KB  im2col ring (A operand)
-constexpr int OFF_W3 = OFF_RING + 2 * SLAB_BYTES;         // 3 x 16 KB  conv3 weight slabs (TMA)
-constexpr int OFF_W2 = OFF_W3 + 3 * SLAB_BYTES;           // 5 x 8 KB   conv2 weight slabs (resident)
+constexpr int NSLOT = 8;                                  // im2col ring slots in tensor memory (32 columns each)
+constexpr int OFF_W3 = 0;                                 // W3S x 16 KB  conv3 weight slabs (TMA)
+constexpr int OFF_W2 = OFF_W3 + W3S * SLAB_BYTES;         // 5 x 8 KB   conv2 weight slabs (resident)
 constexpr int OFF_ACT2 = OFF_W2 + W2_SLABS * W2_SLAB_BYTES;   // 8 frames x 64 px x 128 B
 constexpr int OFF_ACT1 = OFF_ACT2 + GROUP * 64 * 128;     // 2 frames x 256 px x 64 B
 constexpr int OFF_IN = OFF_ACT1 + 2 * 256 * 64;           // 2 frames x 34 x 34 fp32
 constexpr int OFF_MISC = OFF_IN + 2 * 34 * 34 * 4;        // barriers, TMEM slot
-constexpr int TC_SMEM = OFF_MISC + 128 + 1024;            // + alignment slack (<= 227 KB)
+constexpr int TC_SMEM = OFF_MISC + 256 + 1024;            // + alignment slack (<= 227 KB)
 static_assert(TC_SMEM <= 227 * 1024, "visual_cnn_tc: shared memory budget exceeded");
 
 struct CnnTcDev {
@@ -81,17 +84,17 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   extern __shared__ __align__(1024) uint8_t smem_raw_cnn[];
   uint8_t* const smem = smem_raw_cnn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* ring = smem + OFF_RING;
   uint8_t* w3s = smem + OFF_W3;
   uint8_t* w2s = smem + OFF_W2;
   uint8_t* act2 = smem + OFF_ACT2;
   uint8_t* act1 = smem + OFF_ACT1;
   float* sIn = reinterpret_cast<float*>(smem + OFF_IN);
-  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [2] slab written by all 8 builder warps
-  uint64_t* ring_free = ring_full + 2;                             // [2] MMAs that read the slab have completed
-  uint64_t* bar_acc = ring_free + 2;                               // accumulator complete
-  uint64_t* bar_w3 = bar_acc + 1;                                  // [3] W3 slab landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w3 + 3);
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [NSLOT] slab written by all 8 builder warps
+  uint64_t* ring_free = ring_full + NSLOT;                         // [NSLOT] MMAs that read the slab have completed
+  uint64_t* bar_acc = ring_free + NSLOT;                           // accumulator complete
+  uint64_t* bar_w3 = bar_acc + 1;                                  // [W3S] W3 slab landed
+  uint64_t* w3_free = bar_w3 + W3S;                                // [W3S] the MMAs that read the slab have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w3_free + W3S);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -100,15 +103,15 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   for (int i = tid; i < 2 * 34 * 34; i += TC_THREADS) sIn[i] = 0.f;
   if (tid == 0) {
     tma_prefetch_desc(&tmW3);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&ring_full[i], TC_BUILDERS / 32);
       mbar_init(&ring_free[i], 1);
     }
     mbar_init(bar_acc, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(&bar_w3[i], 1);
+    for (int i = 0; i < W3S; ++i) { mbar_init(&bar_w3[i], 1); mbar_init(&w3_free[i], 1); }
     fence_mbar_init();
   }
-  if (warp == TC_BUILDERS / 32) tmem_alloc(tmem_slot, 256);
+  if (warp == TC_BUILDERS / 32) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();     // W2 slabs were written with generic stores, read by the tensor core
   tc_fence_before();
   __syncthreads();
@@ -116,6 +119,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc2 = tmem_base;          // 64 columns
   const uint32_t tmem_acc3 = tmem_base + 64;     // 128 columns
+  const uint32_t tmem_ring = tmem_base + 256;    // NSLOT x 32 columns: A operand slabs (128 rows x 64 bf16)
 
   if (warp == TC_BUILDERS / 32) {
     // =========================== MMA issuer (one lane) ===========================
@@ -126,30 +130,44 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
         for (int pair = 0; pair < GROUP / 2; ++pair) {
           for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
-            const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+            const uint32_t slot = n_slab % NSLOT, use = n_slab / NSLOT;
             mbar_wait(&ring_full[slot], use & 1);
             tc_fence_after();
-            const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
+            const uint32_t a_t = tmem_ring + slot * 32;
             const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w2s + j * W2_SLAB_BYTES), 1024);
             const int ksteps = (j == W2_SLABS - 1) ? 2 : 4;     // the last slab holds tap 8 only
             for (int k = 0; k < ksteps; ++k)
-              umma_f16(tmem_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
+              umma_f16_ts(tmem_acc2, a_t + 8 * k, bdesc + 2 * k, idesc2, (j | k) != 0 ? 1u : 0u);
             umma_commit(&ring_free[slot]);
             if (j == W2_SLABS - 1) umma_commit(bar_acc);
           }
         }
         for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
-          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          const uint32_t slot = n_slab % NSLOT, use = n_slab / NSLOT;
           mbar_wait(&ring_full[slot], use & 1);
-          const uint32_t ws = n_w3 % 3;
-          mbar_wait(&bar_w3[ws], (n_w3 / 3) & 1);
+          const uint32_t ws = n_w3 % W3S;
+          mbar_wait(&bar_w3[ws], (n_w3 / W3S) & 1);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(ring + slot * SLAB_BYTES), 1024);
+          const uint32_t a_t = tmem_ring + slot * 32;
           const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_acc3, adesc + 2 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_ts(tmem_acc3, a_t + 8 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
           umma_commit(&ring_free[slot]);
+          umma_commit(&w3_free[ws]);
           if (t == 8) umma_commit(bar_acc);
+        }
+      }
+    }
+  } else if (warp == TC_BUILDERS / 32 + 1) {
+    // =========================== TMA producer: conv3 weight slabs (one lane) ===========================
+    if (lane == 0) {
+      uint32_t n = 0;
+      for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+        for (int t = 0; t < 9; ++t, ++n) {
+          const uint32_t ws = n % W3S, use = n / W3S;
+          if (use > 0) mbar_wait(&w3_free[ws], (use - 1) & 1);
+          mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
+          tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, t * 128);
         }
       }
     }
@@ -158,42 +176,38 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     const int gid = lane >> 2, tig = lane & 3;
     uint32_t n_slab = 0;      // slabs pushed through the ring so far
     uint32_t acc_phase = 0;
-    uint32_t n_w3 = 0;        // W3 slabs requested so far (this thread mirrors the issuer's count)
 
-    // ---- per-thread gather/scatter constants: thread handles chunk c of rows rb, rb+32, rb+64, rb+96 of every slab
-    const int c = tid & 7, rb = tid >> 3;
-    const uint32_t dst0 = static_cast<uint32_t>(rb * 128 + ((c ^ (rb & 7)) << 4));   // + i*4096
-    // conv2 (rows = (f, y2, x2) of a pair): x2 = rb&7, y2 = (rb>>3) + 4*(i&1), f = i>>1; source act1 (swizzled lines)
-    const int cc2 = c & 3, taphalf = c >> 2;
-    int xo2[3], rowbase2[4];
-    bool vx2[3], top2[4];
+    // ---- per-thread gather constants: thread = row (TMEM lane) brow of every slab, column half bhh (32 of the
+    //      slab's 64 k-values = 64 contiguous bytes of one source pixel)
+    const int bq = warp & 3, bhh = warp >> 2;
+    const int brow = bq * 32 + lane;
+    const uint32_t ring_lane = tmem_ring + (static_cast<uint32_t>(bq * 32) << 16) + bhh * 16;   // + slot * 32
+    // conv2 (row = (f, y2, x2) of a pair, k half = tap 2j + bhh, 32 channels): source act1 (2 pixels per swizzled line)
+    int xo2[3], s02[3];
+    bool vx2[3];
+    const int y2 = (brow >> 3) & 7, f2 = brow >> 6;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int xx = 2 * (rb & 7) + kx - 1;
+      const int xx = 2 * (brow & 7) + kx - 1;
       vx2[kx] = xx >= 0 && xx < 16;
-      xo2[kx] = (xx >> 1) * 128 + (((((xx & 1) << 2) | cc2) ^ ((xx >> 1) & 7)) << 4);
+      xo2[kx] = (xx >> 1) * 128;
+      s02[kx] = (((xx & 1) << 2) ^ ((xx >> 1) & 7));          // chunk slot of channel chunk c is s02 ^ c
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int y2 = (rb >> 3) + 4 * (i & 1), f = i >> 1;
-      rowbase2[i] = (f * 256 + (2 * y2 - 1) * 16) * 64;     // + ky*1024 + xo2[kx]
-      top2[i] = (y2 == 0);                                   // tap row ky = 0 falls above the frame
-    }
-    // conv3 (rows = (g, y3, x3) of the group): x3 = rb&3, y3 = (rb>>2)&3, g = (rb>>4) + 2*i; source act2
-    int xo3[3], rowbase3[4];
+    const int rowbase2 = (f2 * 256 + (2 * y2 - 1) * 16) * 64;   // + ky*1024 + xo2[kx] + ((s02[kx] ^ c) << 4)
+    const bool top2 = (y2 == 0);                                // tap row ky = 0 falls above the frame
+    // conv3 (row = (g, y3, x3) of the group, k half = channels 32*bhh ..): source act2 (one pixel per swizzled line)
+    int xo3[3], s03[3];
     bool vx3[3];
-    const bool top3 = ((rb >> 2) & 3) == 0;
+    const int y3 = (brow >> 2) & 3;
+    const bool top3 = (y3 == 0);
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int xx = 2 * (rb & 3) + kx - 1;
+      const int xx = 2 * (brow & 3) + kx - 1;
       vx3[kx] = xx >= 0 && xx < 8;
-      xo3[kx] = xx * 128 + ((c ^ (xx & 7)) << 4);
+      xo3[kx] = xx * 128;
+      s03[kx] = xx & 7;                                         // chunk slot of chunk c is c ^ s03
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int g = (rb >> 4) + 2 * i, y3 = (rb >> 2) & 3;
-      rowbase3[i] = (g * 64 + (2 * y3 - 1) * 8) * 128;      // + ky*1024 + xo3[kx]
-    }
+    const int rowbase3 = ((brow >> 4) * 64 + (2 * y3 - 1) * 8) * 128;   // + ky*1024 + xo3[kx] + ((c ^ s03[kx]) << 4)
 
     // conv1 B fragments and bias (constant, registers)
     uint32_t bw1[4][2];
@@ -222,9 +236,11 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       }
     };
     // hand a finished slab to the MMA issuer
-    auto publish_slab = [&](uint32_t slot) {
-      fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
-      tc_fence_before();            // earlier tcgen05.ld of this thread are ordered before the MMAs this unblocks
+    // write this thread's 16 columns of slab `slot` and hand the slab to the MMA issuer
+    auto publish_slab = [&](uint32_t slot, const uint32_t (&cols)[16]) {
+      tmem_st_32x32b_x16(ring_lane + slot * 32, cols);
+      tmem_st_wait();
+      tc_fence_before();            // the stores (and earlier tcgen05.ld) are ordered before the MMAs this unblocks
       __syncwarp();
       if (lane == 0) mbar_arrive(&ring_full[slot]);
     };
@@ -258,15 +274,6 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
       const int frame0 = grp * GROUP;
       CTRACE(0);
-      // prefetch the first W3 slabs of this group (slots are free: all MMAs of the previous group have completed)
-      if (tid == 0) {
-        for (int t = 0; t < 3; ++t) {
-          const uint32_t slot = (n_w3 + t) % 3;
-          mbar_arrive_expect_tx(&bar_w3[slot], SLAB_BYTES);
-          tma_load_2d(w3s + slot * SLAB_BYTES, &tmW3, &bar_w3[slot], 0, t * 128);
-        }
-      }
-
       for (int pair = 0; pair < GROUP / 2; ++pair) {
         // ---- stage 2 input frames (interior of the zero-bordered 34x34 tiles) from the prefetch registers ----
 #pragma unroll
@@ -318,20 +325,22 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
 
         // ---- conv2: 5 slabs of two taps, gathered from act1 ----
         for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
-          const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+          const uint32_t slot = n_slab % NSLOT, use = n_slab / NSLOT;
           if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
-          uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
-          const int tap = 2 * j + taphalf;
+          const int tap = 2 * j + bhh;
           const int ky = (tap * 11) >> 5, kx = tap - 3 * ky;                 // tap / 3, tap % 3 for tap < 16
-          const bool okx = (tap < 9) && (kx == 0 ? vx2[0] : (kx == 1 ? vx2[1] : vx2[2]));
-          const int srcx = ky * 1024 + (kx == 0 ? xo2[0] : (kx == 1 ? xo2[1] : xo2[2]));
+          const bool ok = (tap < 9) && (kx == 0 ? vx2[0] : (kx == 1 ? vx2[1] : vx2[2])) && !(ky == 0 && top2);
+          const int src = rowbase2 + ky * 1024 + (kx == 0 ? xo2[0] : (kx == 1 ? xo2[1] : xo2[2]));
+          const int s0 = kx == 0 ? s02[0] : (kx == 1 ? s02[1] : s02[2]);
+          uint32_t cols[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int cch = 0; cch < 4; ++cch) {
             uint4 val = make_uint4(0, 0, 0, 0);
-            if (okx && !(ky == 0 && top2[i])) val = *reinterpret_cast<const uint4*>(act1 + rowbase2[i] + srcx);
-            *reinterpret_cast<uint4*>(dst + i * 4096) = val;
+            if (ok) val = *reinterpret_cast<const uint4*>(act1 + src + ((s0 ^ cch) << 4));
+            cols[4 * cch] = val.x; cols[4 * cch + 1] = val.y; cols[4 * cch + 2] = val.z; cols[4 * cch + 3] = val.w;
           }
-          publish_slab(slot);
+          tc_fence_after();
+          publish_slab(slot, cols);
         }
         CTRACE(4 + pair * 5);          // conv2 slabs built
       }
@@ -339,26 +348,22 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       CTRACE(21);                      // last conv2 epilogue done
 
       // ---- conv3: one slab per tap gathered from act2; weights streamed by TMA ----
-      for (int t = 0; t < 9; ++t, ++n_slab, ++n_w3) {
-        const uint32_t slot = n_slab & 1, use = n_slab >> 1;
+      for (int t = 0; t < 9; ++t, ++n_slab) {
+        const uint32_t slot = n_slab % NSLOT, use = n_slab / NSLOT;
         if (use > 0) mbar_wait(&ring_free[slot], (use - 1) & 1);
-        // the MMAs of tap t-2 have completed -> its W3 slot is free: refill it with tap t+1's slab (t+1 >= 3)
-        if (tid == 0 && t >= 2 && t + 1 < 9) {
-          const uint32_t ws = (n_w3 + 1) % 3;
-          mbar_arrive_expect_tx(&bar_w3[ws], SLAB_BYTES);
-          tma_load_2d(w3s + ws * SLAB_BYTES, &tmW3, &bar_w3[ws], 0, (t + 1) * 128);
-        }
-        uint8_t* dst = ring + slot * SLAB_BYTES + dst0;
         const int ky = (t * 11) >> 5, kx = t - 3 * ky;
-        const bool okx = (kx == 0 ? vx3[0] : (kx == 1 ? vx3[1] : vx3[2])) && !(ky == 0 && top3);
-        const int srcx = ky * 1024 + (kx == 0 ? xo3[0] : (kx == 1 ? xo3[1] : xo3[2]));
+        const bool ok = (kx == 0 ? vx3[0] : (kx == 1 ? vx3[1] : vx3[2])) && !(ky == 0 && top3);
+        const int src = rowbase3 + ky * 1024 + (kx == 0 ? xo3[0] : (kx == 1 ? xo3[1] : xo3[2]));
+        const int s0 = kx == 0 ? s03[0] : (kx == 1 ? s03[1] : s03[2]);
+        uint32_t cols[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int cch = 0; cch < 4; ++cch) {
           uint4 val = make_uint4(0, 0, 0, 0);
-          if (okx) val = *reinterpret_cast<const uint4*>(act2 + rowbase3[i] + srcx);
-          *reinterpret_cast<uint4*>(dst + i * 4096) = val;
+          if (ok) val = *reinterpret_cast<const uint4*>(act2 + src + (((4 * bhh + cch) ^ s0) << 4));
+          cols[4 * cch] = val.x; cols[4 * cch + 1] = val.y; cols[4 * cch + 2] = val.z; cols[4 * cch + 3] = val.w;
         }
-        publish_slab(slot);
+        tc_fence_after();
+        publish_slab(slot, cols);
       }
       CTRACE(22);                      // conv3 slabs built
       // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
@@ -427,7 +432,7 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   __syncthreads();
   if (warp == TC_BUILDERS / 32) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
