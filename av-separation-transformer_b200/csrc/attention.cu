@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   __nv_bfloat16* sKl = sQl + QT * LDS;
   __nv_bfloat16* sVl = sKl + KT * LDS;
 
+  griddep_launch_dependents();
+  griddep_wait();
   const int q0 = blockIdx.x * QT;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -353,8 +355,11 @@ const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
     attr_done = true;
   }
   dim3 grid((Lq + QT - 1) / QT, H, B);
-  kern<<<grid, 128, SMEM, s>>>(d);
-  return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
+  if (launch_pdl(kern, grid, dim3(128), SMEM, s, d) != cudaSuccess) {
+    cudaGetLastError();
+    return "attention: launch failed";
+  }
+  return nullptr;
 }
 
 }  // namespace

@@ -97,6 +97,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -293,6 +295,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // out[b*L + t, :] = lerp of two fp32 source rows (ATen upsample_linear1d, align_corners=False; model.py:114-116)
 __global__ void lerp_rows_kernel(const float* __restrict__ src, int ld_src, int nsrc, int L, int chunks, float scale,
                                  __nv_bfloat16* __restrict__ dst, int ld_dst, long long total) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = static_cast<int>(i % chunks);
@@ -362,8 +366,11 @@ const char* launch_attention_tc(cudaStream_t s, const AttnProblem& p) {
   d.Lq = p.Lq; d.Lk = p.Lk;
   d.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid((p.Lq + QT - 1) / QT, p.H, p.B);
-  attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(tq, tk, tv, to, d);
-  return cudaGetLastError() == cudaSuccess ? nullptr : "attention_tc: launch failed";
+  if (launch_pdl(attention_tc_kernel, grid, dim3(NTHREADS), SMEM_BYTES, s, tq, tk, tv, to, d) != cudaSuccess) {
+    cudaGetLastError();
+    return "attention_tc: launch failed";
+  }
+  return nullptr;
 }
 
 const char* launch_lerp_rows(cudaStream_t s, const float* src, int ld_src, int B, int nsrc, int L, int cols,
@@ -373,9 +380,8 @@ const char* launch_lerp_rows(cudaStream_t s, const float* src, int ld_src, int B
   const long long total = static_cast<long long>(B) * L * chunks;
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  lerp_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(
-      src, ld_src, nsrc, L, chunks, static_cast<float>(nsrc) / static_cast<float>(L),
-      reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst, total);
+  launch_pdl(lerp_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, s, src, ld_src, nsrc, L, chunks,
+             static_cast<float>(nsrc) / static_cast<float>(L), reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst, total);
   return cudaGetLastError() == cudaSuccess ? nullptr : "lerp_rows: launch failed";
 }
 

@@ -138,6 +138,7 @@ struct avsep_handle {
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> host_ev;
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
+  bool pdl = true;       // programmatic dependent launch between consecutive kernels of a stream
   int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
   void* host_ws = nullptr;
   size_t host_ws_bytes = 0;
@@ -1168,6 +1169,7 @@ int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, si
 int avsep_set_profile(avsep_handle* h, int32_t enable) {
   if (!h) return 1;
   h->profile = enable != 0;
+  pdl_set(h->pdl && !h->profile);   // per-launch event pairs measure kernels one at a time
   return 0;
 }
 
@@ -1279,6 +1281,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "host_lanes") == 0) { h->host_lanes = value; return 0; }
+  if (strcmp(name, "pdl") == 0) { h->pdl = value != 0; pdl_set(h->pdl && !h->profile); drop_graphs(h); return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }

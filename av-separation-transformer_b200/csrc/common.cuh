@@ -61,6 +61,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still running; everything before griddep_wait() (barrier init, TMEM alloc,
+// descriptor prefetch, constant loads) overlaps the predecessor's tail, nothing produced by it may be touched earlier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -6,6 +6,13 @@
 namespace avsep {
 
 namespace {
+bool g_pdl = true;
+}
+void pdl_set(bool on) { g_pdl = on; }
+bool pdl_enabled() { return g_pdl; }
+
+
+namespace {
 
 constexpr int LN_WARPS = 8;
 constexpr int LN_MAX_V4 = 8;   // float4 chunks cached per lane: d <= 8*32*4 = 1024
@@ -19,6 +26,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ x_out, void* __restrict__ out_op, int M,
                      int d) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -95,6 +104,8 @@ template <bool TF32>
 __global__ void __launch_bounds__(256)
 prep_audio_kernel(const float* __restrict__ mixed, void* __restrict__ xp, int F, int T, int Fp) {
   __shared__ float tile[32][33];
+  griddep_launch_dependents();
+  griddep_wait();
   const int b = blockIdx.z;
   const int f0 = blockIdx.y * 32;
   const int t0 = blockIdx.x * 32;
@@ -141,16 +152,16 @@ const char* launch_add_layernorm(cudaStream_t s, int prec, const float* x, const
   if (M <= 0) return "layernorm: empty";
   dim3 grid((M + LN_WARPS - 1) / LN_WARPS);
   if (prec == PREC_TF32)
-    add_layernorm_kernel<true><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, x_out, out_op, M, d);
+    launch_pdl(add_layernorm_kernel<true>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, y, gamma, beta, x_out, out_op, M, d);
   else
-    add_layernorm_kernel<false><<<grid, LN_WARPS * 32, 0, s>>>(x, y, gamma, beta, x_out, out_op, M, d);
+    launch_pdl(add_layernorm_kernel<false>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, y, gamma, beta, x_out, out_op, M, d);
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm: launch failed";
 }
 
 const char* launch_prep_audio(cudaStream_t s, int prec, const float* mixed, void* xp, int B, int F, int T, int Fp) {
   dim3 grid((T + 31) / 32, (Fp + 31) / 32, B);
-  if (prec == PREC_TF32) prep_audio_kernel<true><<<grid, 256, 0, s>>>(mixed, xp, F, T, Fp);
-  else prep_audio_kernel<false><<<grid, 256, 0, s>>>(mixed, xp, F, T, Fp);
+  if (prec == PREC_TF32) launch_pdl(prep_audio_kernel<true>, grid, dim3(256), 0, s, mixed, xp, F, T, Fp);
+  else launch_pdl(prep_audio_kernel<false>, grid, dim3(256), 0, s, mixed, xp, F, T, Fp);
   return cudaGetLastError() == cudaSuccess ? nullptr : "prep_audio: launch failed";
 }
 

@@ -113,6 +113,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_acc2 = tmem_base;            // columns [0,256)
   const uint32_t tm_acc1 = tmem_base + 256;      // two stages of 128 columns
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -433,8 +435,11 @@ const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, cons
   d.trace = trace;
   const int m_tiles = (M + 127) / 128;
   const int grid = m_tiles < num_sms ? m_tiles : num_sms;
-  ffn_fused_kernel<<<grid, FFN_THREADS, FFN_SMEM, s>>>(ta, tw1, tw2, tx, top, d);
-  return cudaGetLastError() == cudaSuccess ? nullptr : "ffn_fused: launch failed";
+  if (launch_pdl(ffn_fused_kernel, dim3(grid), dim3(FFN_THREADS), FFN_SMEM, s, ta, tw1, tw2, tx, top, d) != cudaSuccess) {
+    cudaGetLastError();
+    return "ffn_fused: launch failed";
+  }
+  return nullptr;
 }
 
 }  // namespace avsep

@@ -307,6 +307,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the setup above overlapped the previous kernel's tail; its results are needed from here on
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -851,8 +854,10 @@ const char* launch_cfg(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap&
   }
   const int tiles = ((d.M + BM - 1) / BM) * ((d.N + d.n_tile - 1) / d.n_tile);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, NUM_THREADS, SMEM_TOTAL, s>>>(ta, tw, top, tf32m, d);
-  if (cudaGetLastError() != cudaSuccess) return "gemm: kernel launch failed";
+  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), SMEM_TOTAL, s, ta, tw, top, tf32m, d) != cudaSuccess) {
+    cudaGetLastError();
+    return "gemm: kernel launch failed";
+  }
   return nullptr;
 }
 

@@ -7,6 +7,26 @@
 
 namespace avsep {
 
+// Programmatic dependent launch (PDL) of the forward-path kernels: every kernel launched through launch_pdl calls
+// griddep_wait() before it touches anything its predecessor wrote.  pdl_set(false) = plain stream order.
+void pdl_set(bool on);
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+
 enum Precision { PREC_BF16 = 0, PREC_TF32 = 1 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 // How accumulator row m of the GEMM maps to an output row.

@@ -120,6 +120,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   const uint32_t tmem_acc2 = tmem_base;          // 64 columns
   const uint32_t tmem_acc3 = tmem_base + 64;     // 128 columns
   const uint32_t tmem_ring = tmem_base + 256;    // NSLOT x 32 columns: A operand slabs (128 rows x 64 bf16)
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == TC_BUILDERS / 32) {
     // =========================== MMA issuer (one lane) ===========================
@@ -502,7 +504,7 @@ const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, con
   d.M = M; d.num_groups = (M + GROUP - 1) / GROUP;
   d.trace = trace;
   const int grid = d.num_groups < num_sms ? d.num_groups : num_sms;
-  visual_cnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(tm, d);
+  launch_pdl(visual_cnn_tc_kernel, dim3(grid), dim3(TC_THREADS), TC_SMEM, s, tm, d);
   return cudaGetLastError() == cudaSuccess ? nullptr : "visual_cnn_tc: launch failed";
 }
 
