@@ -31,7 +31,7 @@ constexpr int GROUP = 8;                 // frames per conv3 tile
 constexpr int SLAB_BYTES = 128 * 128;    // 128 rows x 128 B
 constexpr int W2_SLABS = 5, W2_SLAB_BYTES = 64 * 128;
 // shared memory map (bytes, all tensor-core regions 1024-aligned)
-constexpr int NSLOT = 8;                                  // im2col ring slots in tensor memory (32 columns each)
+constexpr int NSLOT = 6;                                  // im2col ring slots in tensor memory (32 columns each)
 constexpr int OFF_W3 = 0;                                 // W3S x 16 KB  conv3 weight slabs (TMA)
 constexpr int OFF_W2 = OFF_W3 + W3S * SLAB_BYTES;         // 5 x 8 KB   conv2 weight slabs (resident)
 constexpr int OFF_ACT2 = OFF_W2 + W2_SLABS * W2_SLAB_BYTES;   // 8 frames x 64 px x 128 B
@@ -92,7 +92,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   uint64_t* ring_full = reinterpret_cast<uint64_t*>(smem + OFF_MISC);   // [NSLOT] slab written by all 8 builder warps
   uint64_t* ring_free = ring_full + NSLOT;                         // [NSLOT] MMAs that read the slab have completed
   uint64_t* bar_acc = ring_free + NSLOT;                           // accumulator complete
-  uint64_t* bar_w3 = bar_acc + 1;                                  // [W3S] W3 slab landed
+  uint64_t* bar_acc3 = bar_acc + 1;                                // [2] conv3 accumulator (double-buffered) complete
+  uint64_t* bar_w3 = bar_acc3 + 2;                                 // [W3S] W3 slab landed
   uint64_t* w3_free = bar_w3 + W3S;                                // [W3S] the MMAs that read the slab have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w3_free + W3S);
 
@@ -108,6 +109,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       mbar_init(&ring_free[i], 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(&bar_acc3[0], 1);
+    mbar_init(&bar_acc3[1], 1);
     for (int i = 0; i < W3S; ++i) { mbar_init(&bar_w3[i], 1); mbar_init(&w3_free[i], 1); }
     fence_mbar_init();
   }
@@ -118,8 +121,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc2 = tmem_base;          // 64 columns
-  const uint32_t tmem_acc3 = tmem_base + 64;     // 128 columns
-  const uint32_t tmem_ring = tmem_base + 256;    // NSLOT x 32 columns: A operand slabs (128 rows x 64 bf16)
+  const uint32_t tmem_acc3 = tmem_base + 64;     // 2 x 128 columns: the conv3 epilogue of group g runs inside group g+1
+  const uint32_t tmem_ring = tmem_base + 320;    // NSLOT x 32 columns: A operand slabs (128 rows x 64 bf16)
   griddep_launch_dependents();
   griddep_wait();
 
@@ -128,8 +131,8 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
     if (lane == 0) {
       const uint32_t idesc2 = umma_idesc(1u, 128, 64);
       const uint32_t idesc3 = umma_idesc(1u, 128, 128);
-      uint32_t n_slab = 0, n_w3 = 0;
-      for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+      uint32_t n_slab = 0, n_w3 = 0, lt = 0;
+      for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x, ++lt) {
         for (int pair = 0; pair < GROUP / 2; ++pair) {
           for (int j = 0; j < W2_SLABS; ++j, ++n_slab) {
             const uint32_t slot = n_slab % NSLOT, use = n_slab / NSLOT;
@@ -153,10 +156,11 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
           const uint32_t a_t = tmem_ring + slot * 32;
           const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(w3s + ws * SLAB_BYTES), 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ts(tmem_acc3, a_t + 8 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ts(tmem_acc3 + (lt & 1) * 128, a_t + 8 * k, bdesc + 2 * k, idesc3, (t | k) != 0 ? 1u : 0u);
           umma_commit(&ring_free[slot]);
           umma_commit(&w3_free[ws]);
-          if (t == 8) umma_commit(bar_acc);
+          if (t == 8) umma_commit(&bar_acc3[lt & 1]);
         }
       }
     }
@@ -271,9 +275,71 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
       tc_fence_before();
       named_bar_sync(1, TC_BUILDERS);     // act2 rows of this pair visible; acc2 drained
     };
-    prefetch_pair(blockIdx.x * GROUP);
 
-    for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+    // conv3 epilogue of the CTA's g_lt-th group (frames g_frame0 ..): acc (8 frames x 16 px, 128 ch) -> bias + ReLU ->
+    // mean over 16 px -> pooled.  Deferred: it runs after conv1 of the next group's second pair, when the MMAs have
+    // long completed, instead of waiting for them at the end of the group.
+    auto conv3_epilogue = [&](uint32_t g_lt, int g_frame0) {
+      mbar_wait(&bar_acc3[g_lt & 1], (g_lt >> 1) & 1);
+      tc_fence_after();
+      {
+        const int q = warp & 3, hh = warp >> 2;                  // lane quarter (2 frames), 64-column half
+        const int fr = g_frame0 + q * 2 + (lane >> 4);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          const int col0 = hh * 64 + cc * 32;
+          tmem_ld_32x32b_x32(tmem_acc3 + (g_lt & 1) * 128 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
+          tmem_ld_wait();
+          // bias + ReLU, then sum the 16 pixel rows of each frame (lanes 0-15 / 16-31) with a transposing butterfly:
+          // every step halves the number of live columns per lane, 30 shuffles instead of 4 per column.
+          float x[32];
+#pragma unroll
+          for (int jx = 0; jx < 32; ++jx) x[jx] = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
+#pragma unroll
+          for (int jx = 0; jx < 16; ++jx) {            // lanes with bit3 clear keep columns 0-15, set keep 16-31
+            const bool up = (lane & 8) != 0;
+            const float send = up ? x[jx] : x[jx + 16];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+            x[jx] = (up ? x[jx + 16] : x[jx]) + recv;
+          }
+#pragma unroll
+          for (int jx = 0; jx < 8; ++jx) {
+            const bool up = (lane & 4) != 0;
+            const float send = up ? x[jx] : x[jx + 8];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            x[jx] = (up ? x[jx + 8] : x[jx]) + recv;
+          }
+#pragma unroll
+          for (int jx = 0; jx < 4; ++jx) {
+            const bool up = (lane & 2) != 0;
+            const float send = up ? x[jx] : x[jx + 4];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            x[jx] = (up ? x[jx + 4] : x[jx]) + recv;
+          }
+#pragma unroll
+          for (int jx = 0; jx < 2; ++jx) {
+            const bool up = (lane & 1) != 0;
+            const float send = up ? x[jx] : x[jx + 2];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            x[jx] = (up ? x[jx + 2] : x[jx]) + recv;
+          }
+          // lane l (within its 16-lane half) now holds the frame sums of columns cbase, cbase+1 with
+          // cbase = 16*bit3 + 8*bit2 + 4*bit1 + 2*bit0
+          if (fr < p.M) {
+            const int cbase = ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+            *reinterpret_cast<uint32_t*>(p.pooled + static_cast<size_t>(fr) * 128 + col0 + cbase) =
+                pack_bf16x2(x[0] * (1.f / 16.f), x[1] * (1.f / 16.f));
+          }
+        }
+      }
+      tc_fence_before();
+    };
+    prefetch_pair(blockIdx.x * GROUP);
+    uint32_t lt = 0;
+    int prev_frame0 = 0;
+
+    for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x, ++lt) {
       const int frame0 = grp * GROUP;
       CTRACE(0);
       for (int pair = 0; pair < GROUP / 2; ++pair) {
@@ -321,8 +387,10 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         named_bar_sync(1, TC_BUILDERS);
         CTRACE(2 + pair * 5);          // conv1 done
 
-        // deferred epilogue of the previous pair: its MMAs had the staging + conv1 above to complete
+        // deferred epilogues: the previous pair's conv2 (its MMAs had the staging + conv1 above to complete) and,
+        // in the second pair, the previous group's conv3
         if (pair > 0) conv2_epilogue(pair - 1);
+        if (pair == 1 && lt > 0) conv3_epilogue(lt - 1, prev_frame0);
         CTRACE(3 + pair * 5);          // deferred conv2 epilogue done
 
         // ---- conv2: 5 slabs of two taps, gathered from act1 ----
@@ -368,66 +436,11 @@ visual_cnn_tc_kernel(const __grid_constant__ CUtensorMap tmW3, const CnnTcDev p)
         publish_slab(slot, cols);
       }
       CTRACE(22);                      // conv3 slabs built
-      // ---- conv3 epilogue: acc (8 frames x 16 px, 128 ch) -> bias + ReLU -> mean over 16 px -> pooled ----
-      mbar_wait(bar_acc, acc_phase);
-      CTRACE(23);                      // conv3 accumulator ready
-      acc_phase ^= 1;
-      tc_fence_after();
-      {
-        const int q = warp & 3, hh = warp >> 2;                  // lane quarter (2 frames), 64-column half
-        const int fr = frame0 + q * 2 + (lane >> 4);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t v[32];
-          const int col0 = hh * 64 + cc * 32;
-          tmem_ld_32x32b_x32(tmem_acc3 + (static_cast<uint32_t>(q * 32) << 16) + col0, v);
-          tmem_ld_wait();
-          // bias + ReLU, then sum the 16 pixel rows of each frame (lanes 0-15 / 16-31) with a transposing butterfly:
-          // every step halves the number of live columns per lane, 30 shuffles instead of 4 per column.
-          float x[32];
-#pragma unroll
-          for (int jx = 0; jx < 32; ++jx) x[jx] = fmaxf(__uint_as_float(v[jx]) + __ldg(p.b3 + col0 + jx), 0.f);
-#pragma unroll
-          for (int jx = 0; jx < 16; ++jx) {            // lanes with bit3 clear keep columns 0-15, set keep 16-31
-            const bool up = (lane & 8) != 0;
-            const float send = up ? x[jx] : x[jx + 16];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-            x[jx] = (up ? x[jx + 16] : x[jx]) + recv;
-          }
-#pragma unroll
-          for (int jx = 0; jx < 8; ++jx) {
-            const bool up = (lane & 4) != 0;
-            const float send = up ? x[jx] : x[jx + 8];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-            x[jx] = (up ? x[jx + 8] : x[jx]) + recv;
-          }
-#pragma unroll
-          for (int jx = 0; jx < 4; ++jx) {
-            const bool up = (lane & 2) != 0;
-            const float send = up ? x[jx] : x[jx + 4];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-            x[jx] = (up ? x[jx + 4] : x[jx]) + recv;
-          }
-#pragma unroll
-          for (int jx = 0; jx < 2; ++jx) {
-            const bool up = (lane & 1) != 0;
-            const float send = up ? x[jx] : x[jx + 2];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            x[jx] = (up ? x[jx + 2] : x[jx]) + recv;
-          }
-          // lane l (within its 16-lane half) now holds the frame sums of columns cbase, cbase+1 with
-          // cbase = 16*bit3 + 8*bit2 + 4*bit1 + 2*bit0
-          if (fr < p.M) {
-            const int cbase = ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-            *reinterpret_cast<uint32_t*>(p.pooled + static_cast<size_t>(fr) * 128 + col0 + cbase) =
-                pack_bf16x2(x[0] * (1.f / 16.f), x[1] * (1.f / 16.f));
-          }
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(1, TC_BUILDERS);
+      CTRACE(23);
       CTRACE(24);                      // group done
+      prev_frame0 = frame0;
     }
+    if (lt > 0) conv3_epilogue(lt - 1, prev_frame0);
   }
 
   tc_fence_before();
