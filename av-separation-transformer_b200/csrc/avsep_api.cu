@@ -300,6 +300,8 @@ int linear(avsep_handle* h, cudaStream_t s, const char* label, const void* A, in
   p.taps = 1; p.tap_stride = 0; p.row_shift = 0;
   GemmEpilogue e;
   e.bias = bias; e.act = act;
+  // a GELU whose only consumer is a bf16 operand does not need the fp32-grade erf
+  if (act == ACT_GELU && h->cfg.precision == AVSEP_PREC_BF16 && out_f32 == nullptr) e.act = ACT_GELU_BF16;
   e.out_f32 = out_f32; e.ld_f32 = N;
   e.out_op = out_op; e.ld_op = N;
   CKL(label, launch_gemm(s, h->cfg.precision, p, e));

@@ -238,7 +238,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i], 0.f);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) h[i] = gelu_erf(h[i]);
+          for (int i = 0; i < 32; ++i) h[i] = gelu_bf16_grade(h[i]);   // H is rounded to bf16 next
         }
         // bf16 pairs back into the same accumulator stage: columns [16*part, +16) of the stage hold this warp's 32
         // hidden columns.  They alias fp32 columns other parts are still reading, hence the quarter-wide barrier.

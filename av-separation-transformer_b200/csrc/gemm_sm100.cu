@@ -225,6 +225,9 @@ __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo
   } else if (e.act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) val[j] = gelu_erf(val[j]);
+  } else if (e.act == ACT_GELU_BF16) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = gelu_bf16_grade(val[j]);
   }
   if (e.pe != nullptr && ri.valid) {
     const float* pr = e.pe + static_cast<size_t>(ri.pos) * N + col0;

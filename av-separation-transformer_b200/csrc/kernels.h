@@ -28,7 +28,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 
 enum Precision { PREC_BF16 = 0, PREC_TF32 = 1 };
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BF16 = 3 };   // 3: erf-GELU to bf16 accuracy (polynomial)
 // How accumulator row m of the GEMM maps to an output row.
 //   ROW_IDENT       out row = m
 //   ROW_PAD2PAD     rows live in a per-utterance padded space of Lp = L+2 rows (zero halo row on each side,
