@@ -34,7 +34,7 @@ constexpr int WSLOTS = 8;                             // even: the two 128-row h
 constexpr int OFF_A = 0;                              // 4 slabs  (A tile, K = 256)
 constexpr int OFF_W = OFF_A + 4 * SLAB;               // 8 slabs (weight ring)
 constexpr int OFF_BAR = OFF_W + WSLOTS * SLAB;        // barriers
-constexpr int OFF_RED = OFF_BAR + 256;                // LN partial statistics [128 rows][4 parts] float2
+constexpr int OFF_RED = OFF_BAR + 512;                // LN partial statistics [128 rows][4 parts] float2
 constexpr int OFF_VEC = OFF_RED + 128 * 4 * 8;        // b1 [1024], b2 [256], gamma [256], beta [256]
 constexpr int FFN_SMEM = OFF_VEC + (HID + 3 * D) * 4;
 static_assert(FFN_SMEM <= 227 * 1024, "ffn_fused: shared memory budget exceeded");
@@ -75,7 +75,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc2_full = h_full + 2;        // 1
   uint64_t* acc2_empty = acc2_full + 1;    // 1 (16 warp arrivals)
   uint64_t* resid_bar = acc2_empty + 1;    // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 4);
+  uint64_t* resid_bar2 = resid_bar + 4;    // [4] second residual chunk, prefetched into the idle weight ring (last tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar2 + 4);
   float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
   float* sb1 = reinterpret_cast<float*>(smem + OFF_VEC);
   float* sb2 = sb1 + HID;
@@ -103,7 +104,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
-    for (int i = 0; i < 4; ++i) mbar_init(&resid_bar[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&resid_bar[i], 1); mbar_init(&resid_bar2[i], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -261,10 +262,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (threadIdx.x == 64) FTRACE(2);                      // acc2 complete
       const bool row_ok = (m0 + r) < p.M;
       (void)row_ok;
+      // On the CTA's last tile the weight ring is idle (every slab has been consumed): the second residual chunk is
+      // fetched into ring slot `part` together with the first one instead of after the first chunk's x' store.
+      const bool last_tile = tile + static_cast<int>(gridDim.x) >= m_tiles;
+      uint8_t* const slab1_q = last_tile ? smem + OFF_W + part * SLAB + q * 4096 : slab_q;
       if (p.resid != nullptr && elected) {
         bulk_wait_read0();
         mbar_arrive_expect_tx(&resid_bar[part], SLAB);
         tma_load_2d(slab, &tmX, &resid_bar[part], part * 64, m0);
+        if (last_tile) {
+          mbar_arrive_expect_tx(&resid_bar2[part], SLAB);
+          tma_load_2d(smem + OFF_W + part * SLAB, &tmX, &resid_bar2[part], part * 64 + 32, m0);
+        }
       }
       float val[2][32];
       float sum = 0.f, sq = 0.f;
@@ -273,9 +282,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int c0 = part * 64 + ci * 32;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tm_acc2 + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        uint8_t* const sl_q = ci == 0 ? slab_q : slab1_q;
         if (p.resid != nullptr) {
-          mbar_wait(&resid_bar[part], rph);
-          rph ^= 1;
+          if (ci == 1 && last_tile) {
+            mbar_wait(&resid_bar2[part], 0);
+          } else {
+            mbar_wait(&resid_bar[part], rph);
+            rph ^= 1;
+          }
         }
         tmem_ld_wait();
 #pragma unroll
@@ -287,24 +301,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.resid != nullptr) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float4 x4 = *reinterpret_cast<const float4*>(slab_q + soff(lane, c));
+            const float4 x4 = *reinterpret_cast<const float4*>(sl_q + soff(lane, c));
             val[ci][4 * c] += x4.x; val[ci][4 * c + 1] += x4.y; val[ci][4 * c + 2] += x4.z; val[ci][4 * c + 3] += x4.w;
           }
         }
         if (p.has_xout) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(slab_q + soff(lane, c)) =
+            *reinterpret_cast<float4*>(sl_q + soff(lane, c)) =
                 make_float4(val[ci][4 * c], val[ci][4 * c + 1], val[ci][4 * c + 2], val[ci][4 * c + 3]);
           fence_proxy_async_smem();
         }
         if (p.has_xout || (p.resid != nullptr && ci == 0)) named_bar_sync(part_bar, 128);
         if (elected) {
           if (p.has_xout) {
-            tma_store_2d(&tmX, slab, c0, m0);
+            tma_store_2d(&tmX, sl_q - q * 4096, c0, m0);
             bulk_commit();
           }
-          if (ci == 0 && p.resid != nullptr) {
+          if (ci == 0 && p.resid != nullptr && !last_tile) {
             bulk_wait_read0();
             mbar_arrive_expect_tx(&resid_bar[part], SLAB);
             tma_load_2d(slab, &tmX, &resid_bar[part], c0 + 32, m0);
