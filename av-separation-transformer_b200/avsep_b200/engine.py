@@ -181,6 +181,25 @@ class Engine:
         self._check(rc, "avsep_forward_host")
         return sep, masks
 
+    def forward_host_async(self, mixed: torch.Tensor, frames: torch.Tensor, sep: torch.Tensor, masks: torch.Tensor,
+                           slot: int):
+        """Streaming form: enqueue one batch on I/O slot 0/1 and return; ``host_wait(slot)`` completes it.  All four
+        tensors must be contiguous float32 CPU tensors (pinned for real overlap) that outlive the wait."""
+        for t in (mixed, frames, sep, masks):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("forward_host_async: contiguous float32 CPU tensors required")
+        B, F, T = mixed.shape
+        _, N, Hh, Ww = frames.shape
+        if tuple(sep.shape) != (B, self.cfg.num_speakers, F, T) or sep.shape != masks.shape:
+            raise ValueError("forward_host_async: output buffers must be (B, S, F, T)")
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_forward_host_async(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
+                                                   sep.data_ptr(), masks.data_ptr(), int(slot), self._stream())
+        self._check(rc, "avsep_forward_host_async")
+
+    def host_wait(self, slot: int):
+        self._check(self.lib.avsep_host_wait(self.h, int(slot)), "avsep_host_wait")
+
     def launch_count(self) -> int:
         return int(self.lib.avsep_last_launch_count(self.h))
 

@@ -131,12 +131,18 @@ struct avsep_handle {
   void* own_ws = nullptr;
   size_t own_ws_bytes = 0;
   // host-path staging
-  float *io_mixed = nullptr, *io_frames = nullptr, *io_sep = nullptr, *io_masks = nullptr;
-  size_t io_cap[4] = {0, 0, 0, 0};
+  // host-buffer entry point: two independent I/O slots so that consecutive calls can overlap (copy-in of call i+1
+  // with the kernels and copy-out of call i); slot 0 serves the synchronous avsep_forward_host
+  struct HostSlot {
+    float* io[4] = {nullptr, nullptr, nullptr, nullptr};   // mixed, frames, separated, masks (device)
+    size_t cap[4] = {0, 0, 0, 0};
+    std::vector<cudaEvent_t> ev;                            // 2 per chunk: copy-in done, kernels done
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;       // ev_end: last copy-out done
+    cudaEvent_t ev_lane[3] = {nullptr, nullptr, nullptr};   // last kernels of this slot on each compute lane
+  } slot[2];
   float* synth_waves = nullptr;   // scratch of avsep_synth_batch
   size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
-  std::vector<cudaEvent_t> host_ev;
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
   bool pdl = true;       // programmatic dependent launch between consecutive kernels of a stream
   int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
@@ -660,16 +666,20 @@ void avsep_destroy(avsep_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->own_ws) cudaFree(h->own_ws);
-  if (h->io_mixed) cudaFree(h->io_mixed);
-  if (h->io_frames) cudaFree(h->io_frames);
-  if (h->io_sep) cudaFree(h->io_sep);
-  if (h->io_masks) cudaFree(h->io_masks);
+  for (auto& sl : h->slot) {
+    for (float* ptr : sl.io)
+      if (ptr) cudaFree(ptr);
+    for (cudaEvent_t e : sl.ev) cudaEventDestroy(e);
+    if (sl.ev_start) cudaEventDestroy(sl.ev_start);
+    if (sl.ev_end) cudaEventDestroy(sl.ev_end);
+    for (cudaEvent_t e : sl.ev_lane)
+      if (e) cudaEventDestroy(e);
+  }
   if (h->synth_waves) cudaFree(h->synth_waves);
   if (h->host_ws) cudaFree(h->host_ws);
   for (auto& kv : h->snaps)
     if (kv.second.first) cudaFree(kv.second.first);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-  for (cudaEvent_t e : h->host_ev) cudaEventDestroy(e);
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -931,31 +941,39 @@ int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_fra
                         lip_frames, separated, masks);
 }
 
-int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
-                       int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream) {
+namespace {
+int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int B, int T, int N, int Hh, int Ww,
+                float* separated, float* masks, int slot_id, cudaStream_t s) {
   // Software pipeline over chunks of the batch: H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 run
-  // concurrently on three streams (PCIe is full duplex), so the call costs ~max(copy-in, compute, copy-out).
-  if (!h) return 1;
+  // concurrently on separate streams (PCIe is full duplex), so a call costs ~max(copy-in, compute, copy-out); the
+  // two slots extend the same pipeline across consecutive calls.
   if (!mixed_spec || !lip_frames || !separated || !masks) return fail(h, "avsep_forward_host: null buffer");
+  if (slot_id < 0 || slot_id > 1) return fail(h, "avsep_forward_host_async: slot must be 0 or 1");
   if (check_shape(h, B, T, N, Hh, Ww)) return 1;
   CUDA_OK(cudaSetDevice(h->cfg.device));
-  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  avsep_handle::HostSlot& sl = h->slot[slot_id];
   const size_t F = h->cfg.freq_bins, S = h->cfg.num_speakers;
   const size_t mixed_per = F * T, frames_per = static_cast<size_t>(N) * Hh * Ww, out_per = S * F * T;
-  float** bufs[4] = {&h->io_mixed, &h->io_frames, &h->io_sep, &h->io_masks};
   const size_t need[4] = {B * mixed_per, B * frames_per, B * out_per, B * out_per};
   for (int i = 0; i < 4; ++i) {
-    if (h->io_cap[i] < need[i]) {
-      if (*bufs[i]) cudaFree(*bufs[i]);
-      *bufs[i] = nullptr;
-      h->io_cap[i] = 0;
-      CUDA_OK(cudaMalloc(bufs[i], need[i] * sizeof(float)));
-      h->io_cap[i] = need[i];
+    if (sl.cap[i] < need[i]) {
+      if (sl.ev_end) CUDA_OK(cudaEventSynchronize(sl.ev_end));     // the slot's previous call still owns the buffer
+      if (sl.io[i]) cudaFree(sl.io[i]);
+      sl.io[i] = nullptr;
+      sl.cap[i] = 0;
+      CUDA_OK(cudaMalloc(&sl.io[i], need[i] * sizeof(float)));
+      sl.cap[i] = need[i];
     }
   }
+  float *io_mixed = sl.io[0], *io_frames = sl.io[1], *io_sep = sl.io[2], *io_masks = sl.io[3];
   if (h->hs[0] == nullptr) {
     for (int i = 0; i < 3; ++i) CUDA_OK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
   }
+  auto make_event = [&](cudaEvent_t& e) -> int {
+    if (e == nullptr) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+  };
+  if (make_event(sl.ev_start) || make_event(sl.ev_end)) return 1;
   const int Bc = h->host_chunk > 0 && h->host_chunk < B ? h->host_chunk : B;
   std::vector<int> starts, sizes;
   for (int b0 = 0; b0 < B; b0 += Bc) {
@@ -963,10 +981,10 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
     sizes.push_back((B - b0) < Bc ? (B - b0) : Bc);
   }
   const int nchunks = static_cast<int>(starts.size());
-  while (static_cast<int>(h->host_ev.size()) < 2 * nchunks + 2) {
+  while (static_cast<int>(sl.ev.size()) < 2 * nchunks) {
     cudaEvent_t e;
     CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->host_ev.push_back(e);
+    sl.ev.push_back(e);
   }
   // one workspace + compute stream per lane: with small chunks a single forward cannot fill the GPU, so the kernels
   // of consecutive chunks are allowed to overlap
@@ -974,6 +992,7 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
   Workspace wl[3];
   const size_t per_lane = carve_workspace(h, wl[0], nullptr, Bc, T, N, Hh, Ww);
   if (h->host_ws_bytes < per_lane * lanes) {
+    CUDA_OK(cudaDeviceSynchronize());          // the other slot may still be using the old workspace
     drop_graphs(h);
     if (h->host_ws) cudaFree(h->host_ws);
     h->host_ws = nullptr;
@@ -984,44 +1003,77 @@ int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* li
   for (int l = 0; l < lanes; ++l) {
     carve_workspace(h, wl[l], static_cast<uint8_t*>(h->host_ws) + l * per_lane, Bc, T, N, Hh, Ww);
     if (h->host_comp[l] == nullptr) CUDA_OK(cudaStreamCreateWithFlags(&h->host_comp[l], cudaStreamNonBlocking));
+    if (make_event(sl.ev_lane[l])) return 1;
   }
   cudaStream_t s_in = h->hs[0], s_out = h->hs[2];
-  // order after whatever the caller queued on its stream
-  cudaEvent_t ev_start = h->host_ev[2 * nchunks];
-  CUDA_OK(cudaEventRecord(ev_start, s));
-  CUDA_OK(cudaStreamWaitEvent(s_in, ev_start, 0));
-  for (int l = 0; l < lanes; ++l) CUDA_OK(cudaStreamWaitEvent(h->host_comp[l], ev_start, 0));
-  CUDA_OK(cudaStreamWaitEvent(s_out, ev_start, 0));
+  // order after whatever the caller queued on its stream, and after this slot's previous use: its kernels have read
+  // the input buffers (before they are overwritten) and its copy-out has read the output buffers
+  CUDA_OK(cudaEventRecord(sl.ev_start, s));
+  CUDA_OK(cudaStreamWaitEvent(s_in, sl.ev_start, 0));
+  for (int l = 0; l < 3; ++l)
+    if (sl.ev_lane[l]) CUDA_OK(cudaStreamWaitEvent(s_in, sl.ev_lane[l], 0));
+  for (int l = 0; l < lanes; ++l) {
+    CUDA_OK(cudaStreamWaitEvent(h->host_comp[l], sl.ev_start, 0));
+    CUDA_OK(cudaStreamWaitEvent(h->host_comp[l], sl.ev_end, 0));
+  }
+  CUDA_OK(cudaStreamWaitEvent(s_out, sl.ev_start, 0));
   int64_t launches = 0;
   for (int c = 0; c < nchunks; ++c) {
     const size_t b0 = starts[c];
     const int bc = sizes[c];
     const int lane = c % lanes;
     cudaStream_t s_comp = h->host_comp[lane];
-    CUDA_OK(cudaMemcpyAsync(h->io_mixed + b0 * mixed_per, mixed_spec + b0 * mixed_per, bc * mixed_per * 4,
+    CUDA_OK(cudaMemcpyAsync(io_mixed + b0 * mixed_per, mixed_spec + b0 * mixed_per, bc * mixed_per * 4,
                             cudaMemcpyHostToDevice, s_in));
-    CUDA_OK(cudaMemcpyAsync(h->io_frames + b0 * frames_per, lip_frames + b0 * frames_per, bc * frames_per * 4,
+    CUDA_OK(cudaMemcpyAsync(io_frames + b0 * frames_per, lip_frames + b0 * frames_per, bc * frames_per * 4,
                             cudaMemcpyHostToDevice, s_in));
-    CUDA_OK(cudaEventRecord(h->host_ev[2 * c], s_in));
-    CUDA_OK(cudaStreamWaitEvent(s_comp, h->host_ev[2 * c], 0));
+    CUDA_OK(cudaEventRecord(sl.ev[2 * c], s_in));
+    CUDA_OK(cudaStreamWaitEvent(s_comp, sl.ev[2 * c], 0));
     Workspace wc = wl[lane];
     wc.B = bc;
-    if (forward_cached(h, s_comp, wc, static_cast<uint8_t*>(h->host_ws) + lane * per_lane, h->io_mixed + b0 * mixed_per,
-                       h->io_frames + b0 * frames_per, h->io_sep + b0 * out_per, h->io_masks + b0 * out_per))
+    if (forward_cached(h, s_comp, wc, static_cast<uint8_t*>(h->host_ws) + lane * per_lane, io_mixed + b0 * mixed_per,
+                       io_frames + b0 * frames_per, io_sep + b0 * out_per, io_masks + b0 * out_per))
       return 1;
     launches += h->launches;
-    CUDA_OK(cudaEventRecord(h->host_ev[2 * c + 1], s_comp));
-    CUDA_OK(cudaStreamWaitEvent(s_out, h->host_ev[2 * c + 1], 0));
-    CUDA_OK(cudaMemcpyAsync(separated + b0 * out_per, h->io_sep + b0 * out_per, bc * out_per * 4,
+    CUDA_OK(cudaEventRecord(sl.ev[2 * c + 1], s_comp));
+    CUDA_OK(cudaStreamWaitEvent(s_out, sl.ev[2 * c + 1], 0));
+    CUDA_OK(cudaMemcpyAsync(separated + b0 * out_per, io_sep + b0 * out_per, bc * out_per * 4,
                             cudaMemcpyDeviceToHost, s_out));
-    CUDA_OK(cudaMemcpyAsync(masks + b0 * out_per, h->io_masks + b0 * out_per, bc * out_per * 4,
+    CUDA_OK(cudaMemcpyAsync(masks + b0 * out_per, io_masks + b0 * out_per, bc * out_per * 4,
                             cudaMemcpyDeviceToHost, s_out));
   }
   h->launches = launches;
-  cudaEvent_t ev_end = h->host_ev[2 * nchunks + 1];
-  CUDA_OK(cudaEventRecord(ev_end, s_out));
-  CUDA_OK(cudaStreamWaitEvent(s, ev_end, 0));
-  CUDA_OK(cudaStreamSynchronize(s_out));
+  for (int l = 0; l < lanes; ++l) CUDA_OK(cudaEventRecord(sl.ev_lane[l], h->host_comp[l]));
+  // The caller's stream is deliberately NOT made to wait for the results: that would chain call i+1 (which is ordered
+  // after the caller's stream) behind call i's copy-out.  Results are consumed on the host after avsep_host_wait.
+  CUDA_OK(cudaEventRecord(sl.ev_end, s_out));
+  return 0;
+}
+}  // namespace
+
+int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
+                       int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream) {
+  if (!h) return 1;
+  if (host_submit(h, mixed_spec, lip_frames, B, T, N, Hh, Ww, separated, masks, 0, static_cast<cudaStream_t>(cuda_stream)))
+    return 1;
+  CUDA_OK(cudaEventSynchronize(h->slot[0].ev_end));
+  return 0;
+}
+
+int avsep_forward_host_async(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
+                             int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, int32_t slot,
+                             void* cuda_stream) {
+  if (!h) return 1;
+  return host_submit(h, mixed_spec, lip_frames, B, T, N, Hh, Ww, separated, masks, slot,
+                     static_cast<cudaStream_t>(cuda_stream));
+}
+
+int avsep_host_wait(avsep_handle* h, int32_t slot) {
+  if (!h) return 1;
+  if (slot < 0 || slot > 1) return fail(h, "avsep_host_wait: slot must be 0 or 1");
+  if (h->slot[slot].ev_end == nullptr) return 0;       // nothing was ever submitted on this slot
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  CUDA_OK(cudaEventSynchronize(h->slot[slot].ev_end));
   return 0;
 }
 

@@ -134,6 +134,34 @@ def test_host_path_chunks_and_lanes(chunk, lanes):
         assert np.array_equal(sep_h.numpy(), sep_d) and np.array_equal(masks_h.numpy(), masks_d)
 
 
+def test_host_path_streaming_slots_overlap_safely():
+    """avsep_forward_host_async on alternating slots: every batch of a stream equals its synchronous result, also when
+    a slot is resubmitted without an explicit wait in between (the device-side ordering protects its buffers)."""
+    cfg = CONFIGS["tiny2"]
+    P = make_state_dict(cfg, seed=53, gain=2.0)
+    model = build_model(cfg, P, "bf16")
+    model.prepack()
+    eng = model.engine
+    eng.set_option("host_chunk", 4)
+    batches = []
+    for i in range(6):
+        mixed, frames = make_inputs(cfg, 9, 32, 10, 16, 16, seed=100 + i, kind="randn")
+        mt, ft = torch.from_numpy(mixed).pin_memory(), torch.from_numpy(frames).pin_memory()
+        ref = eng.forward_host(mt, ft)
+        batches.append((mt, ft, ref[0].clone(), ref[1].clone()))
+    outs = [(torch.empty_like(b[2]).pin_memory(), torch.empty_like(b[3]).pin_memory()) for b in batches]
+    for rounds in range(2):
+        for i, (mt, ft, _, _) in enumerate(batches):
+            eng.forward_host_async(mt, ft, outs[i][0], outs[i][1], i % 2)
+        eng.host_wait(0)
+        eng.host_wait(1)
+        for (mt, ft, rs, rm), (os_, om) in zip(batches, outs):
+            assert torch.equal(os_, rs) and torch.equal(om, rm)
+            os_.zero_(); om.zero_()
+    with pytest.raises(RuntimeError, match="slot"):
+        eng.forward_host_async(batches[0][0], batches[0][1], outs[0][0], outs[0][1], 2)
+
+
 def test_submodule_dropins_match_oracle():
     """Reference tests drive the sub-modules directly (tests/test_model.py:77-179), incl. F=65, hd=16, N=10 -> T=50/20."""
     from avsep_b200 import AudioEncoder, CrossModalFusion, SeparationDecoder, VisualEncoder

@@ -28,8 +28,19 @@ def both():
     with torch.cuda.stream(s2): d2h()
 print(json.dumps({"h2d_ms": timed(h2d), "d2h_ms": timed(d2h), "both_ms": timed(both),
                   "h2d_MB": (mixed.numel() + frames.numel()) * 4 / 1e6, "d2h_MB": 2 * sep.numel() * 4 / 1e6}), flush=True)
-for chunk, lanes in [(64, 1), (64, 2), (64, 3), (48, 2), (32, 2), (32, 3), (96, 2), (128, 2), (256, 1)]:
+sep2 = torch.empty_like(sep).pin_memory(); masks2 = torch.empty_like(masks).pin_memory()
+outs = [(sep, masks), (sep2, masks2)]
+def stream_run(n):
+    for i in range(n):
+        sl = i % 2
+        if i >= 2: eng.host_wait(sl)
+        eng.forward_host_async(mixed, frames, outs[sl][0], outs[sl][1], sl)
+    eng.host_wait(0); eng.host_wait(1)
+for chunk, lanes in [(64, 1), (64, 2), (96, 2), (128, 1), (128, 2), (256, 1), (32, 2), (48, 2)]:
     eng.set_option("host_chunk", chunk); eng.set_option("host_lanes", lanes)
     for _ in range(3): eng.forward_host(mixed, frames, sep, masks)
-    ms = timed(lambda: eng.forward_host(mixed, frames, sep, masks), 20)
-    print(json.dumps({"chunk": chunk, "lanes": lanes, "ms": round(ms, 3), "utt_s_per_s": round(B / ms * 1e3)}), flush=True)
+    ms = timed(lambda: eng.forward_host(mixed, frames, sep, masks), 10)
+    stream_run(6); torch.cuda.synchronize(); t0 = time.perf_counter(); stream_run(20); torch.cuda.synchronize()
+    ms2 = (time.perf_counter() - t0) / 20 * 1e3
+    print(json.dumps({"chunk": chunk, "lanes": lanes, "sync_ms": round(ms, 3), "sync_utt_s_per_s": round(B / ms * 1e3),
+                      "stream_ms": round(ms2, 3), "stream_utt_s_per_s": round(B / ms2 * 1e3)}), flush=True)
