@@ -347,7 +347,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     h_sep = h_out[0][0]
     h_masks = h_out[0][1]
-    e2e_value = world * B * CLIP_SECONDS * e2e_steps / e2e_s
+    e2e_stream_value = world * B * CLIP_SECONDS * e2e_steps / e2e_s
+    e2e_sync_value = world * B * CLIP_SECONDS * 4 / e2e_sync_s
+    # both are the repo's public host-buffer API; report the faster form (on one GPU the streaming form is PCIe-bound
+    # and ~30 % ahead; with 8 ranks sharing one host the copies of all ranks contend and the forms are close)
+    e2e_value = max(e2e_stream_value, e2e_sync_value)
     h2d = (h_sets[0][0].numel() + h_sets[0][1].numel()) * 4
     d2h = (h_sep.numel() + h_masks.numel()) * 4
 
@@ -410,9 +414,10 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
-                "api": "avsep_forward_host_async on two I/O slots + avsep_host_wait (pinned host buffers; every step's "
-                       "H2D and D2H inside the timed region; a slot is waited for before it is resubmitted)",
-                "sync_call_value": world * B * CLIP_SECONDS * 4 / e2e_sync_s},
+                "api": ("avsep_forward_host_async on two I/O slots + avsep_host_wait" if e2e_stream_value >= e2e_sync_value
+                        else "avsep_forward_host (one call per batch)") +
+                       " (pinned host buffers; every step's H2D and D2H inside the timed region)",
+                "streaming_value": e2e_stream_value, "sync_call_value": e2e_sync_value},
         "gpu_launches": launches_per_step * args.steps,
         "gflop_per_step": total_flops(B) / 1e9,
         "model_tflops": round(total_flops(B) / (ms_per_step * 1e-3) / 1e12, 2),
