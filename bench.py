@@ -405,6 +405,20 @@ def run_ours(args, rank, local_rank, world):
                     "launch_ms": round(te["ms_per_step"] / n_top, 4),
                     "algorithmic_bytes_per_launch": bytes_[top] / n_top}
 
+    # Secondary limiter of the GEMM-class kernels (tools/tma_rate.cu): a B200 SM ingests TMA boxes from L2 at
+    # 41.4 B/clk = 81 GB/s whatever the number of boxes in flight or of SMs streaming (12 TB/s chip-wide).  The fused
+    # FFN re-streams W1 + W2 (1 MB) for every 128-row tile, plus the A tile (64 KB) and the fp32 residual (128 KB).
+    if top == "ffn.fused":
+        d = MODEL["d_model"]
+        tiles = sum((m + 127) // 128 for m in ([B * T_FRAMES] * (MODEL["num_encoder_layers"] + MODEL["num_fusion_layers"])
+                                                + [B * N_FRAMES] * MODEL["num_encoder_layers"]))
+        per_tile = 2 * 4 * d * d * 2 + 128 * d * 2 + 128 * d * 4
+        sms_busy = min(148, max(1, tiles // n_top))
+        gbs_per_sm = tiles * per_tile / (te["ms_per_step"] * 1e-3) / 1e9 / sms_busy
+        roofline["operand_stream"] = {"what": "TMA ingest L2 -> shared memory per SM, whole kernel incl. prologue and epilogue",
+                                      "achieved_gb_s_per_sm": round(gbs_per_sm, 1), "peak_gb_s_per_sm": 81.0,
+                                      "frac": round(gbs_per_sm / 81.0, 3), "peak_source": "tools/tma_rate.cu on this pool's B200"}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1,0 +1,83 @@
+// Microbenchmark: sustained TMA load rate from an L2-resident buffer into a shared-memory ring (16 KB boxes,
+// 128B swizzle), per SM, with 1 .. 148 CTAs streaming at once, every CTA reading the SAME 1 MB (the weight-stream
+// pattern of the fused FFN / GEMM kernels) or its OWN 1 MB.
+#include "common.cuh"
+#include <cudaTypedefs.h>
+#include <cstdio>
+#include <cstdlib>
+using namespace avsep;
+
+constexpr int BOX = 16384;
+
+template <int SLOTS>
+__global__ void __launch_bounds__(64, 1) tma_rate_kernel(const __grid_constant__ CUtensorMap tm, int boxes_per_mb,
+                                                         int own, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[SLOTS];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SLOTS; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int base = own ? blockIdx.x * boxes_per_mb : 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < reps + SLOTS; ++i) {
+      const int slot = i % SLOTS;
+      if (i >= SLOTS) mbar_wait(&full[slot], ((i / SLOTS) - 1) & 1);      // previous fill of this slot has landed
+      if (i < reps) {
+        mbar_arrive_expect_tx(&full[slot], BOX);
+        tma_load_2d(smem + slot * BOX, &tm, &full[slot], 0, (base + (i % boxes_per_mb)) * 128);
+      }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+}
+
+int main() {
+  const int n_sm = 148, boxes_per_mb = 64;                 // 64 boxes of [128 rows x 64 bf16] = 1 MB
+  const size_t rows = static_cast<size_t>(n_sm) * boxes_per_mb * 128;
+  void* buf;
+  cudaMalloc(&buf, rows * 128);
+  cudaMemset(buf, 0, rows * 128);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  auto enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {64, rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    printf("encode failed\n");
+    return 1;
+  }
+  long long* out;
+  cudaMallocManaged(&out, n_sm * sizeof(long long));
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  const int reps = 4096;
+  auto run = [&](auto kern, int slots, int own, int ctas) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, slots * BOX + 1024);
+    for (int it = 0; it < 2; ++it) {       // first pass warms L2
+      kern<<<ctas, 64, slots * BOX + 1024>>>(tm, boxes_per_mb, own, reps, out);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
+    }
+    double worst = 0;
+    for (int i = 0; i < ctas; ++i) worst = out[i] > worst ? out[i] : worst;
+    const double bpc = double(reps) * BOX / worst;
+    printf("%2d slots in flight, %s 1 MB, %3d CTAs: %.1f B/clk/SM  (%.0f GB/s/SM, %.2f TB/s aggregate at %.2f GHz)\n", slots,
+           own ? "own " : "same", ctas, bpc, bpc * clk_khz * 1e-6, bpc * clk_khz * 1e-6 * ctas * 1e-3, clk_khz * 1e-6);
+  };
+  for (int ctas : {1, 148}) {
+    run(tma_rate_kernel<2>, 2, 0, ctas);
+    run(tma_rate_kernel<4>, 4, 0, ctas);
+    run(tma_rate_kernel<8>, 8, 0, ctas);
+    run(tma_rate_kernel<12>, 12, 0, ctas);
+  }
+  run(tma_rate_kernel<8>, 8, 1, 74);
+  run(tma_rate_kernel<8>, 8, 1, 148);
+  return 0;
+}
