@@ -223,6 +223,25 @@ def test_alternative_execution_paths_agree(option):
         model.engine.set_option(option, 1)
 
 
+@pytest.mark.parametrize("attn_tc", [0, 1])
+def test_long_form_attention_paths_agree(attn_tc):
+    """Long-form case (T=1251, N=500): the tcgen05 attention kernel (+ materialised K/V interpolation) and the
+    mma.sync kernel (interpolation on load) are both parity-green against the reference golden."""
+    z, meta = load_golden("c3_long")
+    cfg, P, mixed, frames = case_tensors(meta)
+    model = build_model(cfg, P, "bf16")
+    model.prepack()
+    model.engine.set_option("attn_tc", attn_tc)
+    try:
+        for _ in range(3):
+            sep, masks = _run(model, mixed, frames)
+        sf, st = meta["stride_f"], meta["stride_t"]
+        rep = err_report(sep[:, :, ::sf, ::st], masks[:, :, ::sf, ::st], z["separated"], z["masks"], mixed[:, ::sf, ::st])
+        assert rep["masks"] < TOL["bf16"] and rep["separated_scaled"] < TOL["bf16"], (attn_tc, rep)
+    finally:
+        model.engine.set_option("attn_tc", 1)
+
+
 def test_graph_replay_is_bit_identical_to_eager():
     cfg = CONFIGS["default"]
     P = make_state_dict(cfg, seed=71, gain=2.0)

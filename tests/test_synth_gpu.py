@@ -125,3 +125,26 @@ def test_evaluate_separation_mirror_runs_on_device():
     ref_in = np.mean([so.input_snrs(it["mixed_spec"], it["clean_specs"]) for it in (so.synth_item(cfg, i) for i in range(8))])
     assert abs(in_snr - ref_in) < 1e-4
     assert np.isfinite(out_snr)
+
+
+def test_synth_and_snr_edge_geometries():
+    """Single speaker, tiny FFT, one item, more video frames than fit evenly; SNR with one speaker."""
+    from avsep_b200.engine import Engine, EngineConfig
+    kw = dict(sample_rate=4000, duration=0.25, n_fft=64, hop_length=16, num_frames=7, frame_h=8, frame_w=12,
+              speaker_freqs=(300.0,))
+    cfg = so.SynthConfig(**kw)
+    ds = _ds(**kw)
+    b = ds.batch([11])
+    torch.cuda.synchronize()
+    ref = so.synth_item(cfg, 11)
+    for k in ("mixed_spec", "lip_frames", "clean_specs"):
+        got = b[k][0].cpu().numpy()
+        assert got.shape == ref[k].shape, k
+        assert np.abs(got - ref[k]).max() <= 2e-6 * max(1.0, np.abs(ref[k]).max()) + 2e-5, k
+    eng = ds.engine
+    tg = b["clean_specs"]
+    sep = (tg * 0.9).contiguous()
+    i_snr, o_snr, perm, si = eng.eval_snr(sep, tg, b["mixed_spec"])
+    assert abs(float(o_snr[0]) - so.permutation_snr(sep[0].cpu().numpy(), tg[0].cpu().numpy())) < 2e-5
+    assert int(perm[0]) == 0
+    assert abs(float(i_snr[0, 0]) - so.input_snrs(b["mixed_spec"][0].cpu().numpy(), tg[0].cpu().numpy())[0]) < 2e-5
