@@ -144,6 +144,7 @@ struct avsep_handle {
   size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
+  bool ffn_cg2 = false;  // experimental: fused FFN on CTA pairs (tcgen05 cta_group::2), see ffn_fused_cg2_sm100.cu
   bool pdl = true;       // programmatic dependent launch between consecutive kernels of a stream
   int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
   void* host_ws = nullptr;
@@ -376,7 +377,8 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
     if (h->fuse_ffn && ffn_fusable(prec, d) && M >= h->ffn_fused_min_rows) {
-      CKL("ffn.fused", launch_ffn_fused(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x, g, b, a_op, M, h->num_sms));
+      CKL("ffn.fused", (h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x,
+                                                                             g, b, a_op, M, h->num_sms, nullptr));
     } else {
       if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
       if (linear_resid_ln(h, s, "gemm.ffn2", ffn, M, 4 * d, w.w2, w.b2, d, x, g, b, a_op, y)) return 1;
@@ -467,8 +469,9 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
     if (h->fuse_ffn && ffn_fusable(prec, d) && Ma >= h->ffn_fused_min_rows) {
-      CKL("ffn.fused", launch_ffn_fused(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU, w.x_a, w.x_a, g, b, w.a_op, Ma,
-                                        h->num_sms));
+      CKL("ffn.fused", (h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU,
+                                                                             w.x_a, w.x_a, g, b, w.a_op, Ma, h->num_sms,
+                                                                             nullptr));
     } else {
       if (linear(h, s, "gemm.ffn1", w.a_op, Ma, d, fw.w1, fw.b1, 4 * d, ACT_GELU, nullptr, w.ffn_a)) return 1;
       if (linear_resid_ln(h, s, "gemm.ffn2", w.ffn_a, Ma, 4 * d, fw.w2, fw.b2, d, w.x_a, g, b, w.a_op, w.y_a)) return 1;
@@ -1314,8 +1317,8 @@ int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const f
                          const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
                          void* out_op, int32_t M, void* cuda_stream) {
   if (!h) return 1;
-  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act, x_inout, x_inout, gamma, beta,
-                      out_op, M, h->num_sms));
+  CK((h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
+                                                             x_inout, x_inout, gamma, beta, out_op, M, h->num_sms, nullptr));
   return 0;
 }
 
@@ -1325,8 +1328,8 @@ int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, c
                                const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
                                void* out_op, int32_t M, unsigned long long* trace_dev, void* cuda_stream) {
   if (!h) return 1;
-  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act, x_inout, x_inout, gamma, beta,
-                      out_op, M, h->num_sms, trace_dev));
+  CK((h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
+                                                             x_inout, x_inout, gamma, beta, out_op, M, h->num_sms, trace_dev));
   return 0;
 }
 
@@ -1335,6 +1338,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "host_lanes") == 0) { h->host_lanes = value; return 0; }
+  if (strcmp(name, "ffn_cg2") == 0) { h->ffn_cg2 = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "pdl") == 0) { h->pdl = value != 0; pdl_set(h->pdl && !h->profile); drop_graphs(h); return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }

@@ -88,6 +88,11 @@ const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, cons
                              const float* b2, int act, const float* resid, float* x_out, const float* gamma,
                              const float* beta, void* out_op, int M, int num_sms,
                              unsigned long long* trace = nullptr);
+// cta_group::2 variant (CTA pairs, half of every weight slab per CTA); experimental, see ffn_fused_cg2_sm100.cu
+const char* launch_ffn_fused_cg2(cudaStream_t s, const void* a, const void* w1, const float* b1, const void* w2,
+                             const float* b2, int act, const float* resid, float* x_out, const float* gamma,
+                             const float* beta, void* out_op, int M, int num_sms,
+                             unsigned long long* trace = nullptr);
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).

@@ -22,6 +22,7 @@ for M, act in ((16128, 1), (16128, 2)):
     t = trace.cpu().numpy().reshape(148, 64).astype(np.int64)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
+    t = t[t[:, 8] > 0]          # CTAs whose MMA thread stamped (with cta_group::2 pairs: the leaders)
     r = (t - t0) / 1e3
     print(f"== fused FFN M={M} act={act} ctas={len(t)} (us since first CTA entry, mean over CTAs)")
     print(f"   A landed {r[:,1].mean():.2f}   acc2 complete {r[:,2].mean():.2f}   epilogue-2 done {r[:,3].mean():.2f} (max {r[:,3].max():.2f})")
