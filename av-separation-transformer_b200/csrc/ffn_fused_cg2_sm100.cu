@@ -1,7 +1,7 @@
 // EXPERIMENTAL cta_group::2 variant of the fused feed-forward kernel (ffn_fused_sm100.cu); selected with
-// avsep_set_option("ffn_cg2", 1), parity-tested, off by default: measured 25.0 us per launch against 23.3 us for the
-// one-CTA kernel at M = 16128 (tools/ffn_trace.py) - the weight bytes per SM halve, but the operand stream of the pair
-// runs at 16 B/clk per CTA (cross-CTA completion / free signalling), so the MMA thread still waits on operands.
+// avsep_set_option("ffn_cg2", 1), parity-tested, off by default: measured 23.0 us per launch against 23.3 us for the
+// one-CTA kernel at M = 16128 (FFN_CG2=1 tools/ffn_trace.py) - the weight bytes per SM halve, but the MMA thread still
+// waits on operands ~40 % of the time (1.75 us per chunk for 1.04 us of tensor time), as in the one-CTA kernel.
 //
 // Fused feed-forward sub-layer for d_model = 256 (hidden = 1024), bf16 operands:
 //
@@ -139,15 +139,25 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      uint32_t wn = 0;      // weight slabs issued so far
       // Every load of the pair signals the LEADER's barrier (the MMA thread lives there): the leader expects the bytes
       // of both halves, the peer's TMA completes its share on the leader's barrier directly.
-      auto load_w = [&](const CUtensorMap* tm, int c0, int c1) {      // one 64-row x 64-column box = one ring slot
-        const uint32_t slot = wn % WSLOTS, use = wn / WSLOTS;
-        mbar_wait(&w_empty[slot], (use & 1) ^ 1);
+      // Two rings with fixed roles (so every slot's barrier completes exactly once per wrap): slots 0..7 hold W1 half
+      // chunks (64 rows, 8 KB), slots 8..15 hold this CTA's halves of W2 k-slabs as four 16 KB pairs.  A ring group
+      // (4 slots = one chunk's worth) is freed by one multicast commit.
+      uint32_t w1n = 0, w2n = 0;
+      auto load_w1 = [&](int c0, int c1) {
+        const uint32_t slot = w1n & 7, use = w1n >> 3;
+        if ((slot & 3) == 0) mbar_wait(&w_empty[slot], (use & 1) ^ 1);
         if (leader) mbar_arrive_expect_tx(&w_full[slot], 2 * WSLOT);
-        tma_load_2d_cg2(smem + OFF_W + slot * WSLOT, tm, &w_full[slot], 0, c0, c1);
-        ++wn;
+        tma_load_2d_cg2(smem + OFF_W + slot * WSLOT, &tmW1, &w_full[slot], 0, c0, c1);
+        ++w1n;
+      };
+      auto load_w2 = [&](int c0, int c1) {
+        const uint32_t pr = w2n & 3, use = w2n >> 2, slot = 8 + 2 * pr;
+        if ((pr & 1) == 0) mbar_wait(&w_empty[slot], (use & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&w_full[slot], 4 * WSLOT);
+        tma_load_2d_cg2(smem + OFF_W + slot * WSLOT, &tmW2, &w_full[slot], 0, c0, c1);
+        ++w2n;
       };
       int lt = 0;
       for (int ct = cluster_id; ct < cl_tiles; ct += n_clusters, ++lt) {
@@ -157,10 +167,9 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int k = 0; k < 4; ++k) tma_load_2d_cg2(smem + OFF_A + k * SLAB, &tmA, a_full, 0, k * 64, tile * 128);
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK)                       // this CTA's half of W1 chunk j: rows j*128 + rank*64 .. +64, k-slab k
-            for (int k = 0; k < 4; ++k) load_w(&tmW1, k * 64, j * CHUNK + static_cast<int>(crank) * 64);
+            for (int k = 0; k < 4; ++k) load_w1(k * 64, j * CHUNK + static_cast<int>(crank) * 64);
           if (j >= 1)                           // this CTA's half of W2: rows rank*128 .. +128 (two slots), hidden columns (j-1)*128 + k*64
-            for (int k = 0; k < 2; ++k)
-              for (int hf = 0; hf < 2; ++hf) load_w(&tmW2, (j - 1) * CHUNK + k * 64, static_cast<int>(crank) * 128 + hf * 64);
+            for (int k = 0; k < 2; ++k) load_w2((j - 1) * CHUNK + k * 64, static_cast<int>(crank) * 128);
         }
       }
     }
@@ -169,14 +178,21 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // ---------------- leader: MMA issuer for the pair ----------------
       const uint32_t idesc = umma_idesc(1u, 256, 128);
       const uint32_t idesc2 = umma_idesc(1u, 256, 256);
-      uint32_t wn = 0;
+      uint32_t w1n = 0, w2n = 0;
       uint32_t c1n = 0;      // GEMM1 chunks issued so far (acc1 stage = c1n & 1)
       uint32_t c2n = 0;      // GEMM2 chunks issued so far
-      auto next_w = [&]() -> uint32_t {
-        const uint32_t slot = wn % WSLOTS, use = wn / WSLOTS;
-        mbar_wait(&w_full[slot], use & 1);        // both halves (the peer's TMA signals this barrier too)
+      auto next_w1 = [&]() -> uint32_t {
+        const uint32_t slot = w1n & 7, use = w1n >> 3;
+        mbar_wait(&w_full[slot], use & 1);          // both halves (the peer's TMA signals this barrier too)
         tc_fence_after();
-        ++wn;
+        ++w1n;
+        return slot;
+      };
+      auto next_w2 = [&]() -> uint32_t {
+        const uint32_t slot = 8 + 2 * (w2n & 3), use = w2n >> 2;
+        mbar_wait(&w_full[slot], use & 1);
+        tc_fence_after();
+        ++w2n;
         return slot;
       };
       int lt = 0;
@@ -191,13 +207,13 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t st = c1n & 1;
             const uint32_t d_tmem = tm_acc1 + st * CHUNK;
             for (int k = 0; k < 4; ++k) {
-              const uint32_t slot = next_w();
+              const uint32_t slot = next_w1();
               const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_A + k * SLAB), 1024);
               const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_W + slot * WSLOT), 1024);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 umma_f16_cg2(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-              umma_commit_cg2(&w_empty[slot], BOTH);
+              if (k == 3) umma_commit_cg2(&w_empty[slot & ~3u], BOTH);     // the chunk's four W1 slots
             }
             umma_commit_cg2(&acc1_full[st], BOTH);
             FTRACE(8 + 4 * j);                               // GEMM1_j issued
@@ -209,15 +225,13 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&h_full[st2], (c2n >> 1) & 1);
             tc_fence_after();
             for (int k = 0; k < 2; ++k) {
-              const uint32_t slot = next_w();
-              const uint32_t slot1 = next_w();            // rows 64..127 of this CTA's half: the adjacent slot (slot is even)
+              const uint32_t slot = next_w2();            // one barrier for the 128-row box (two adjacent slots)
               const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_W + slot * WSLOT), 1024);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 umma_f16_ts_cg2(tm_acc2, tm_acc1 + st2 * CHUNK + (k * 4 + kk) * 8, bdesc + 2 * kk, idesc2,
                                 ((j - 1) | k | kk) != 0 ? 1u : 0u);
-              umma_commit_cg2(&w_empty[slot], BOTH);
-              umma_commit_cg2(&w_empty[slot1], BOTH);
+              if (k == 1) umma_commit_cg2(&w_empty[slot - 2], BOTH);       // the chunk's two W2 pairs (group barrier = first pair's slot)
             }
             FTRACE(8 + 4 * (j - 1) + 1);                     // GEMM2_{j-1} issued
             ++c2n;
@@ -456,9 +470,9 @@ const char* launch_ffn_fused_cg2(cudaStream_t s, const void* a, const void* w1, 
   }
   CUtensorMap ta, tw1, tw2, tx, top;
   if (const char* e = enc2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, D, M, D, 64, 128)) return e;
-  // one box = 64 weight rows x 64 columns = one 8 KB ring slot
+  // W1: 64 rows x 64 columns = one 8 KB ring slot; W2: 128 rows x 64 columns = two adjacent slots
   if (const char* e = enc2d(&tw1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w1, D, HID, D, 64, 64)) return e;
-  if (const char* e = enc2d(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2, HID, D, HID, 64, 64)) return e;
+  if (const char* e = enc2d(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w2, HID, D, HID, 64, 128)) return e;
   tx = ta; top = ta;
   if (x_out != nullptr)
     if (const char* e = enc2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x_out, D, M, D, 32, 128)) return e;
