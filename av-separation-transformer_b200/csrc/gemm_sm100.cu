@@ -900,11 +900,19 @@ const char* launch_gemm(cudaStream_t s, int prec, const GemmProblem& p, const Ge
   } else if (force_bn > 0) {
     n_tile = force_bn;
   } else {
-    // widest tile that still gives every SM work; N is split evenly and rounded to the UMMA N granularity (16)
-    int bn = BN_MAX;
-    while (bn > 64 && m_tiles * ((p.N + bn - 1) / bn) < g_num_sms) bn >>= 1;
-    const int ntiles = (p.N + bn - 1) / bn;
-    n_tile = ((p.N + ntiles - 1) / ntiles + 15) / 16 * 16;
+    // Tile width by a two-term cost model fitted to tools/gemm_bn_sweep.py: the kernel is paced by operand ingest
+    // (A tile 128 rows + W tile n_tile rows per k-step) and by the epilogue (~ n_tile), and a CTA runs
+    // ceil(tiles / SMs) tiles back to back.  N is split evenly and rounded to the UMMA N granularity (16).
+    int best = BN_MAX;
+    long best_cost = -1;
+    for (int bn = BN_MAX; bn >= 64; bn -= 64) {
+      const int ntiles = (p.N + bn - 1) / bn;
+      const int width = ((p.N + ntiles - 1) / ntiles + 15) / 16 * 16;
+      const long rounds = (static_cast<long>(m_tiles) * ntiles + g_num_sms - 1) / g_num_sms;
+      const long cost = rounds * (128 + width);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = width; }
+    }
+    n_tile = best;
   }
   if (n_tile > BN_MAX || n_tile < 16 || (n_tile % 16) != 0) return "gemm: bad tile width";
   GemmDev d;
