@@ -263,7 +263,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator stage complete
   uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator stage drained by the epilogue
   uint64_t* resid_bar = tempty_bar + 2;         // [4] residual slab of column part p landed (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 4);
+  uint64_t* resid_bar2 = resid_bar + 4;         // [4] second residual chunk, fetched into the idle pipeline stages (last tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar2 + 4);
   float2* red = reinterpret_cast<float2*>(smem + RED_OFFSET);
   float* sbias = reinterpret_cast<float*>(smem + VEC_OFFSET);       // [2][BN_MAX], double-buffered per tile
   float* sgamma = sbias + 2 * BN_MAX;
@@ -294,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tempty_bar[a], NUM_EPI_WARPS);
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) mbar_init(&resid_bar[a], 1);
+    for (int a = 0; a < 4; ++a) { mbar_init(&resid_bar[a], 1); mbar_init(&resid_bar2[a], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -454,31 +455,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // residual chunk: TMA-loaded slab -> own-row LDS; x' chunk: own-row STS into the same slab -> one TMA store;
         // normalised bf16 row (64 columns = 128 B): own-row STS -> one TMA store.  No per-element address math.
         const RowInfo ri = row_info(e, m, p.M);
+        // On the CTA's last tile every pipeline stage has been consumed (this tile's accumulator is complete and
+        // nothing more will be loaded): the second residual chunk is fetched into stage memory right away instead of
+        // after the first chunk's x' store has left the slab.
+        const bool last_tile = tile + static_cast<int>(gridDim.x) >= total_tiles;
+        uint8_t* const slab1 = last_tile ? smem + part * 16384 : slab;
+        if (last_tile && e.resid != nullptr && elected) {
+          mbar_arrive_expect_tx(&resid_bar2[part], 16384);
+          tma_load_2d(slab1, &tmF32, &resid_bar2[part], part * 64 + 32, m0);
+        }
         float val[2][32];
         float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int c0 = part * 64 + ci * 32;
+          uint8_t* const sl = ci == 0 ? slab : slab1;
+          uint8_t* const sl_q = sl + q * 4096;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
           if (e.resid != nullptr) {
-            mbar_wait(&resid_bar[part], rph);
-            rph ^= 1;
+            if (ci == 1 && last_tile) {
+              mbar_wait(&resid_bar2[part], 0);
+            } else {
+              mbar_wait(&resid_bar[part], rph);
+              rph ^= 1;
+            }
           }
           tmem_ld_wait();
           value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
-          if (e.resid != nullptr) stg_add_own_f32(slab_q, lane, val[ci]);
+          if (e.resid != nullptr) stg_add_own_f32(sl_q, lane, val[ci]);
           if (e.out_f32 != nullptr) {
-            stg_write_own_f32(slab_q, lane, val[ci]);
+            stg_write_own_f32(sl_q, lane, val[ci]);
             fence_proxy_async_smem();
           }
           if (e.out_f32 != nullptr || (e.resid != nullptr && ci == 0)) named_bar_sync(part_bar, 128);
           if (elected) {
             if (e.out_f32 != nullptr) {
-              tma_store_2d(&tmF32, slab, c0, m0);
+              tma_store_2d(&tmF32, sl, c0, m0);
               bulk_commit();
             }
-            if (ci == 0 && e.resid != nullptr) {
+            if (ci == 0 && e.resid != nullptr && !last_tile) {
               bulk_wait_read0();                              // the store has read the slab: refill it
               mbar_arrive_expect_tx(&resid_bar[part], 16384);
               tma_load_2d(slab, &tmF32, &resid_bar[part], c0 + 32, m0);

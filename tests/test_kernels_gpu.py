@@ -146,7 +146,8 @@ def test_attention_split_fp32_grade(eng32):
     assert (out2 - ref2).abs().max().item() < 2e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (16128, 256, 1024), (77, 64, 64), (300, 128, 512), (130, 32, 64)])
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 256), (16128, 256, 1024), (77, 64, 64), (300, 128, 512), (130, 32, 64),
+                                   (148 * 128 + 700, 256, 256)])     # last: some CTAs run two tiles (both epilogue paths)
 def test_gemm_fused_residual_layernorm(eng, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
