@@ -284,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (threadIdx.x == 64) {
       tma_store_3d(&tmO, sQ, h * HD, q0, b);
       bulk_commit();
-      bulk_wait0();
+      bulk_wait_read0();     // the staging tile may be released; the stores themselves complete with the grid
     }
   }
   tc_fence_before();

@@ -422,7 +422,7 @@ ffn_fused_cg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (threadIdx.x == 64) mbar_arrive(a_empty);
       if (threadIdx.x == 64) FTRACE(3);                      // epilogue-2 done
     }
-    if (elected) bulk_wait0();
+    if (elected) bulk_wait_read0();     // shared memory may be released; the stores complete with the grid
   }
 
   tc_fence_before();

@@ -827,7 +827,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
-  if (p.use_tma && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) bulk_wait0();   // outstanding TMA stores
+  if (p.use_tma && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) bulk_wait_read0();   // outstanding TMA stores have read their slabs (they complete with the grid)
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TRACE(7);              // all tiles of this CTA done
