@@ -112,7 +112,20 @@ AVSEP_API int avsep_set_debug(avsep_handle* h, int32_t enable);
 /* Copies a snapshot to a HOST buffer of `capacity` floats; returns the element count in *count. Synchronises. */
 AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* host_out, size_t capacity, size_t* count);
 
-/* Execution options (A/B testing): "fuse_ln" (default 1) = residual+LayerNorm inside the GEMM epilogue. */
+/* Execution options (A/B switches; every position is parity-tested).  name -> meaning (default):
+ *   "fuse_ln" (1)            residual + LayerNorm inside the GEMM epilogue (0: separate add+LayerNorm kernel)
+ *   "epilogue_tma" (1)       TMA-slab GEMM epilogues (0: cooperative stores)
+ *   "fuse_ffn" (1)           one kernel per feed-forward sub-layer when d_model = 256, bf16, rows >= ffn_fused_min_rows
+ *   "ffn_fused_min_rows" (2048)
+ *   "ffn_cg2" (0)            experimental cta_group::2 variant of the fused feed-forward kernel
+ *   "cnn_tc" (1)             tcgen05 CNN for 32x32 frames (0: generic mma.sync kernel)
+ *   "attn_tc" (1)            1: tcgen05 attention when min(Lq, Lk) >= attn_tc_min_len; 0: never; 2: whenever usable
+ *   "attn_tc_min_len" (96)
+ *   "use_graph" (1)          CUDA-graph replay keyed by (shape, buffers)
+ *   "two_stream" (1)         audio and visual branches on two streams
+ *   "pdl" (1)                programmatic dependent launch between consecutive kernels
+ *   "host_chunk" (64), "host_lanes" (2)   avsep_forward_host pipeline: utterances per chunk, concurrent compute lanes
+ *   "profile_spin_us"        length of the GPU spin kernel that precedes a profiled forward */
 AVSEP_API int avsep_set_option(avsep_handle* h, const char* name, int32_t value);
 
 /* Per-kernel timing: when enabled every launch of the forward is bracketed by a cudaEvent pair on the launching
