@@ -1,7 +1,8 @@
-"""Small end-to-end invocations for compute-sanitizer runs (every forward-path kernel, both precisions, synthesis, SNR)."""
+"""Small end-to-end invocations of every forward-path kernel in several configurations, both precisions, plus synthesis
+and SNR evaluation (test infrastructure: it uses the oracle's weight / input generator)."""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200"))
 from helpers import build_model
 from oracle.weights import CONFIGS, make_state_dict, make_inputs

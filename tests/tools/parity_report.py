@@ -1,7 +1,7 @@
 """Print the golden-case parity numbers (max |error| of masks / separated) for a precision path."""
 import os, sys, json
 import numpy as np, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200"))
 from helpers import load_golden, case_tensors, build_model, err_report
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"

@@ -4,7 +4,7 @@ Prints items/s for: host draws only (numpy RNG, unavoidable), device arithmetic 
 the whole GPU-backed dataset.batch(), and the oracle's CPU item loop."""
 import json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200")); sys.path.insert(0, ROOT)
 from avsep_b200.dataset import SyntheticAVDataset
 from oracle import synth_oracle as so
