@@ -344,6 +344,115 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnDev p) {
   }
 }
 
+// Single-tile specialisation for Lq, Lk <= 64 (the 1-second clips: T = 63, N = 50), bf16, head dim 64: no online-softmax
+// state, Q fragments re-read from shared memory per k-step, so the kernel fits 72 registers and seven CTAs per SM -
+// the B*H = 1024 CTAs of a B = 256 launch then run as one wave instead of two (the generic kernel needs 128 registers).
+template <bool LERP>
+__global__ void __launch_bounds__(128, 7) attention_small_kernel(const AttnDev p) {
+  constexpr int HD = 64, LDS = HD + 8, KS = HD / 16, NT_O = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sK = sQ + QT * LDS;
+  __nv_bfloat16* sV = sK + KT * LDS;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const __nv_bfloat16* qsrc = reinterpret_cast<const __nv_bfloat16*>(p.q) + static_cast<size_t>(b) * p.Lq * p.ldq + h * HD;
+    load_tile_bf16<HD>(sQ, qsrc, p.ldq, 0, p.Lq);
+    if constexpr (LERP) {
+      const float* ksrc = reinterpret_cast<const float*>(p.k) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
+      const float* vsrc = reinterpret_cast<const float*>(p.v) + static_cast<size_t>(b) * p.nsrc * p.ldkv + h * HD;
+      load_tile_lerp<HD>(sK, ksrc, p.ldkv, 0, p.Lk, p.nsrc, p.lerp_scale);
+      load_tile_lerp<HD>(sV, vsrc, p.ldkv, 0, p.Lk, p.nsrc, p.lerp_scale);
+    } else {
+      const __nv_bfloat16* ksrc = reinterpret_cast<const __nv_bfloat16*>(p.k) + static_cast<size_t>(b) * p.Lk * p.ldkv + h * HD;
+      const __nv_bfloat16* vsrc = reinterpret_cast<const __nv_bfloat16*>(p.v) + static_cast<size_t>(b) * p.Lk * p.ldkv + h * HD;
+      load_tile_bf16<HD>(sK, ksrc, p.ldkv, 0, p.Lk);
+      load_tile_bf16<HD>(sV, vsrc, p.ldkv, 0, p.Lk);
+    }
+  }
+  __syncthreads();
+  // ---- S = Q K^T (16 x 64 per warp) ----
+  float s[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    uint32_t qf[4];
+    ldmatrix_x4(qf, smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bf[4];
+      ldmatrix_x4(bf, smem_u32(sK + (np * 16 + ((lane >> 4) << 3) + (lane & 7)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8));
+      mma_bf16_16816(s[2 * np], qf, bf[0], bf[1]);
+      mma_bf16_16816(s[2 * np + 1], qf, bf[2], bf[3]);
+    }
+  }
+  // ---- softmax over the (single) tile ----
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * (lane & 3);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float val = (c + (e & 1)) < p.Lk ? s[nt][e] * p.scale_log2 : -INFINITY;
+      s[nt][e] = val;
+      if (e < 2) mx0 = fmaxf(mx0, val); else mx1 = fmaxf(mx1, val);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pf[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float p0 = exp2f(s[nt][0] - mx0), p1 = exp2f(s[nt][1] - mx0);
+    const float p2 = exp2f(s[nt][2] - mx1), p3 = exp2f(s[nt][3] - mx1);
+    l0 += p0 + p1; l1 += p2 + p3;
+    pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+    pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  // ---- O = P V ----
+  float o[NT_O][4];
+#pragma unroll
+  for (int i = 0; i < NT_O; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NT_O / 2; ++np) {
+      uint32_t bf[4];
+      ldmatrix_x4_trans(bf, smem_u32(sV + (ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + np * 16 + (lane >> 4) * 8));
+      mma_bf16_16816(o[2 * np], pf[ks], bf[0], bf[1]);
+      mma_bf16_16816(o[2 * np + 1], pf[ks], bf[2], bf[3]);
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  const int r0 = warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(b) * p.Lq * p.ldo + h * HD + 2 * (lane & 3);
+#pragma unroll
+  for (int nt = 0; nt < NT_O; ++nt) {
+    if (r0 < p.Lq)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r0) * p.ldo + nt * 8) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
+    if (r1 < p.Lq)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(r1) * p.ldo + nt * 8) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+  }
+}
+
+template <bool LERP>
+const char* launch_small(cudaStream_t s, const AttnDev& d, int B, int H) {
+  constexpr int SMEM = 3 * 64 * (64 + 8) * 2;
+  dim3 grid(1, H, B);
+  if (launch_pdl(attention_small_kernel<LERP>, grid, dim3(128), SMEM, s, d) != cudaSuccess) {
+    cudaGetLastError();
+    return "attention: launch failed";
+  }
+  return nullptr;
+}
+
 template <int HD, bool LERP, bool SPLIT>
 const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
   constexpr int SMEM = (SPLIT ? 6 : 3) * 64 * (HD + 8) * 2;
@@ -367,7 +476,10 @@ const char* launch_t(cudaStream_t s, const AttnDev& d, int B, int H, int Lq) {
 namespace {
 int g_tc_mode = 1;
 int g_tc_min_len = 96;
+bool g_small = true;      // single-tile kernel for Lq, Lk <= 64
 }  // namespace
+
+void attention_set_small(bool on) { g_small = on; }
 
 void attention_set_tc(int mode, int min_len) {
   g_tc_mode = mode;
@@ -395,6 +507,10 @@ const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p) {
   if (split) {
     if ((p.ldq & 3) || (p.ldo & 1) || (p.ldkv & 3)) return "attention: misaligned leading dimension";
   } else {
+    if (g_small && p.hd == 64 && p.Lq <= QT && p.Lk <= KT && !(p.ldq & 7) && !(p.ldo & 1) && !(lerp ? (p.ldkv & 3) : (p.ldkv & 7)))
+      return lerp ? launch_small<true>(s, d, p.B, p.H) : launch_small<false>(s, d, p.B, p.H);
+  }
+  if (!split) {
     if ((p.ldq & 7) || (p.ldo & 1) || (lerp ? (p.ldkv & 3) : (p.ldkv & 7))) return "attention: misaligned leading dimension";
   }
 #define AVSEP_ATTN_CASE(HDV)                                                                              \

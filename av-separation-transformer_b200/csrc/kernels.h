@@ -116,7 +116,8 @@ const char* launch_attention(cudaStream_t s, int prec, const AttnProblem& p);
 bool attention_tc_usable(int prec, const AttnProblem& p);
 bool attention_tc_wanted(int prec, const AttnProblem& p);      // usable and selected by the current mode
 const char* launch_attention_tc(cudaStream_t s, const AttnProblem& p);
-void attention_set_tc(int mode, int min_len);                  // min_len <= 0 keeps the current value
+void attention_set_tc(int mode, int min_len);
+void attention_set_small(bool on);                             // single-tile kernel for Lq, Lk <= 64 (bf16, head dim 64)                  // min_len <= 0 keeps the current value
 // dst[b*L + t, 0:cols] (bf16) = linear interpolation (align_corners=False) of src rows [b*nsrc + i, 0:cols] (fp32)
 const char* launch_lerp_rows(cudaStream_t s, const float* src, int ld_src, int B, int nsrc, int L, int cols,
                              void* dst_bf16, int ld_dst);

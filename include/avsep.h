@@ -121,6 +121,7 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
  *   "cnn_tc" (1)             tcgen05 CNN for 32x32 frames (0: generic mma.sync kernel)
  *   "attn_tc" (1)            1: tcgen05 attention when min(Lq, Lk) >= attn_tc_min_len; 0: never; 2: whenever usable
  *   "attn_tc_min_len" (96)
+ *   "attn_small" (1)         single-tile attention kernel (72 registers, 7 CTAs/SM) when Lq, Lk <= 64, bf16, head dim 64
  *   "use_graph" (1)          CUDA-graph replay keyed by (shape, buffers)
  *   "two_stream" (1)         audio and visual branches on two streams
  *   "pdl" (1)                programmatic dependent launch between consecutive kernels

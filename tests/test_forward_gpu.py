@@ -205,7 +205,8 @@ def test_errors_are_loud():
         model(torch.zeros(1, 65, 5001, device="cuda"), torch.zeros(1, 4, 16, 16, device="cuda"))  # > PE table
 
 
-@pytest.mark.parametrize("option", ["fuse_ln", "epilogue_tma", "cnn_tc", "use_graph", "two_stream", "fuse_ffn", "pdl"])
+@pytest.mark.parametrize("option", ["fuse_ln", "epilogue_tma", "cnn_tc", "use_graph", "two_stream", "fuse_ffn", "pdl",
+                                    "attn_small"])
 def test_alternative_execution_paths_agree(option):
     """Every A/B switch of the library (unfused LayerNorm kernel, cooperative epilogue, generic mma.sync CNN, eager
     launches) must stay parity-green: same golden case, same tolerance."""
