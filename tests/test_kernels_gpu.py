@@ -192,7 +192,8 @@ def test_conv1d_implicit_gemm(eng, B, L, N, K):
 
 
 @pytest.mark.parametrize("B,H,hd,Lq,Lk", [(2, 4, 64, 63, 63), (3, 4, 16, 32, 32), (1, 2, 64, 200, 200),
-                                           (2, 8, 64, 50, 50), (1, 1, 32, 5, 5), (1, 2, 128, 70, 70)])
+                                           (2, 8, 64, 50, 50), (1, 1, 32, 5, 5), (1, 2, 128, 70, 70),
+                                           (1, 4, 64, 20, 60), (2, 4, 64, 64, 1), (2, 2, 64, 1, 64), (1, 4, 64, 64, 65)])
 def test_attention_self(eng, B, H, hd, Lq, Lk):
     g = torch.Generator(device="cuda").manual_seed(B * 100 + Lq)
     d = H * hd
