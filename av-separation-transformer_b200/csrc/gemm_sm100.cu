@@ -420,12 +420,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tt = m - tb * e.T;
         const float* mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
         const size_t out_base = static_cast<size_t>(tb) * e.S * e.F * e.T + tt;
-        for (int c0 = part * 32; c0 < p.n_tile; c0 += 128) {
+        // Each column part takes a contiguous, balanced share of the tile in units of 16 columns (176 columns ->
+        // 48/48/48/32), walked 32 columns at a time; handing out whole 32-column chunks round-robin left two parts
+        // with twice the work of the others and the tile waiting on them at the next barrier.
+        const int units = p.n_tile >> 4, ubase = units >> 2, urem = units & 3;
+        const int cbeg = (part * ubase + min(part, urem)) << 4;
+        const int cend = cbeg + ((ubase + (part < urem ? 1 : 0)) << 4);
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
           const int col0 = n0 + c0;
           if (col0 >= p.N) break;                      // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
-          const int ncols = min(32, min(p.N - col0, p.n_tile - c0));
+          const int ncols = min(32, min(p.N - col0, cend - c0));
           int f = col0 % e.F;
           float mx[32];
           if (valid) {                                 // all mixed_spec loads in flight before any store
