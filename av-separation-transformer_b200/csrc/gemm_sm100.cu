@@ -200,7 +200,7 @@ __device__ __forceinline__ RowInfo row_info(const GemmEpilogue& e, int m, int M)
 }
 
 // acc chunk -> value chunk: (+ prior contents when ACCUM) + bias (shared memory), activation, + PE, halo zeroing.
-template <bool ACCUM>
+template <bool ACCUM, bool SKIP_PE = false>
 __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo& ri, const uint32_t (&v)[32],
                                             float (&val)[32], const float* sbias_c0, int col0, int ncols, int N) {
   const bool full = (ncols == 32);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo
 #pragma unroll
     for (int j = 0; j < 32; ++j) val[j] = gelu_bf16_grade(val[j]);
   }
-  if (e.pe != nullptr && ri.valid) {
+  if (!SKIP_PE && e.pe != nullptr && ri.valid) {
     const float* pr = e.pe + static_cast<size_t>(ri.pos) * N + col0;
     if (full && (N & 3) == 0) {
 #pragma unroll
@@ -588,6 +588,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const unsigned long long op_row =
             (ri.valid && e.out_op != nullptr)
                 ? reinterpret_cast<unsigned long long>(e.out_op) + static_cast<size_t>(ri.orow) * e.ld_op * (TF32 ? 4 : 2) : 0ull;
+        // positional-encoding rows are fetched like the residual: whole 128-byte lines, 4 rows per warp instruction,
+        // through the warp's transpose buffer (a thread-per-row read touches 32 lines per instruction)
+        const unsigned long long pe_row =
+            (ri.valid && !ri.zero_row && e.pe != nullptr) ? reinterpret_cast<unsigned long long>(e.pe + static_cast<size_t>(ri.pos) * p.N) : 0ull;
         float val[2][32];
         float sum = 0.f;
 #pragma unroll
@@ -596,11 +600,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int c0 = (ch_first + ci) * 32;
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
-            if (e.resid != nullptr) stg_load_rows(stg, resid_row ? resid_row + c0 * 4 : 0ull, lane);
+            if (e.pe != nullptr) stg_load_rows(stg, pe_row ? pe_row + c0 * 4 : 0ull, lane);
             tmem_ld_wait();
-            value_chunk<false>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
+            value_chunk<false, true>(e, ri, v, val[ci], sb + c0, c0, 32, p.N);
             __syncwarp();
-            if (e.resid != nullptr) stg_add_own_f32(stg, lane, val[ci]);
+            if (e.pe != nullptr) {
+              stg_add_own_f32(stg, lane, val[ci]);
+              __syncwarp();
+            }
+            if (e.resid != nullptr) {
+              stg_load_rows(stg, resid_row ? resid_row + c0 * 4 : 0ull, lane);
+              __syncwarp();
+              stg_add_own_f32(stg, lane, val[ci]);
+            }
             if (e.out_f32 != nullptr) {
               stg_write_own_f32(stg, lane, val[ci]);
               __syncwarp();
