@@ -126,7 +126,9 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
  *   "two_stream" (1)         audio and visual branches on two streams
  *   "pdl" (1)                programmatic dependent launch between consecutive kernels
  *   "host_chunk" (64), "host_lanes" (2)   avsep_forward_host pipeline: utterances per chunk, concurrent compute lanes
- *   "profile_spin_us"        length of the GPU spin kernel that precedes a profiled forward */
+ *   "profile_spin_us"        length of the GPU spin kernel that precedes a profiled forward
+ * Kernel-selection switches ("epilogue_tma", "attn_tc", "attn_tc_min_len", "attn_small", "pdl") are process-wide:
+ * they apply to every handle of the process, not only to `h`. */
 AVSEP_API int avsep_set_option(avsep_handle* h, const char* name, int32_t value);
 
 /* Per-kernel timing: when enabled every launch of the forward is bracketed by a cudaEvent pair on the launching
