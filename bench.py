@@ -355,6 +355,34 @@ def run_ours(args, rank, local_rank, world):
     h2d = (h_sets[0][0].numel() + h_sets[0][1].numel()) * 4
     d2h = (h_sep.numel() + h_masks.numel()) * 4
 
+    # ---- N > 1: the same steps with the outputs collected on rank 0 (the headline keeps every rank's
+    # outputs on its own GPU; a consumer that wants them in one place pays an NCCL gather over NVLink).  Two wire
+    # formats: masks + separated in fp32 (what the reference returns), and masks only in bf16 (rank 0 holds the
+    # mixture and can rebuild `separated = masks * mixed`).  Not overlapped with the next step's kernels.
+    gathered = None
+    if world > 1:
+        gathered = {}
+        for tag, fn in (("masks+separated fp32", lambda: (masks, sep)), ("masks bf16", lambda: (masks.to(torch.bfloat16),))):
+            bufs = [[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in fn()]
+            def gstep(i):
+                step(i)
+                for t, gl in zip(fn(), bufs):
+                    dist.gather(t, gl, dst=0)
+            for i in range(3):
+                gstep(i)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_g = max(5, min(args.steps, 50))
+            g0.record(stream)
+            for i in range(n_g):
+                gstep(i)
+            g1.record(stream)
+            barrier()
+            g_ms = max_over_ranks(g0.elapsed_time(g1)) / n_g
+            gathered[tag] = {"ms_per_step": round(g_ms, 4), "value": throughput(world, B, g_ms),
+                             "bytes_into_rank0_per_step": sum(t.numel() * t.element_size() for t in fn()) * (world - 1)}
+            del bufs
+
     # ---- per-kernel pass (same steps again, every launch bracketed by CUDA events on the launching stream) ----
     eng.set_profile(True)
     eng.profile_report(reset=True)
@@ -438,6 +466,8 @@ def run_ours(args, rank, local_rank, world):
         "roofline": roofline,
         "kernels": breakdown,
     }
+    if gathered is not None:
+        out["outputs_gathered_to_rank0"] = gathered
     if world == 1 and not args.no_cpu_baseline:
         m_cpu, f_cpu = sets[0][0][:CPU_SAMPLE_B].cpu(), sets[0][1][:CPU_SAMPLE_B].cpu()
         v, cores, best, reps = cpu_reference_throughput(model.state_dict(), m_cpu, f_cpu)
