@@ -358,30 +358,68 @@ def run_ours(args, rank, local_rank, world):
     # ---- N > 1: the same steps with the outputs collected on rank 0 (the headline keeps every rank's
     # outputs on its own GPU; a consumer that wants them in one place pays an NCCL gather over NVLink).  Two wire
     # formats: masks + separated in fp32 (what the reference returns), and masks only in bf16 (rank 0 holds the
-    # mixture and can rebuild `separated = masks * mixed`).  Not overlapped with the next step's kernels.
+    # mixture and can rebuild `separated = masks * mixed`); each measured back to back and with the gather of step i
+    # overlapped with the kernels of step i+1 (two output buffer sets).
     gathered = None
     if world > 1:
         gathered = {}
-        for tag, fn in (("masks+separated fp32", lambda: (masks, sep)), ("masks bf16", lambda: (masks.to(torch.bfloat16),))):
-            bufs = [[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in fn()]
-            def gstep(i):
-                step(i)
-                for t, gl in zip(fn(), bufs):
-                    dist.gather(t, gl, dst=0)
-            for i in range(3):
-                gstep(i)
-            barrier()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_g = max(5, min(args.steps, 50))
-            g0.record(stream)
-            for i in range(n_g):
-                gstep(i)
-            g1.record(stream)
-            barrier()
-            g_ms = max_over_ranks(g0.elapsed_time(g1)) / n_g
-            gathered[tag] = {"ms_per_step": round(g_ms, 4), "value": throughput(world, B, g_ms),
-                             "bytes_into_rank0_per_step": sum(t.numel() * t.element_size() for t in fn()) * (world - 1)}
-            del bufs
+        sep2, masks2 = torch.empty_like(sep), torch.empty_like(masks)
+        out_sets = [(sep, masks), (sep2, masks2)]
+
+        def step_into(i, o):
+            mixed, frames = sets[i % n_sets]
+            rc = eng.lib.avsep_forward(eng.h, mixed.data_ptr(), frames.data_ptr(), B, T_FRAMES, N_FRAMES, FRAME_HW,
+                                       FRAME_HW, out_sets[o][0].data_ptr(), out_sets[o][1].data_ptr(), None, 0,
+                                       C.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError(eng.lib.avsep_last_error(eng.h).decode())
+
+        wires = (("masks+separated fp32", lambda o: (out_sets[o][1], out_sets[o][0])),
+                 ("masks bf16", lambda o: (out_sets[o][1].to(torch.bfloat16),)))
+        for tag, pick in wires:
+            for overlapped in (False, True):
+                # destination lists on rank 0, one per output buffer set
+                dst = [[[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in pick(o)] for o in (0, 1)]
+                pending = [None, None]
+
+                def gstep(i):
+                    o = i & 1 if overlapped else 0
+                    if pending[o] is not None:                 # the gather that last read this buffer set
+                        for w in pending[o]:
+                            w.wait()
+                    step_into(i, o)
+                    works = [dist.gather(t, gl, dst=0, async_op=True) for t, gl in zip(pick(o), dst[o])]
+                    if overlapped:
+                        pending[o] = works                     # the next step (other buffer set) runs under it
+                    else:
+                        for w in works:
+                            w.wait()
+
+                def drain():
+                    for o in (0, 1):
+                        if pending[o] is not None:
+                            for w in pending[o]:
+                                w.wait()
+                            pending[o] = None
+
+                for i in range(4):
+                    gstep(i)
+                drain()
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_g = max(6, min(args.steps, 50))
+                g0.record(stream)
+                for i in range(n_g):
+                    gstep(i)
+                drain()
+                g1.record(stream)
+                barrier()
+                g_ms = max_over_ranks(g0.elapsed_time(g1)) / n_g
+                gathered[tag + (", overlapped with the next step" if overlapped else "")] = {
+                    "ms_per_step": round(g_ms, 4), "value": throughput(world, B, g_ms),
+                    "bytes_into_rank0_per_step": sum(t.numel() * t.element_size() for t in pick(0)) * (world - 1)}
+                del dst
+        del sep2, masks2
 
     # ---- per-kernel pass (same steps again, every launch bracketed by CUDA events on the launching stream) ----
     eng.set_profile(True)
