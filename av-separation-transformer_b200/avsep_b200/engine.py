@@ -302,6 +302,46 @@ class Engine:
         self._check(rc, "avsep_eval_snr")
         return in_snr, out_snr, perm, si
 
+    def stft(self, waves, n_fft: int = 512, hop_length: int = 128, want_mag: bool = True):
+        """avsep_stft: (B, L) float32 waveforms -> complex64 (B, F, T) with the framing of the reference's
+        SyntheticAVDataset._stft (dataset.py:122-135) and, optionally, its float32 magnitude (the model input)."""
+        dev = torch.device("cuda", self.device)
+        if waves.device != dev or waves.dtype != torch.float32 or not waves.is_contiguous() or waves.dim() != 2:
+            raise ValueError("stft: waves must be a contiguous float32 (B, L) tensor on the engine device")
+        B, L = waves.shape
+        F, T = n_fft // 2 + 1, 1 + L // hop_length
+        spec = torch.empty(B, F, T, device=dev, dtype=torch.complex64)
+        mag = torch.empty(B, F, T, device=dev, dtype=torch.float32) if want_mag else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_stft(self.h, waves.data_ptr(), B, L, n_fft, hop_length, spec.data_ptr(),
+                                     mag.data_ptr() if want_mag else None, self._stream())
+        self._check(rc, "avsep_stft")
+        return spec, mag
+
+    def istft(self, spec, masks=None, length: int = None, n_fft: int = 512, hop_length: int = 128):
+        """avsep_istft: complex64 (B, F, T) mixture spectrum (+ (B, S, F, T) float32 masks) -> (B, S, L) float32
+        waveforms by weighted overlap-add; without masks the plain inverse, (B, 1, L)."""
+        dev = torch.device("cuda", self.device)
+        if spec.device != dev or spec.dtype != torch.complex64 or not spec.is_contiguous() or spec.dim() != 3:
+            raise ValueError("istft: spec must be a contiguous complex64 (B, F, T) tensor on the engine device")
+        B, F, T = spec.shape
+        if F != n_fft // 2 + 1:
+            raise ValueError("istft: spec has %d bins, n_fft=%d needs %d" % (F, n_fft, n_fft // 2 + 1))
+        S = 1
+        if masks is not None:
+            if masks.device != dev or masks.dtype != torch.float32 or not masks.is_contiguous() or masks.dim() != 4:
+                raise ValueError("istft: masks must be a contiguous float32 (B, S, F, T) tensor on the engine device")
+            S = masks.shape[1]
+            if (masks.shape[0], masks.shape[2], masks.shape[3]) != (B, F, T):
+                raise ValueError("istft: masks / spec shape mismatch")
+        L = (T - 1) * hop_length if length is None else int(length)
+        waves = torch.empty(B, S, L, device=dev, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_istft(self.h, spec.data_ptr(), masks.data_ptr() if masks is not None else None, B, S,
+                                      T, n_fft, hop_length, L, waves.data_ptr(), self._stream())
+        self._check(rc, "avsep_istft")
+        return waves
+
     def set_option(self, name: str, value: int):
         """Execution options: 'fuse_ln' (0/1), 'host_chunk' (utterances per pipeline chunk of forward_host)."""
         self._check(self.lib.avsep_set_option(self.h, name.encode(), int(value)), "avsep_set_option")

@@ -254,6 +254,20 @@ class AVSeparationTransformer(_InferenceOnly):
             return self._get_engine(mixed_spec.device).forward(mixed_spec, lip_frames)
         return self._get_engine(torch.device(self.host_device)).forward_host(mixed_spec, lip_frames)
 
+    def separate_waveforms(self, mixed_wave: torch.Tensor, lip_frames: torch.Tensor, n_fft: int = None,
+                           hop_length: int = 128):
+        """Waveform in, waveforms out (not a reference method: the reference lists phase / iSTFT reconstruction as
+        missing, README.md:140).  mixed_wave (B, L) float32 CUDA -> (B, S, L): complex STFT with the framing of
+        SyntheticAVDataset._stft (dataset.py:122-135), forward on its magnitude, masks applied to the complex
+        mixture, weighted overlap-add inverse.  Also returns the masks."""
+        if not mixed_wave.is_cuda:
+            raise ValueError("separate_waveforms: mixed_wave must be a CUDA tensor")
+        n_fft = 2 * (self.config.freq_bins - 1) if n_fft is None else n_fft
+        eng = self._get_engine(mixed_wave.device)
+        spec, mag = eng.stft(mixed_wave, n_fft, hop_length)
+        _, masks = eng.forward(mag, lip_frames)
+        return eng.istft(spec, masks, mixed_wave.shape[1], n_fft, hop_length), masks
+
     @property
     def engine(self) -> Engine:
         """The live engine (after the first forward / prepack), for debug snapshots and launch counts."""

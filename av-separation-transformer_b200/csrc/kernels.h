@@ -155,4 +155,10 @@ const char* launch_synth(cudaStream_t s, const SynthProblem& p);
 const char* launch_eval_snr(cudaStream_t s, const float* separated, const float* targets, const float* mixed, int B,
                             int S, int FT, double* input_snr, double* output_snr, int* best_perm, double* si_snr);
 
+// ---- waveform side (waveform.cu): complex STFT with the reference's framing, masked inverse STFT ----
+const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L, int nfft, int hop, float* spec,
+                                float* mag);
+const char* launch_istft_masked(cudaStream_t s, const float* spec, const float* masks, int B, int S, int T, int nfft,
+                                int hop, int L, float* waves);
+
 }  // namespace avsep

@@ -205,6 +205,25 @@ AVSEP_API int avsep_eval_snr(avsep_handle* h, const float* separated, const floa
                              int32_t B, int32_t S, int32_t F, int32_t T, double* input_snr, double* output_snr,
                              int32_t* best_perm, double* si_snr, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The waveform side.  The reference has no counterpart: it works on magnitude
+ * spectrograms only and lists "STFT phase / iSTFT reconstruction" as missing (reference README.md:140).  The
+ * analysis keeps the framing of SyntheticAVDataset._stft (dataset.py:122-135): frame i starts at i*hop_length (no
+ * centring), is zero-padded past the end of the signal and weighted by np.hanning(n_fft); T = 1 + L / hop_length.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* waves (B, L) float32 -> spec (B, F, T) complex64 (interleaved re, im), F = n_fft/2 + 1; mag (B, F, T) float32 or
+ * NULL receives |spec|, bit-identical to the mixed_spec avsep_synth_batch produces from the same samples. */
+AVSEP_API int avsep_stft(avsep_handle* h, const float* waves, int32_t B, int32_t L, int32_t n_fft, int32_t hop_length,
+                         float* spec, float* mag, void* cuda_stream);
+
+/* Masked inverse: waves[b,s,n] = sum_i w[n-i*hop] * irfft(masks[b,s,:,i] * spec[b,:,i])[n-i*hop] / sum_i w^2[n-i*hop]
+ * (weighted overlap-add; numpy irfft semantics; samples with a zero window sum - n = 0 - are 0).
+ *   spec (B, F, T) complex64; masks (B, S, F, T) float32, or NULL with S = 1 for the plain inverse;
+ *   waves (B, S, L) float32 with L <= (T-1)*hop_length + n_fft.  avsep_istft(avsep_stft(x)) == x for n >= 1. */
+AVSEP_API int avsep_istft(avsep_handle* h, const float* spec, const float* masks, int32_t B, int32_t S, int32_t T,
+                          int32_t n_fft, int32_t hop_length, int32_t L, float* waves, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
