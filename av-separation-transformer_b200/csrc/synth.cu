@@ -301,8 +301,12 @@ const char* launch_synth(cudaStream_t s, const SynthProblem& p) {
                                                                  p.duration / static_cast<double>(p.n), p.waves);
   const size_t smem = static_cast<size_t>(p.nfft) * sizeof(double) +
                       (3 * static_cast<size_t>(p.nfft) + static_cast<size_t>(F) * TG) * sizeof(float);
-  stft_mag_kernel<<<dim3((T + TG - 1) / TG, p.B * (p.S + 1)), p.nfft / 2, smem, s>>>(
-      p.waves, p.n, p.nfft, log2n, p.hop, T, F, p.S, p.mixed_spec, p.clean_specs);
+  if (p.nfft == 512 && p.B * (p.S + 1) <= 65535) {   // the reference's default geometry: register radix-8 transform
+    if (const char* e = launch_stft512_synth(s, p.waves, p.B, p.S, p.n, p.hop, p.mixed_spec, p.clean_specs)) return e;
+  } else {
+    stft_mag_kernel<<<dim3((T + TG - 1) / TG, p.B * (p.S + 1)), p.nfft / 2, smem, s>>>(
+        p.waves, p.n, p.nfft, log2n, p.hop, T, F, p.S, p.mixed_spec, p.clean_specs);
+  }
   lip_frames_kernel<<<dim3(p.nf, p.S, p.B), 256, 0, s>>>(p.waves, p.noise, p.S, p.n, p.nf, p.Hh, p.Ww, p.lip_frames);
   return cudaGetLastError() == cudaSuccess ? nullptr : "synth: launch failed";
 }

@@ -14,6 +14,7 @@
 // ifft(z) = a + ib for real a, b).  fp32 shared-memory radix-2 transforms, fp64 window: HBM/latency-bound CUDA-core
 // work, no tensor cores.
 #include "common.cuh"
+#include "fft512.cuh"
 #include "kernels.h"
 
 namespace avsep {
@@ -203,6 +204,160 @@ __global__ void istft_masked_kernel(const float2* __restrict__ spec, const float
   }
 }
 
+// ---- n_fft = 512 (the reference's default geometry): register radix-8 transforms, fft512.cuh ----------------------
+//
+// 256 threads = 4 groups of 64; each group transforms one frame pair, so a CTA covers 8 frames in one pass.
+
+// grid (ceil(T/8), number of signals).  Output selection: S1 == 0 -> spec / mag indexed by signal; S1 > 0 (the
+// synthesis layout, signals (B, S1) with the mixture first) -> magnitudes only, mag = mixed_spec (B, F, T) and
+// mag2 = clean_specs (B, S1-1, F, T) or null.
+__global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ waves, int n, int hop, int T,
+                                                      float2* __restrict__ spec, float* __restrict__ mag,
+                                                      float* __restrict__ mag2, int S1) {
+  constexpr int NF = 512, F = 257;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* win = reinterpret_cast<double*>(sm_raw);                 // [512]
+  float2* tw = reinterpret_cast<float2*>(win + NF);                // [512]
+  float2* stage = tw + NF;                                         // [F][8]
+  float* xch = reinterpret_cast<float*>(stage + F * 8);            // [4 groups][2 planes][FFT512_XCH]
+  const int sig = blockIdx.y;
+  const int t0 = blockIdx.x * 8;
+  const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+  const float* x = waves + static_cast<size_t>(sig) * n;
+  fft512_fill_twiddles(tw, tid, 256);
+  win[tid] = hann(tid, NF);
+  win[tid + 256] = hann(tid + 256, NF);
+  __syncthreads();
+  const int ng = min(8, T - t0);
+  const int ta = t0 + 2 * g;
+  const bool has_a = 2 * g < ng, has_b = 2 * g + 1 < ng;
+  float* xr = xch + g * 2 * FFT512_XCH;
+  float* xi = xr + FFT512_XCH;
+  float2 v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = t + 64 * q;
+    const int sa = ta * hop + k, sb = sa + hop;
+    const float va = (has_a && sa < n) ? x[sa] : 0.f;
+    const float vb = (has_b && sb < n) ? x[sb] : 0.f;
+    const double w = win[k];
+    v[q] = make_float2(static_cast<float>(static_cast<double>(va) * w),     // float32 `frame *= window`
+                       static_cast<float>(static_cast<double>(vb) * w));
+  }
+  fft512_regs<-1>(v, t, xr, xi, tw);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {          // natural order: consecutive threads -> k = hi + 8 lo + 64 i
+    const int k = fft512_out_index(t, i);
+    xr[k] = v[i].x; xi[k] = v[i].y;
+  }
+  __syncthreads();
+  for (int f = t; f < F; f += 64) {
+    const int fn = (NF - f) & (NF - 1);
+    const float zr = xr[f], zi = xi[f], yr = xr[fn], yi = xi[fn];
+    if (has_a) stage[f * 8 + 2 * g] = make_float2(0.5f * (zr + yr), 0.5f * (zi - yi));       // A = (Z + conj Z~)/2
+    if (has_b) stage[f * 8 + 2 * g + 1] = make_float2(0.5f * (zi + yi), 0.5f * (yr - zr));   // B = (Z - conj Z~)/2i
+  }
+  __syncthreads();
+  float* m_out = mag;
+  size_t base = static_cast<size_t>(sig) * F * T;
+  if (S1 > 0) {
+    const int b = sig / S1, j = sig - b * S1;
+    m_out = j == 0 ? mag : mag2;
+    base = j == 0 ? static_cast<size_t>(b) * F * T : (static_cast<size_t>(b) * (S1 - 1) + (j - 1)) * F * T;
+  }
+  for (int e = tid; e < F * 8; e += 256) {
+    const int f = e >> 3, gg = e & 7;
+    if (gg >= ng) continue;
+    const size_t o = base + static_cast<size_t>(f) * T + t0 + gg;
+    const float2 z = stage[e];
+    if (spec) spec[o] = z;
+    if (m_out) m_out[o] = 0.5f * hypotf(2.0f * z.x, 2.0f * z.y);
+  }
+}
+
+// grid (ceil(L/CH), S, B), CH = (9 - R) * hop with R = ceil(512 / hop) <= 8: exactly the (at most) 8 frames
+// i_first .. i_first + 7 overlap the CTA's samples.  Their masked half spectra are staged once (row-contiguous
+// loads), each group inverts one pair, the 8 time frames replace the staged tile, and every output sample gathers
+// its frames in ascending order (deterministic, no atomics).
+__global__ void __launch_bounds__(256) istft512_kernel(const float2* __restrict__ spec, const float* __restrict__ masks,
+                                                       int S, int hop, int T, int L, int CH, int R,
+                                                       float* __restrict__ out) {
+  constexpr int NF = 512, F = 257, NBP8 = 9;   // pitch 18 words: conflict-free 64-bit accesses down a column
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double* win = reinterpret_cast<double*>(sm_raw);                 // [512]
+  float2* tw = reinterpret_cast<float2*>(win + NF);                // [512]
+  float* xch = reinterpret_cast<float*>(tw + NF);                  // [4][2][FFT512_XCH]
+  float2* tile = reinterpret_cast<float2*>(xch + 8 * FFT512_XCH);  // [F][NBP8]; later float frames[8][512]
+  float* frames = reinterpret_cast<float*>(tile);
+  const int b = blockIdx.z, s = blockIdx.y;
+  const int n0 = blockIdx.x * CH;
+  const int n1 = min(n0 + CH, L);
+  const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
+  const int i_first = n0 / hop - (R - 1);                          // may be negative: those frames do not exist
+  fft512_fill_twiddles(tw, tid, 256);
+  win[tid] = hann(tid, NF);
+  win[tid + 256] = hann(tid + 256, NF);
+  const float2* X = spec + static_cast<size_t>(b) * F * T;
+  const float* Mk = masks ? masks + (static_cast<size_t>(b) * S + s) * F * T : nullptr;
+  for (int e = tid; e < F * 8; e += 256) {
+    const int f = e >> 3, j = e & 7;
+    const int fr = i_first + j;
+    float2 z = make_float2(0.f, 0.f);
+    if (fr >= 0 && fr < T) {
+      const size_t o = static_cast<size_t>(f) * T + fr;
+      z = X[o];
+      if (Mk) { const float m = Mk[o]; z.x *= m; z.y *= m; }
+      if (f == 0 || f == NF / 2) z.y = 0.f;                        // irfft ignores the imaginary part of DC / Nyquist
+    }
+    tile[f * NBP8 + j] = z;
+  }
+  __syncthreads();
+  float* xr = xch + g * 2 * FFT512_XCH;
+  float* xi = xr + FFT512_XCH;
+  float2 v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {          // Z[k] = A[k] + i B[k], Hermitian extensions of the pair (2g, 2g+1)
+    const int k = t + 64 * q;
+    const int f = k <= NF / 2 ? k : NF - k;
+    const float sgn = k <= NF / 2 ? 1.f : -1.f;
+    const float2 a = tile[f * NBP8 + 2 * g];
+    const float2 bb = tile[f * NBP8 + 2 * g + 1];
+    v[q] = make_float2(a.x - sgn * bb.y, sgn * a.y + bb.x);
+  }
+  fft512_regs<1>(v, t, xr, xi, tw);      // its barriers also order the tile reads above before the overwrite below
+  const float inv_n = 1.0f / static_cast<float>(NF);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = fft512_out_index(t, i);
+    frames[(2 * g) * NF + k] = v[i].x * inv_n;
+    frames[(2 * g + 1) * NF + k] = v[i].y * inv_n;
+  }
+  __syncthreads();
+  float* y = out + (static_cast<size_t>(b) * S + s) * L;
+  for (int i = tid; i < n1 - n0; i += 256) {
+    const int n = n0 + i;
+    double acc = 0.0, wss = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int fr = i_first + j;
+      const int k = n - fr * hop;
+      if (fr >= 0 && fr < T && k >= 0 && k < NF) {
+        const double w = win[k];
+        acc += w * static_cast<double>(frames[j * NF + k]);
+        wss += w * w;
+      }
+    }
+    y[n] = wss > 1e-11 ? static_cast<float>(acc / wss) : 0.f;
+  }
+}
+
+constexpr size_t kStft512Smem = 512 * sizeof(double) + 512 * sizeof(float2) + 257 * 8 * sizeof(float2) +
+                                8 * FFT512_XCH * sizeof(float);
+constexpr size_t kIstft512Smem = 512 * sizeof(double) + 512 * sizeof(float2) + 8 * FFT512_XCH * sizeof(float) +
+                                 257 * 9 * sizeof(float2);
+static_assert(257 * 9 * sizeof(float2) >= 8 * 512 * sizeof(float), "the time frames must fit in the staged tile");
+
 bool fft_geometry_ok(int nfft, int hop, int* log2n) {
   if (nfft < 8 || nfft > 2048 || (nfft & (nfft - 1)) || hop < 1 || hop > nfft) return false;
   *log2n = 0;
@@ -218,6 +373,11 @@ const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L
   if (B <= 0 || L <= 0) return "stft: empty problem";
   if (!fft_geometry_ok(nfft, hop, &log2n)) return "stft: n_fft must be a power of two in [8, 2048], 1 <= hop <= n_fft";
   const int T = 1 + L / hop, F = nfft / 2 + 1;
+  if (nfft == 512 && B <= 65535) {
+    stft512_kernel<<<dim3((T + 7) / 8, B), 256, kStft512Smem, s>>>(waves, L, hop, T, reinterpret_cast<float2*>(spec),
+                                                                   mag, nullptr, 0);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "stft: launch failed";
+  }
   const size_t smem = static_cast<size_t>(nfft) * sizeof(double) + 3 * static_cast<size_t>(nfft) * sizeof(float) +
                       static_cast<size_t>(F) * TGA * sizeof(float2);
   static size_t granted = 48 * 1024;
@@ -231,6 +391,17 @@ const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L
   return cudaGetLastError() == cudaSuccess ? nullptr : "stft: launch failed";
 }
 
+// Magnitude-only analysis of the synthesis layout (signals (B, S+1, n), mixture first) for n_fft = 512: used by
+// launch_synth instead of its radix-2 kernel.
+const char* launch_stft512_synth(cudaStream_t s, const float* waves, int B, int S, int n, int hop, float* mixed_spec,
+                                 float* clean_specs) {
+  const int T = 1 + n / hop;
+  if (static_cast<long long>(B) * (S + 1) > 65535) return "synth: batch * (speakers + 1) above 65535";
+  stft512_kernel<<<dim3((T + 7) / 8, B * (S + 1)), 256, kStft512Smem, s>>>(waves, n, hop, T, nullptr, mixed_spec,
+                                                                           clean_specs, S + 1);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "synth: stft launch failed";
+}
+
 const char* launch_istft_masked(cudaStream_t s, const float* spec, const float* masks, int B, int S, int T, int nfft,
                                 int hop, int L, float* waves) {
   int log2n;
@@ -240,6 +411,12 @@ const char* launch_istft_masked(cudaStream_t s, const float* spec, const float* 
   if (masks == nullptr && S != 1) return "istft: without masks there is one output per utterance (S = 1)";
   if (static_cast<long long>(T - 1) * hop + nfft < L) return "istft: the frames do not reach the requested length";
   const int F = nfft / 2 + 1;
+  if (nfft == 512 && hop >= 64) {
+    const int R = (512 + hop - 1) / hop, CH = (9 - R) * hop;
+    istft512_kernel<<<dim3((L + CH - 1) / CH, S, B), 256, kIstft512Smem, s>>>(
+        reinterpret_cast<const float2*>(spec), masks, S, hop, T, L, CH, R, waves);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "istft: launch failed";
+  }
   int tg = 4096 / hop;
   tg = tg < 1 ? 1 : (tg > 8 ? 8 : tg);
   const int CH = tg * hop;

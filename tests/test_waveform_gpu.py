@@ -105,6 +105,24 @@ def test_istft_ignores_imaginary_dc_and_nyquist_like_irfft(eng):
     assert (got[:, :, 0] == 0).all() and (got[:, :, L - 1] == 0).all()
 
 
+@pytest.mark.parametrize("hop,L", [(128, 1000), (100, 2696), (64, 1500), (512, 4000), (300, 1000), (32, 900), (129, 127)])
+def test_n_fft_512_geometries_match_oracle(eng, hop, L):
+    """n_fft = 512 takes the register radix-8 kernels for hop >= 64 (any hop for the analysis) and the radix-2 ones
+    below; hops that do not divide n_fft, a hop of a whole frame, and a signal shorter than one hop."""
+    rng = np.random.default_rng(hop)
+    x = (0.3 * rng.standard_normal((2, L))).astype(np.float32)
+    spec, mag = eng.stft(torch.from_numpy(x).cuda(), 512, hop)
+    T = 1 + L // hop
+    assert spec.shape == (2, 257, T)
+    masks = rng.uniform(0, 1, (2, 2, 257, T)).astype(np.float32)
+    got = eng.istft(spec, torch.from_numpy(masks).cuda(), L, 512, hop).cpu().numpy()
+    for b in range(2):
+        ref = wo.stft_complex(x[b], 512, hop)
+        assert np.abs(spec[b].cpu().numpy() - ref).max() <= TOL_SPEC_REL * np.abs(ref).max()
+        want = wo.istft_masked(spec[b].cpu().numpy(), masks[b], L, 512, hop)
+        assert _wave_err(got[b], want, 512, hop) <= TOL_WAVE
+
+
 @pytest.mark.parametrize("B,L,n_fft,hop", [(256, 8000, 512, 128), (4, 160000, 512, 128), (3, 5000, 2048, 2048), (5, 777, 8, 3)])
 def test_round_trip_and_mask_linearity_at_size(eng, B, L, n_fft, hop):
     g = torch.Generator(device="cuda").manual_seed(3)
