@@ -380,12 +380,9 @@ const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L
   }
   const size_t smem = static_cast<size_t>(nfft) * sizeof(double) + 3 * static_cast<size_t>(nfft) * sizeof(float) +
                       static_cast<size_t>(F) * TGA * sizeof(float2);
-  static size_t granted = 48 * 1024;
-  if (smem > granted) {
-    if (cudaFuncSetAttribute(stft_complex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return "stft: cannot raise the shared-memory limit";
-    granted = 227 * 1024;
-  }
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(stft_complex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return "stft: cannot raise the shared-memory limit";
   stft_complex_kernel<<<dim3((T + TGA - 1) / TGA, B), nfft / 2, smem, s>>>(waves, L, nfft, log2n, hop, T, F,
                                                                           reinterpret_cast<float2*>(spec), mag);
   return cudaGetLastError() == cudaSuccess ? nullptr : "stft: launch failed";
@@ -423,12 +420,10 @@ const char* launch_istft_masked(cudaStream_t s, const float* spec, const float* 
   const size_t smem = (static_cast<size_t>(nfft) + CH) * sizeof(double) + static_cast<size_t>(F) * NBP * sizeof(float2) +
                       3 * static_cast<size_t>(nfft) * sizeof(float);
   if (smem > 227 * 1024) return "istft: geometry needs more than 227 KB of shared memory";
-  static size_t granted = 48 * 1024;
-  if (smem > granted) {
-    if (cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return "istft: cannot raise the shared-memory limit";
-    granted = 227 * 1024;
-  }
+  // per call, not cached: the attribute is per device and a process may hold engines on several
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return "istft: cannot raise the shared-memory limit";
   istft_masked_kernel<<<dim3((L + CH - 1) / CH, S, B), nfft / 2, smem, s>>>(
       reinterpret_cast<const float2*>(spec), masks, S, nfft, log2n, hop, T, F, L, CH, waves);
   return cudaGetLastError() == cudaSuccess ? nullptr : "istft: launch failed";
