@@ -656,6 +656,7 @@ int avsep_create(const avsep_config* cfg, avsep_handle** out) {
   if (prop.major != 10) return fail(nullptr, "avsep_create: kernels are built for sm_100a (B200) only");
   if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, "avsep_create: cudaSetDevice failed");
   if (const char* e = gemm_init()) return fail(nullptr, e);
+  if (const char* e = fft512_init_tables()) return fail(nullptr, e);
   avsep_handle* h = new avsep_handle();
   h->cfg = *cfg;
   h->Fp = (cfg->freq_bins + 7) / 8 * 8;

@@ -54,14 +54,25 @@ __device__ __forceinline__ void dft8(float2 (&a)[8]) {
   a[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
 }
 
-// tw[m] = (cos(2 pi m / 512), sin(2 pi m / 512)), m = 0 .. 511, in shared memory
+// Twiddle tables in shared memory, laid out the way the passes read them (conflict free): pass 1 reads
+// tw[p * 64 + t] = W_512^(t p) with consecutive t; pass 2 reads tw[512 + t2 * 9 + p2] = W_64^(t2 p2) (8 distinct
+// entries per access, pitch 18 words).  Stored as (cos, sin) of the positive angle.
+constexpr int FFT512_TW = 512 + 72;   // float2 entries
+
 __device__ __forceinline__ void fft512_fill_twiddles(float2* tw, int tid, int nthreads) {
-  for (int m = tid; m < 512; m += nthreads) {
+  for (int m = tid; m < FFT512_TW; m += nthreads) {
+    int num;                                        // angle = 2 pi num / 512
+    if (m < 512) num = (m >> 6) * (m & 63);
+    else { const int r = m - 512; num = 8 * (r / 9) * (r % 9); }
     float sv, cv;
-    sincospif(static_cast<float>(m) / 256.0f, &sv, &cv);
+    sincospif(static_cast<float>(num & 511) / 256.0f, &sv, &cv);
     tw[m] = make_float2(cv, sv);
   }
 }
+
+// Natural-order index k -> padded position (4 floats of padding per 32): the register layout after the last pass
+// (k = hi + 8 lo + 64 i) then lands on 32 distinct banks, and consecutive k stay conflict free.  < FFT512_XCH.
+__device__ __forceinline__ int fft512_nat(int k) { return k + ((k >> 5) << 2); }
 
 template <int SGN>
 __device__ __forceinline__ float2 twiddle_mul(float2 z, float2 w) {   // z * (w.x + SGN i w.y)
@@ -74,7 +85,7 @@ __device__ __forceinline__ void fft512_regs(float2 (&v)[8], int t, float* xr, fl
   dft8<SGN>(v);
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
-    const float2 z = p == 0 ? v[0] : twiddle_mul<SGN>(v[p], tw[t * p]);
+    const float2 z = p == 0 ? v[0] : twiddle_mul<SGN>(v[p], tw[p * 64 + t]);
     xr[p * 72 + t] = z.x; xi[p * 72 + t] = z.y;
   }
   __syncthreads();
@@ -85,7 +96,7 @@ __device__ __forceinline__ void fft512_regs(float2 (&v)[8], int t, float* xr, fl
   dft8<SGN>(v);
 #pragma unroll
   for (int p2 = 0; p2 < 8; ++p2) {
-    const float2 z = p2 == 0 ? v[0] : twiddle_mul<SGN>(v[p2], tw[8 * lo * p2]);
+    const float2 z = p2 == 0 ? v[0] : twiddle_mul<SGN>(v[p2], tw[512 + lo * 9 + p2]);
     xr[hi * 72 + p2 * 9 + lo] = z.x; xi[hi * 72 + p2 * 9 + lo] = z.y;
   }
   __syncthreads();

@@ -158,6 +158,7 @@ const char* launch_eval_snr(cudaStream_t s, const float* separated, const float*
 // ---- waveform side (waveform.cu): complex STFT with the reference's framing, masked inverse STFT ----
 const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L, int nfft, int hop, float* spec,
                                 float* mag);
+const char* fft512_init_tables();   // window + twiddle tables of the n_fft = 512 kernels, once per device (avsep_create)
 const char* launch_stft512_synth(cudaStream_t s, const float* waves, int B, int S, int n, int hop, float* mixed_spec,
                                  float* clean_specs);
 const char* launch_istft_masked(cudaStream_t s, const float* spec, const float* masks, int B, int S, int T, int nfft,

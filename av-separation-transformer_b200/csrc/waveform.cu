@@ -206,7 +206,21 @@ __global__ void istft_masked_kernel(const float2* __restrict__ spec, const float
 
 // ---- n_fft = 512 (the reference's default geometry): register radix-8 transforms, fft512.cuh ----------------------
 //
-// 256 threads = 4 groups of 64; each group transforms one frame pair, so a CTA covers 8 frames in one pass.
+// 256 threads = 4 groups of 64; each group transforms one frame pair, so a CTA covers 8 frames in one pass.  The fp64
+// Hann window and the twiddle tables live in device globals filled once per device (fft512_init_tables, called by
+// avsep_create): evaluating 512 fp64 cosines per CTA was a fifth of the instructions of these kernels.
+__device__ double g_hann512[512];
+__device__ float2 g_tw512[FFT512_TW];
+
+__global__ void fft512_tables_kernel() {
+  const int tid = threadIdx.x;
+  for (int k = tid; k < 512; k += blockDim.x) g_hann512[k] = hann(k, 512);
+  fft512_fill_twiddles(g_tw512, tid, blockDim.x);
+}
+
+__device__ __forceinline__ void fft512_load_twiddles(float2* tw, int tid) {
+  for (int m = tid; m < FFT512_TW; m += 256) tw[m] = g_tw512[m];
+}
 
 // grid (ceil(T/8), number of signals).  Output selection: S1 == 0 -> spec / mag indexed by signal; S1 > 0 (the
 // synthesis layout, signals (B, S1) with the mixture first) -> magnitudes only, mag = mixed_spec (B, F, T) and
@@ -216,17 +230,14 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
                                                       float* __restrict__ mag2, int S1) {
   constexpr int NF = 512, F = 257;
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  double* win = reinterpret_cast<double*>(sm_raw);                 // [512]
-  float2* tw = reinterpret_cast<float2*>(win + NF);                // [512]
-  float2* stage = tw + NF;                                         // [F][8]
-  float* xch = reinterpret_cast<float*>(stage + F * 8);            // [4 groups][2 planes][FFT512_XCH]
+  float2* tw = reinterpret_cast<float2*>(sm_raw);                  // [FFT512_TW]
+  float2* stage = tw + FFT512_TW;                                  // [F][9] (pitch 9: conflict-free column writes)
+  float* xch = reinterpret_cast<float*>(stage + F * 9);            // [4 groups][2 planes][FFT512_XCH]
   const int sig = blockIdx.y;
   const int t0 = blockIdx.x * 8;
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
   const float* x = waves + static_cast<size_t>(sig) * n;
-  fft512_fill_twiddles(tw, tid, 256);
-  win[tid] = hann(tid, NF);
-  win[tid + 256] = hann(tid + 256, NF);
+  fft512_load_twiddles(tw, tid);
   __syncthreads();
   const int ng = min(8, T - t0);
   const int ta = t0 + 2 * g;
@@ -240,23 +251,23 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
     const int sa = ta * hop + k, sb = sa + hop;
     const float va = (has_a && sa < n) ? x[sa] : 0.f;
     const float vb = (has_b && sb < n) ? x[sb] : 0.f;
-    const double w = win[k];
+    const double w = g_hann512[k];
     v[q] = make_float2(static_cast<float>(static_cast<double>(va) * w),     // float32 `frame *= window`
                        static_cast<float>(static_cast<double>(vb) * w));
   }
   fft512_regs<-1>(v, t, xr, xi, tw);
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {          // natural order: consecutive threads -> k = hi + 8 lo + 64 i
-    const int k = fft512_out_index(t, i);
+  for (int i = 0; i < 8; ++i) {          // natural order (padded): k = hi + 8 lo + 64 i
+    const int k = fft512_nat(fft512_out_index(t, i));
     xr[k] = v[i].x; xi[k] = v[i].y;
   }
   __syncthreads();
   for (int f = t; f < F; f += 64) {
-    const int fn = (NF - f) & (NF - 1);
-    const float zr = xr[f], zi = xi[f], yr = xr[fn], yi = xi[fn];
-    if (has_a) stage[f * 8 + 2 * g] = make_float2(0.5f * (zr + yr), 0.5f * (zi - yi));       // A = (Z + conj Z~)/2
-    if (has_b) stage[f * 8 + 2 * g + 1] = make_float2(0.5f * (zi + yi), 0.5f * (yr - zr));   // B = (Z - conj Z~)/2i
+    const int kf = fft512_nat(f), kn = fft512_nat((NF - f) & (NF - 1));
+    const float zr = xr[kf], zi = xi[kf], yr = xr[kn], yi = xi[kn];
+    if (has_a) stage[f * 9 + 2 * g] = make_float2(0.5f * (zr + yr), 0.5f * (zi - yi));       // A = (Z + conj Z~)/2
+    if (has_b) stage[f * 9 + 2 * g + 1] = make_float2(0.5f * (zi + yi), 0.5f * (yr - zr));   // B = (Z - conj Z~)/2i
   }
   __syncthreads();
   float* m_out = mag;
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(256) stft512_kernel(const float* __restrict__ 
     const int f = e >> 3, gg = e & 7;
     if (gg >= ng) continue;
     const size_t o = base + static_cast<size_t>(f) * T + t0 + gg;
-    const float2 z = stage[e];
+    const float2 z = stage[f * 9 + gg];
     if (spec) spec[o] = z;
     if (m_out) m_out[o] = 0.5f * hypotf(2.0f * z.x, 2.0f * z.y);
   }
@@ -285,32 +296,45 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float2* __restrict_
                                                        float* __restrict__ out) {
   constexpr int NF = 512, F = 257, NBP8 = 9;   // pitch 18 words: conflict-free 64-bit accesses down a column
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  double* win = reinterpret_cast<double*>(sm_raw);                 // [512]
-  float2* tw = reinterpret_cast<float2*>(win + NF);                // [512]
-  float* xch = reinterpret_cast<float*>(tw + NF);                  // [4][2][FFT512_XCH]
-  float2* tile = reinterpret_cast<float2*>(xch + 8 * FFT512_XCH);  // [F][NBP8]; later float frames[8][512]
+  float2* tw = reinterpret_cast<float2*>(sm_raw);                  // [FFT512_TW]
+  float* xch = reinterpret_cast<float*>(tw + FFT512_TW);           // [4][2][FFT512_XCH]
+  float2* tile = reinterpret_cast<float2*>(xch + 8 * FFT512_XCH);  // [F][NBP8]; later float frames[8][FFT512_XCH]
   float* frames = reinterpret_cast<float*>(tile);
   const int b = blockIdx.z, s = blockIdx.y;
   const int n0 = blockIdx.x * CH;
   const int n1 = min(n0 + CH, L);
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
   const int i_first = n0 / hop - (R - 1);                          // may be negative: those frames do not exist
-  fft512_fill_twiddles(tw, tid, 256);
-  win[tid] = hann(tid, NF);
-  win[tid + 256] = hann(tid + 256, NF);
+  fft512_load_twiddles(tw, tid);
   const float2* X = spec + static_cast<size_t>(b) * F * T;
   const float* Mk = masks ? masks + (static_cast<size_t>(b) * S + s) * F * T : nullptr;
-  for (int e = tid; e < F * 8; e += 256) {
-    const int f = e >> 3, j = e & 7;
+  {
+    // thread -> (frame column j, rows f0 + 32 it): 8 consecutive threads read the 64 contiguous bytes of one bin's
+    // frames; loads are issued three rows ahead of their use so that six are in flight per thread
+    const int j = tid & 7, f0 = tid >> 3;
     const int fr = i_first + j;
-    float2 z = make_float2(0.f, 0.f);
-    if (fr >= 0 && fr < T) {
-      const size_t o = static_cast<size_t>(f) * T + fr;
-      z = X[o];
-      if (Mk) { const float m = Mk[o]; z.x *= m; z.y *= m; }
-      if (f == 0 || f == NF / 2) z.y = 0.f;                        // irfft ignores the imaginary part of DC / Nyquist
+    const bool fr_ok = fr >= 0 && fr < T;
+    const float2* Xp = X + (fr_ok ? fr : 0);
+    const float* Mp = Mk ? Mk + (fr_ok ? fr : 0) : nullptr;
+#pragma unroll
+    for (int it0 = 0; it0 < 9; it0 += 3) {
+      float2 z[3];
+      float m[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int f = f0 + 32 * (it0 + u);
+        const bool ok = fr_ok && f < F;
+        z[u] = ok ? __ldg(Xp + static_cast<size_t>(f) * T) : make_float2(0.f, 0.f);
+        m[u] = (ok && Mp) ? __ldg(Mp + static_cast<size_t>(f) * T) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int f = f0 + 32 * (it0 + u);
+        float2 zz = make_float2(z[u].x * m[u], z[u].y * m[u]);
+        if (f == 0 || f == NF / 2) zz.y = 0.f;                     // irfft ignores the imaginary part of DC / Nyquist
+        if (f < F) tile[f * NBP8 + j] = zz;
+      }
     }
-    tile[f * NBP8 + j] = z;
   }
   __syncthreads();
   float* xr = xch + g * 2 * FFT512_XCH;
@@ -329,34 +353,32 @@ __global__ void __launch_bounds__(256) istft512_kernel(const float2* __restrict_
   const float inv_n = 1.0f / static_cast<float>(NF);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int k = fft512_out_index(t, i);
-    frames[(2 * g) * NF + k] = v[i].x * inv_n;
-    frames[(2 * g + 1) * NF + k] = v[i].y * inv_n;
+    const int k = fft512_nat(fft512_out_index(t, i));
+    frames[(2 * g) * FFT512_XCH + k] = v[i].x * inv_n;
+    frames[(2 * g + 1) * FFT512_XCH + k] = v[i].y * inv_n;
   }
   __syncthreads();
   float* y = out + (static_cast<size_t>(b) * S + s) * L;
   for (int i = tid; i < n1 - n0; i += 256) {
     const int n = n0 + i;
     double acc = 0.0, wss = 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int fr = i_first + j;
+    // frames covering n: fr*hop <= n < fr*hop + 512, ascending
+    const int fr_hi = min(n / hop, T - 1);
+    const int below = n - NF + 1;
+    for (int fr = max(max(below > 0 ? (below + hop - 1) / hop : 0, i_first), 0); fr <= fr_hi; ++fr) {
       const int k = n - fr * hop;
-      if (fr >= 0 && fr < T && k >= 0 && k < NF) {
-        const double w = win[k];
-        acc += w * static_cast<double>(frames[j * NF + k]);
-        wss += w * w;
-      }
+      const double w = g_hann512[k];
+      acc += w * static_cast<double>(frames[(fr - i_first) * FFT512_XCH + fft512_nat(k)]);
+      wss += w * w;
     }
     y[n] = wss > 1e-11 ? static_cast<float>(acc / wss) : 0.f;
   }
 }
 
-constexpr size_t kStft512Smem = 512 * sizeof(double) + 512 * sizeof(float2) + 257 * 8 * sizeof(float2) +
-                                8 * FFT512_XCH * sizeof(float);
-constexpr size_t kIstft512Smem = 512 * sizeof(double) + 512 * sizeof(float2) + 8 * FFT512_XCH * sizeof(float) +
-                                 257 * 9 * sizeof(float2);
-static_assert(257 * 9 * sizeof(float2) >= 8 * 512 * sizeof(float), "the time frames must fit in the staged tile");
+constexpr size_t kStft512Smem = FFT512_TW * sizeof(float2) + 257 * 9 * sizeof(float2) + 8 * FFT512_XCH * sizeof(float);
+constexpr size_t kIstft512Smem = FFT512_TW * sizeof(float2) + 8 * FFT512_XCH * sizeof(float) + 257 * 9 * sizeof(float2);
+static_assert(257 * 9 * sizeof(float2) >= 8 * FFT512_XCH * sizeof(float), "the time frames must fit in the staged tile");
+static_assert(kStft512Smem <= 48 * 1024 && kIstft512Smem <= 48 * 1024, "no opt-in shared memory needed");
 
 bool fft_geometry_ok(int nfft, int hop, int* log2n) {
   if (nfft < 8 || nfft > 2048 || (nfft & (nfft - 1)) || hop < 1 || hop > nfft) return false;
@@ -366,6 +388,12 @@ bool fft_geometry_ok(int nfft, int hop, int* log2n) {
 }
 
 }  // namespace
+
+const char* fft512_init_tables() {
+  fft512_tables_kernel<<<1, 256>>>();
+  if (cudaGetLastError() != cudaSuccess) return "fft512: table kernel launch failed";
+  return cudaDeviceSynchronize() == cudaSuccess ? nullptr : "fft512: table kernel failed";
+}
 
 const char* launch_stft_complex(cudaStream_t s, const float* waves, int B, int L, int nfft, int hop, float* spec,
                                 float* mag) {
