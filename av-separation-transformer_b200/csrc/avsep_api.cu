@@ -1097,7 +1097,6 @@ int avsep_synth_batch(avsep_handle* h, const avsep_synth_config* cfg, int32_t B,
   const size_t need = static_cast<size_t>(B) * (p.S + 1) * p.n;
   if (h->synth_cap < need) {
     if (h->synth_waves) cudaFree(h->synth_waves);
-  if (h->host_ws) cudaFree(h->host_ws);
     h->synth_waves = nullptr; h->synth_cap = 0;
     CUDA_OK(cudaMalloc(&h->synth_waves, need * sizeof(float)));
     h->synth_cap = need;

@@ -120,38 +120,32 @@ __global__ void stft_mag_kernel(const float* __restrict__ waves, int n, int nfft
   }
 }
 
-// One CTA per (b, speaker, video frame): energy = fp32 mean of x^2 over the frame's audio span, brightness =
-// min(1, 20*energy), patch = clip(float(brightness) + noise, 0, 1) in the centre 50 %, zeros elsewhere
-// (dataset.py:91-104,137-147).
-__global__ void lip_frames_kernel(const float* __restrict__ waves, const float* __restrict__ noise, int S, int n,
-                                  int nf, int Hh, int Ww, float* __restrict__ frames) {
-  __shared__ float red[32];
-  __shared__ float s_bright;
-  const int fi = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
+// One warp per (b, speaker, video frame), no block-level synchronisation: energy = fp32 mean of x^2 over the frame's
+// audio span, brightness = min(1, 20*energy), patch = clip(float(brightness) + noise, 0, 1) in the centre 50 %, zeros
+// elsewhere (dataset.py:91-104,137-147).
+__global__ void __launch_bounds__(256) lip_frames_kernel(const float* __restrict__ waves,
+                                                         const float* __restrict__ noise, int B, int S, int n, int nf,
+                                                         int Hh, int Ww, float* __restrict__ frames) {
+  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= static_cast<long long>(B) * S * nf) return;
+  const int lane = threadIdx.x & 31;
+  const int fi = static_cast<int>(wid % nf);
+  const long long bs = wid / nf;                 // b * S + s
+  const int s = static_cast<int>(bs % S), b = static_cast<int>(bs / S);
   const int step = n / nf;
   const int a = fi * step;
   const int e = min(a + step, n);
   const float* x = waves + (static_cast<size_t>(b) * (S + 1) + 1 + s) * n;
   float acc = 0.f;
-  for (int i = a + threadIdx.x; i < e; i += blockDim.x) acc = fmaf(x[i], x[i], acc);
+  for (int i = a + lane; i < e; i += 32) acc = fmaf(x[i], x[i], acc);
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) {
-      const float energy = v / static_cast<float>(e - a);
-      s_bright = static_cast<float>(fmin(1.0, static_cast<double>(energy) * 20.0));
-    }
-  }
-  __syncthreads();
-  const float bright = s_bright;
+  const float energy = acc / static_cast<float>(e - a);
+  const float bright = static_cast<float>(fmin(1.0, static_cast<double>(energy) * 20.0));
   const int h0 = Hh / 4, h1 = 3 * Hh / 4, w0 = Ww / 4, w1 = 3 * Ww / 4;
   const int ph = h1 - h0, pw = w1 - w0;
-  float* out = frames + ((static_cast<size_t>(b) * S + s) * nf + fi) * Hh * Ww;
-  const float* nz = noise ? noise + ((static_cast<size_t>(b) * S + s) * nf + fi) * ph * pw : nullptr;
-  for (int p = threadIdx.x; p < Hh * Ww; p += blockDim.x) {
+  float* out = frames + static_cast<size_t>(wid) * Hh * Ww;
+  const float* nz = noise ? noise + static_cast<size_t>(wid) * ph * pw : nullptr;
+  for (int p = lane; p < Hh * Ww; p += 32) {
     const int y = p / Ww, xq = p - y * Ww;
     float v = 0.f;
     if (y >= h0 && y < h1 && xq >= w0 && xq < w1) {
@@ -307,7 +301,9 @@ const char* launch_synth(cudaStream_t s, const SynthProblem& p) {
     stft_mag_kernel<<<dim3((T + TG - 1) / TG, p.B * (p.S + 1)), p.nfft / 2, smem, s>>>(
         p.waves, p.n, p.nfft, log2n, p.hop, T, F, p.S, p.mixed_spec, p.clean_specs);
   }
-  lip_frames_kernel<<<dim3(p.nf, p.S, p.B), 256, 0, s>>>(p.waves, p.noise, p.S, p.n, p.nf, p.Hh, p.Ww, p.lip_frames);
+  const long long lip_warps = static_cast<long long>(p.B) * p.S * p.nf;
+  lip_frames_kernel<<<static_cast<unsigned>((lip_warps + 7) / 8), 256, 0, s>>>(p.waves, p.noise, p.B, p.S, p.n, p.nf,
+                                                                              p.Hh, p.Ww, p.lip_frames);
   return cudaGetLastError() == cudaSuccess ? nullptr : "synth: launch failed";
 }
 
