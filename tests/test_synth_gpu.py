@@ -148,3 +148,21 @@ def test_synth_and_snr_edge_geometries():
     assert abs(float(o_snr[0]) - so.permutation_snr(sep[0].cpu().numpy(), tg[0].cpu().numpy())) < 2e-5
     assert int(perm[0]) == 0
     assert abs(float(i_snr[0, 0]) - so.input_snrs(b["mixed_spec"][0].cpu().numpy(), tg[0].cpu().numpy())[0]) < 2e-5
+
+
+def test_synth_scratch_growth_leaves_the_host_workspace_alone():
+    """One handle serving both the host-buffer forward and the synthesis: growing the synthesis scratch must not
+    touch the forward's workspace (regression: it used to free it)."""
+    from avsep_b200 import AVSeparationTransformer, SyntheticAVDataset
+    torch.manual_seed(0)
+    model = AVSeparationTransformer(d_model=64, nhead=4, num_encoder_layers=1, num_fusion_layers=1).eval()
+    g = torch.Generator().manual_seed(1)
+    mixed = torch.rand(3, 257, 63, generator=g)
+    frames = torch.rand(3, 50, 32, 32, generator=g)
+    sep0, masks0 = (t.clone() for t in model(mixed, frames))          # CPU tensors -> avsep_forward_host
+    ds = SyntheticAVDataset(engine=model.engine)
+    ds.batch(range(2))
+    ds.batch(range(24))                                               # scratch grows
+    torch.cuda.synchronize()
+    sep1, masks1 = model(mixed, frames)
+    assert torch.equal(masks0, masks1) and torch.equal(sep0, sep1)
