@@ -690,8 +690,10 @@ void avsep_destroy(avsep_handle* h) {
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i) {
     if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+    if (h->host_comp[i]) cudaStreamDestroy(h->host_comp[i]);
+  }
   delete h;
 }
 
