@@ -249,6 +249,54 @@ __device__ __forceinline__ void value_chunk(const GemmEpilogue& e, const RowInfo
   }
 }
 
+// Decoder-head epilogue (EPI_TAIL) for 16 columns of one accumulator row, split in two so that the mixed_spec loads
+// of the next chunk are issued before the stores of the current one (and the first chunk's before the accumulator is
+// even complete): column c = s*F + f sits c*T floats further in masks / separated and f*T further in mixed_spec.
+// Whole chunks that do not cross a speaker boundary take branch-free bodies - the per-element guards and the frequency
+// wrap cost more instructions than the sigmoid.  All tests except `valid` are warp-uniform.
+__device__ __forceinline__ void tail_load16(const GemmEpilogue& e, int N, int col0, const float* mixed_row, bool valid,
+                                            float (&mx)[16]) {
+  const int ncols = min(16, N - col0);
+  if (!valid || ncols <= 0) return;
+  int f = col0 % e.F;
+  if (ncols == 16 && f + 16 <= e.F) {
+    const float* mp = mixed_row + static_cast<size_t>(f) * e.T;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mx[j] = __ldg(mp + static_cast<size_t>(j) * e.T);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      mx[j] = (j < ncols) ? __ldg(mixed_row + static_cast<size_t>(f) * e.T) : 0.f;
+      if (++f == e.F) f = 0;
+    }
+  }
+}
+
+__device__ __forceinline__ void tail_store16(const GemmEpilogue& e, int N, int col0, size_t out_base, bool valid,
+                                             const uint32_t (&v)[16], const float* sb, const float (&mx)[16]) {
+  const int ncols = min(16, N - col0);
+  if (!valid || ncols <= 0) return;
+  float* mo = e.masks + out_base + static_cast<size_t>(col0) * e.T;
+  float* so = e.separated + out_base + static_cast<size_t>(col0) * e.T;
+  if (ncols == 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float mk = sigmoid_fast(__uint_as_float(v[j]) + sb[j]);
+      __stcs(mo + static_cast<size_t>(j) * e.T, mk);
+      __stcs(so + static_cast<size_t>(j) * e.T, mk * mx[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < ncols) {
+        const float mk = sigmoid_fast(__uint_as_float(v[j]) + sb[j]);
+        __stcs(mo + static_cast<size_t>(j) * e.T, mk);
+        __stcs(so + static_cast<size_t>(j) * e.T, mk * mx[j]);
+      }
+    }
+  }
+}
+
 template <int EPI, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -403,6 +451,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_2d(slab, &tmF32, &resid_bar[part], part * 64, m0);
         }
       }
+      // EPI_TAIL: this thread's row of the (B,S,F,T) outputs, its share of the tile's columns, and the mixed_spec
+      // values of its first 16 columns - requested now, while the tile's MMAs are still running
+      bool t_valid = false;
+      const float* t_mixed_row = nullptr;
+      size_t t_out_base = 0;
+      int t_cbeg = 0, t_cend = 0;
+      float mxa[16], mxb[16];
+      if constexpr (EPI == EPI_TAIL) {
+        // SeparationDecoder head (model.py:204-207,220): column c = s*F + f, so masks[b,s,f,t] sits at
+        // ((b*S*F + c)*T + t); lanes are consecutive t, so the (B,S,F,T) stores and the mixed_spec (B,F,T) loads are
+        // both contiguous across the warp.
+        t_valid = m < p.M;
+        const int tb = m / e.T;
+        const int tt = m - tb * e.T;
+        t_mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
+        t_out_base = static_cast<size_t>(tb) * e.S * e.F * e.T + tt;
+        // Each column part takes a contiguous, balanced share of the tile in units of 16 columns (176 columns ->
+        // 48/48/48/32); handing out whole 32-column chunks round-robin left two parts with twice the work of the
+        // others and the tile waiting on them at the next barrier.
+        const int units = p.n_tile >> 4, ubase = units >> 2, urem = units & 3;
+        t_cbeg = (part * ubase + min(part, urem)) << 4;
+        t_cend = t_cbeg + ((ubase + (part < urem ? 1 : 0)) << 4);
+        if (t_cbeg < t_cend) tail_load16(e, p.N, n0 + t_cbeg, t_mixed_row, t_valid, mxa);
+      }
       if (lt == 1 && threadIdx.x == 64) TRACE(2);               // [2] tile-1 epilogue entered (bias load issued)
       asm volatile("bar.sync 5, 512;" ::: "memory");            // bias slice visible to all epilogue warps
       if (lt == 1 && threadIdx.x == 64) TRACE(3);               // [3] bias barrier passed
@@ -412,48 +484,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN_MAX);
 
       if constexpr (EPI == EPI_TAIL) {
-        // SeparationDecoder head (model.py:204-207,220): column c = s*F + f, so masks[b,s,f,t] sits at
-        // ((b*S*F + c)*T + t); lanes are consecutive t, so the (B,S,F,T) stores and the mixed_spec (B,F,T) loads are
-        // both contiguous across the warp.
-        const bool valid = m < p.M;
-        const int tb = m / e.T;
-        const int tt = m - tb * e.T;
-        const float* mixed_row = e.mixed + static_cast<size_t>(tb) * e.F * e.T + tt;
-        const size_t out_base = static_cast<size_t>(tb) * e.S * e.F * e.T + tt;
-        // Each column part takes a contiguous, balanced share of the tile in units of 16 columns (176 columns ->
-        // 48/48/48/32), walked 32 columns at a time; handing out whole 32-column chunks round-robin left two parts
-        // with twice the work of the others and the tile waiting on them at the next barrier.
-        const int units = p.n_tile >> 4, ubase = units >> 2, urem = units & 3;
-        const int cbeg = (part * ubase + min(part, urem)) << 4;
-        const int cend = cbeg + ((ubase + (part < urem ? 1 : 0)) << 4);
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          const int col0 = n0 + c0;
-          if (col0 >= p.N) break;                      // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr_row + static_cast<uint32_t>(c0), v);
-          const int ncols = min(32, min(p.N - col0, cend - c0));
-          int f = col0 % e.F;
-          float mx[32];
-          if (valid) {                                 // all mixed_spec loads in flight before any store
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              mx[j] = (j < ncols) ? __ldg(mixed_row + static_cast<size_t>(f) * e.T) : 0.f;
-              if (++f == e.F) f = 0;
-            }
-          }
+        // 16 columns at a time (16 accumulator values + two 16-value mixed_spec buffers stay within the 96 registers
+        // this 640-thread CTA allows), two chunks per iteration so that the buffers alternate statically.
+        for (int c0 = t_cbeg; c0 < t_cend; c0 += 32) {
+          if (n0 + c0 >= p.N) break;                   // warp-uniform
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr_row + static_cast<uint32_t>(c0), v);
+          const bool second = c0 + 16 < t_cend;
+          if (second) tail_load16(e, p.N, n0 + c0 + 16, t_mixed_row, t_valid, mxb);
           tmem_ld_wait();
-          if (valid) {
-            float* mo = e.masks + out_base + static_cast<size_t>(col0) * e.T;
-            float* so = e.separated + out_base + static_cast<size_t>(col0) * e.T;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < ncols) {
-                const float z = __uint_as_float(v[j]) + sb[c0 + j];
-                const float mk = __fdividef(1.0f, 1.0f + __expf(-z));
-                __stcs(mo + static_cast<size_t>(j) * e.T, mk);
-                __stcs(so + static_cast<size_t>(j) * e.T, mk * mx[j]);
-              }
-            }
+          tail_store16(e, p.N, n0 + c0, t_out_base, t_valid, v, sb + c0, mxa);
+          if (second && n0 + c0 + 16 < p.N) {
+            tmem_ld_32x32b_x16(taddr_row + static_cast<uint32_t>(c0 + 16), v);
+            if (c0 + 32 < t_cend) tail_load16(e, p.N, n0 + c0 + 32, t_mixed_row, t_valid, mxa);
+            tmem_ld_wait();
+            tail_store16(e, p.N, n0 + c0 + 16, t_out_base, t_valid, v, sb + c0 + 16, mxb);
           }
         }
       } else if constexpr (EPI == EPI_LN_TMA) {
