@@ -1317,7 +1317,13 @@ int avsep_test_gemm_trace(avsep_handle* h, const void* A, const void* W, const f
   p.A = A; p.lda = K; p.rowsA = M; p.M = M; p.W = W; p.ldw = K; p.N = N; p.K = K; p.taps = 1;
   GemmEpilogue e;
   e.bias = bias; e.act = act;
-  if (ln) {
+  if (ln == 7) {
+    // decoder head (EPI_TAIL) for the trace tool: S = 2, F = N / 2, T = act; mixed = gamma, masks = x_or_out,
+    // separated = out_op (all float32)
+    e.kind = EPI_TAIL; e.act = ACT_NONE;
+    e.S = 2; e.F = N / 2; e.T = act;
+    e.mixed = gamma; e.masks = x_or_out; e.separated = static_cast<float*>(out_op);
+  } else if (ln) {
     e.kind = EPI_LN;
     e.resid = x_or_out; e.out_f32 = x_or_out; e.ld_f32 = N; e.ln_gamma = gamma; e.ln_beta = beta;
     e.out_op = out_op; e.ld_op = N;
