@@ -439,7 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m = m0 + r;
       // stage this tile's bias slice in shared memory while the main loop is still running
       float* sb = sbias + (lt & 1) * BN_MAX;
-      {
+      if constexpr (EPI != EPI_TAIL) {
         const int i = threadIdx.x - 64;                       // 0..511 over the 16 epilogue warps
         if (i < BN_MAX) sb[i] = (e.bias != nullptr && i < p.n_tile && n0 + i < p.N) ? __ldg(e.bias + n0 + i) : 0.f;
       }
@@ -474,9 +474,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         t_cbeg = (part * ubase + min(part, urem)) << 4;
         t_cend = t_cbeg + ((ubase + (part < urem ? 1 : 0)) << 4);
         if (t_cbeg < t_cend) tail_load16(e, p.N, n0 + t_cbeg, t_mixed_row, t_valid, mxa);
+        // each column part stages its own bias slice and synchronises only its 4 warps (same columns, same amount
+        // of work): with one 512-thread barrier per tile every part waited ~1.2 us for the slowest of the 16 warps
+        const int c = t_cbeg + r;
+        if (c < t_cend) sb[c] = (e.bias != nullptr && n0 + c < p.N) ? __ldg(e.bias + n0 + c) : 0.f;
       }
       if (lt == 1 && threadIdx.x == 64) TRACE(2);               // [2] tile-1 epilogue entered (bias load issued)
-      asm volatile("bar.sync 5, 512;" ::: "memory");            // bias slice visible to all epilogue warps
+      if constexpr (EPI == EPI_TAIL) named_bar_sync(part_bar, 128);
+      else asm volatile("bar.sync 5, 512;" ::: "memory");       // bias slice visible to all epilogue warps
       if (lt == 1 && threadIdx.x == 64) TRACE(3);               // [3] bias barrier passed
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
