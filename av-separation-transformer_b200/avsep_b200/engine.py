@@ -144,37 +144,89 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ---- shape contract (every entry point validates BEFORE a pointer reaches the C ABI: the library sizes its
+    # copies and strides from the engine config, so a wrong F / d / batch would read or write out of bounds) ----
+    def _check_inputs(self, what: str, mixed=None, frames=None, rows=None, rows2=None, out=None):
+        """mixed (B,F,T) | frames (B,N,H,W) | rows / rows2 (B,L,d) | out = (separated, masks) (B,S,F,T).
+        Returns (B, T, N, Hh, Ww) with None for the dims that were not given.  Raises ValueError."""
+        cfg = self.cfg
+        B = T = N = Hh = Ww = None
+        if mixed is not None:
+            if mixed.dim() != 3:
+                raise ValueError(f"{what}: mixed_spec must be (B, freq_bins, T), got {tuple(mixed.shape)}")
+            B, F, T = mixed.shape
+            if F != cfg.freq_bins:
+                raise ValueError(f"{what}: mixed_spec has {F} frequency bins, model expects {cfg.freq_bins}")
+        if frames is not None:
+            if frames.dim() != 4:
+                raise ValueError(f"{what}: lip_frames must be (B, num_frames, H, W), got {tuple(frames.shape)}")
+            Bf, N, Hh, Ww = frames.shape
+            if B is not None and Bf != B:
+                raise ValueError(f"{what}: batch size of mixed_spec ({B}) and lip_frames ({Bf}) differ")
+            B = Bf
+        for r in (rows, rows2):
+            if r is None:
+                continue
+            if r.dim() != 3 or r.shape[2] != cfg.d_model:
+                raise ValueError(f"{what}: expected (B, L, {cfg.d_model}) rows, got {tuple(r.shape)}")
+            if B is not None and r.shape[0] != B:
+                raise ValueError(f"{what}: batch sizes differ ({B} vs {r.shape[0]})")
+            B = r.shape[0]
+        if B is not None and B < 1:
+            raise ValueError(f"{what}: empty batch")
+        if out is not None:
+            want = (B, cfg.num_speakers, cfg.freq_bins, T)
+            for t in out:
+                if tuple(t.shape) != want or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise ValueError(f"{what}: output buffers must be contiguous float32 {want}, got {tuple(t.shape)}")
+        return B, T, N, Hh, Ww
+
     # ---- forward ---------------------------------------------------------------------------------
-    def forward(self, mixed: torch.Tensor, frames: torch.Tensor):
+    def forward(self, mixed: torch.Tensor, frames: torch.Tensor, out=None):
+        """Device tensors in, device tensors out.  ``out=(separated, masks)`` reuses caller-owned (B,S,F,T) float32
+        buffers: with fixed input and output buffers every call after the second is one CUDA-graph replay."""
         mixed = self._dev_f32(mixed, "mixed_spec")
         frames = self._dev_f32(frames, "lip_frames")
-        B, F, T = mixed.shape
-        Bf, N, Hh, Ww = frames.shape
-        if F != self.cfg.freq_bins:
-            raise ValueError(f"mixed_spec has {F} frequency bins, model expects {self.cfg.freq_bins}")
-        if Bf != B:
-            raise ValueError("batch size of mixed_spec and lip_frames differ")
-        S = self.cfg.num_speakers
-        sep = torch.empty((B, S, F, T), device=mixed.device, dtype=torch.float32)
-        masks = torch.empty_like(sep)
-        with torch.cuda.device(self.device):
-            rc = self.lib.avsep_forward(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
-                                        sep.data_ptr(), masks.data_ptr(), None, 0, self._stream())
+        B, T, N, Hh, Ww = self._check_inputs("forward", mixed=mixed, frames=frames, out=out)
+        F, S = self.cfg.freq_bins, self.cfg.num_speakers
+        if out is None:
+            sep = torch.empty((B, S, F, T), device=mixed.device, dtype=torch.float32)
+            masks = torch.empty_like(sep)
+        else:
+            sep, masks = out
+            for t in out:
+                if not t.is_cuda or t.device.index != self.device:
+                    raise ValueError(f"forward: output buffers must live on cuda:{self.device}")
+        args = (self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww, sep.data_ptr(), masks.data_ptr(), None, 0,
+                self._stream())
+        if torch.cuda.current_device() == self.device:      # the library selects its device itself; only restore the
+            rc = self.lib.avsep_forward(*args)               # caller's when it differs
+        else:
+            with torch.cuda.device(self.device):
+                rc = self.lib.avsep_forward(*args)
         self._check(rc, "avsep_forward")
         return sep, masks
+
+    @staticmethod
+    def _host_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor) or t.is_cuda:
+            raise ValueError(f"{name} must be a CPU tensor")
+        return t.contiguous().float()
 
     def forward_host(self, mixed: torch.Tensor, frames: torch.Tensor, sep: torch.Tensor = None,
                      masks: torch.Tensor = None):
         """CPU tensors in, CPU tensors out; H2D, kernels and D2H all inside the C call (pinned memory advised)."""
-        mixed = mixed.contiguous().float()
-        frames = frames.contiguous().float()
-        B, F, T = mixed.shape
-        _, N, Hh, Ww = frames.shape
-        S = self.cfg.num_speakers
+        mixed = self._host_f32(mixed, "mixed_spec")
+        frames = self._host_f32(frames, "lip_frames")
+        B, T, N, Hh, Ww = self._check_inputs("forward_host", mixed=mixed, frames=frames)
+        F, S = self.cfg.freq_bins, self.cfg.num_speakers
         if sep is None:
             sep = torch.empty((B, S, F, T), dtype=torch.float32).pin_memory()
         if masks is None:
             masks = torch.empty((B, S, F, T), dtype=torch.float32).pin_memory()
+        self._check_inputs("forward_host", mixed=mixed, out=(sep, masks))
+        if sep.is_cuda or masks.is_cuda:
+            raise ValueError("forward_host: output buffers must be CPU tensors")
         with torch.cuda.device(self.device):
             rc = self.lib.avsep_forward_host(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
                                              sep.data_ptr(), masks.data_ptr(), self._stream())
@@ -188,10 +240,7 @@ class Engine:
         for t in (mixed, frames, sep, masks):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("forward_host_async: contiguous float32 CPU tensors required")
-        B, F, T = mixed.shape
-        _, N, Hh, Ww = frames.shape
-        if tuple(sep.shape) != (B, self.cfg.num_speakers, F, T) or sep.shape != masks.shape:
-            raise ValueError("forward_host_async: output buffers must be (B, S, F, T)")
+        B, T, N, Hh, Ww = self._check_inputs("forward_host_async", mixed=mixed, frames=frames, out=(sep, masks))
         with torch.cuda.device(self.device):
             rc = self.lib.avsep_forward_host_async(self.h, mixed.data_ptr(), frames.data_ptr(), B, T, N, Hh, Ww,
                                                    sep.data_ptr(), masks.data_ptr(), int(slot), self._stream())
@@ -206,7 +255,7 @@ class Engine:
     # ---- sub-modules -------------------------------------------------------------------------------
     def audio_encoder(self, mixed):
         mixed = self._dev_f32(mixed, "mixed_spec")
-        B, F, T = mixed.shape
+        B, T, _, _, _ = self._check_inputs("audio_encoder", mixed=mixed)
         out = torch.empty((B, T, self.cfg.d_model), device=mixed.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             rc = self.lib.avsep_audio_encoder(self.h, mixed.data_ptr(), B, T, out.data_ptr(), self._stream())
@@ -215,7 +264,9 @@ class Engine:
 
     def visual_encoder(self, frames, target_len: int):
         frames = self._dev_f32(frames, "lip_frames")
-        B, N, Hh, Ww = frames.shape
+        B, _, N, Hh, Ww = self._check_inputs("visual_encoder", frames=frames)
+        if int(target_len) < 1:
+            raise ValueError("visual_encoder: target_len must be >= 1")
         out = torch.empty((B, int(target_len), self.cfg.d_model), device=frames.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             rc = self.lib.avsep_visual_encoder(self.h, frames.data_ptr(), B, N, Hh, Ww, int(target_len),
@@ -226,6 +277,7 @@ class Engine:
     def fusion(self, audio, visual):
         audio = self._dev_f32(audio, "audio")
         visual = self._dev_f32(visual, "visual")
+        self._check_inputs("fusion", rows=audio, rows2=visual)
         B, T, d = audio.shape
         L = visual.shape[1]
         out = torch.empty_like(audio)
@@ -238,7 +290,10 @@ class Engine:
     def decoder(self, fused, mixed):
         fused = self._dev_f32(fused, "fused")
         mixed = self._dev_f32(mixed, "mixed_spec")
+        self._check_inputs("decoder", mixed=mixed, rows=fused)
         B, T, d = fused.shape
+        if mixed.shape[2] != T:
+            raise ValueError(f"decoder: fused has {T} frames, mixed_spec has {mixed.shape[2]}")
         F, S = self.cfg.freq_bins, self.cfg.num_speakers
         sep = torch.empty((B, S, F, T), device=fused.device, dtype=torch.float32)
         masks = torch.empty_like(sep)

@@ -39,12 +39,26 @@ def _encoder_stack(d_model: int, nhead: int, num_layers: int, dropout: float) ->
         return nn.TransformerEncoder(layer, num_layers=num_layers)
 
 
+def _refresh_after_load(module, incompatible_keys):      # module-level so that torch.save(model) can pickle the hook
+    module.refresh_weights()
+
+
 class _InferenceOnly(nn.Module):
-    """Shared behaviour: eval-only, lazily (re)built engine keyed on parameter versions."""
+    """Shared behaviour: eval-only, lazily (re)built engine.
+
+    The engine holds a prepacked copy of the weights.  It is rebuilt when the weights may have changed:
+    ``load_state_dict`` / ``.to()`` / ``.cuda()`` / ``.float()`` (hooks below), any in-place update that bumps a
+    tensor's autograd version counter (``p.copy_()``, ``p.add_()``, optimiser steps -- a ~10 us sum over a cached
+    tensor list per forward), or an explicit ``refresh_weights()``.  Edits through ``p.data`` do not bump the
+    counter: call ``refresh_weights()`` after them."""
 
     def _post_init(self):
         self._engine = None
-        self._engine_key = None
+        self._engine_sig = None
+        self._tensors = None          # cached list of parameters + buffers (rebuilt when Parameter objects change)
+        self._weights_epoch = 0
+        self.host_device = getattr(self, "host_device", "cuda:0")
+        self.register_load_state_dict_post_hook(_refresh_after_load)
         nn.Module.train(self, False)
 
     def train(self, mode: bool = True):
@@ -61,29 +75,73 @@ class _InferenceOnly(nn.Module):
     def _state_prefix(self) -> str:
         return ""
 
-    def _weights_key(self, device_index: int):
-        items = list(self.named_parameters()) + list(self.named_buffers())
-        return (device_index,) + tuple((n, t._version, t.data_ptr()) for n, t in items)
+    def refresh_weights(self):
+        """Mark the prepacked weights stale (the next forward re-uploads them)."""
+        self._weights_epoch += 1
+        self._tensors = None
+        return self
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float(): Parameter storage may be replaced
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_weights_epoch"):
+            self.refresh_weights()
+        return out
+
+    def _weights_sig(self, device_index: int):
+        if self._tensors is None:
+            self._tensors = [t for _, t in self.named_parameters()] + [t for _, t in self.named_buffers()]
+        v = 0
+        for t in self._tensors:
+            v += t._version
+        return (device_index, self._weights_epoch, v)
 
     def _get_engine(self, device: torch.device) -> Engine:
         if device.type != "cuda":
             raise RuntimeError("avsep_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         index = device.index if device.index is not None else torch.cuda.current_device()
-        key = self._weights_key(index)
-        if self._engine is None or self._engine_key != key:
+        sig = self._weights_sig(index)
+        if self._engine is None or self._engine_sig != sig:
             if self._engine is not None:
                 self._engine.close()
             eng = Engine(self._engine_config(), index)
             pre = self._state_prefix()
             state = {pre + k: v for k, v in self.state_dict().items()}
             eng.load_state(state, fill_missing=bool(pre))
-            self._engine, self._engine_key = eng, key
+            self._engine, self._engine_sig = eng, sig
         return self._engine
 
     def prepack(self, device="cuda"):
         """Fold/repack/upload the weights now (otherwise done lazily on the first forward)."""
         self._get_engine(torch.device(device))
         return self
+
+    def _run(self, fn_name: str, *tensors, extra=()):
+        """Route one call: CUDA tensors run in place; CPU tensors (how the reference's own tests call the modules,
+        tests/test_model.py:77-179) are uploaded to ``host_device``, run there and come back as CPU tensors --
+        the arithmetic is on the GPU either way (there is no CPU implementation)."""
+        first = tensors[0]
+        if first.is_cuda:
+            return getattr(self._get_engine(first.device), fn_name)(*tensors, *extra)
+        dev = torch.device(self.host_device)
+        out = getattr(self._get_engine(dev), fn_name)(*[t.to(dev) for t in tensors], *extra)
+        return tuple(o.cpu() for o in out) if isinstance(out, tuple) else out.cpu()
+
+    # the engine owns a ctypes handle: never pickled / deep-copied, rebuilt lazily by the copy
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_sig"] = None
+        state["_tensors"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_engine", "_engine_sig", "_tensors") else copy.deepcopy(v, memo)
+        return new
 
 
 class PositionalEncoding(nn.Module):
@@ -127,7 +185,7 @@ class AudioEncoder(_InferenceOnly):
         return "audio_encoder."
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self._get_engine(x.device).audio_encoder(x)
+        return self._run("audio_encoder", x)
 
 
 class VisualEncoder(_InferenceOnly):
@@ -154,7 +212,7 @@ class VisualEncoder(_InferenceOnly):
         return "visual_encoder."
 
     def forward(self, frames: torch.Tensor, target_len: int) -> torch.Tensor:
-        return self._get_engine(frames.device).visual_encoder(frames, target_len)
+        return self._run("visual_encoder", frames, extra=(target_len,))
 
 
 class CrossAttentionLayer(nn.Module):
@@ -186,7 +244,7 @@ class CrossModalFusion(_InferenceOnly):
         return "fusion."
 
     def forward(self, audio: torch.Tensor, visual: torch.Tensor) -> torch.Tensor:
-        return self._get_engine(audio.device).fusion(audio, visual)
+        return self._run("fusion", audio, visual)
 
 
 class SeparationDecoder(_InferenceOnly):
@@ -213,7 +271,7 @@ class SeparationDecoder(_InferenceOnly):
     def forward(self, fused: torch.Tensor) -> torch.Tensor:
         B, T, _ = fused.shape
         ones = torch.ones((B, self.freq_bins, T), device=fused.device, dtype=torch.float32)
-        return self._get_engine(fused.device).decoder(fused, ones)[1]
+        return self._run("decoder", fused, ones)[1]
 
     def separate(self, masks: torch.Tensor, mixed_spec: torch.Tensor) -> torch.Tensor:
         # model.py:210-220; stand-alone use only -- in the full model the multiply is fused into the decoder epilogue
@@ -249,10 +307,13 @@ class AVSeparationTransformer(_InferenceOnly):
     def _engine_config(self):
         return self.config
 
-    def forward(self, mixed_spec: torch.Tensor, lip_frames: torch.Tensor):
+    def forward(self, mixed_spec: torch.Tensor, lip_frames: torch.Tensor, out=None):
+        """``out=(separated, masks)``: optional caller-owned output buffers (not a reference argument); with fixed
+        input and output buffers the call is a single CUDA-graph replay."""
         if mixed_spec.is_cuda:
-            return self._get_engine(mixed_spec.device).forward(mixed_spec, lip_frames)
-        return self._get_engine(torch.device(self.host_device)).forward_host(mixed_spec, lip_frames)
+            return self._get_engine(mixed_spec.device).forward(mixed_spec, lip_frames, out)
+        eng = self._get_engine(torch.device(self.host_device))
+        return eng.forward_host(mixed_spec, lip_frames, *(out or ()))
 
     def separate_waveforms(self, mixed_wave: torch.Tensor, lip_frames: torch.Tensor, n_fft: int = None,
                            hop_length: int = 128):

@@ -1,0 +1,192 @@
+"""Batch sharding of the forward path over the GPUs of one box, one process per GPU.
+
+No op of the model mixes utterances in eval mode (reference model.py: BatchNorm on running statistics :83-89,
+attention per sample), so the batch shards with no collective inside the model.  What moves between GPUs is what the
+north star names: the root's inputs are scattered, ``separated`` / ``masks`` are gathered.
+
+    root (rank 0)                          rank r > 0
+    -------------                          ----------
+    global inputs  [sets][world*B, ...] -> pull own shard over NVLink      (copy stream, copy engine)
+                                           forward on the local shard      (compute stream, libavsep kernels)
+    global outputs [2][world*B, ...]    <- push separated + masks shard    (copy stream, copy engine)
+
+The root's buffers come from ``avsep_shared_alloc`` (cudaMalloc + an inter-process handle); the other ranks map them
+with ``avsep_shared_open`` and move data with ``avsep_copy_async`` -- peer-memory copies executed by the copy engines,
+so the transfers of step i-1 / i+1 run under the kernels of step i without taking SMs from them (an NCCL send/recv
+pair needs CTAs on both ends).  ``torch.distributed`` carries the 64-byte handles and the barriers, nothing else.
+The root computes its own shard in place (zero copy).  Local input / output buffers are double buffered and ordered
+with events; the root's output buffers are double buffered as well, so a consumer on the root can read step i-1 while
+step i is being written.
+
+The memory backend is injected so that the bookkeeping (shard offsets, buffer rotation, ordering) is covered by
+world_size-2 gloo tests on CPU (tests/test_multirank_cpu.py); on a GPU box the backend is the C ABI above.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+__all__ = ["shard_slices", "PeerMemoryCuda", "ShardedForward"]
+
+
+def shard_slices(world: int, per_rank_batch: int):
+    """[(lo, hi)] per rank: contiguous, disjoint shards that tile the global batch (weak scaling: fixed per-rank batch)."""
+    return [(r * per_rank_batch, (r + 1) * per_rank_batch) for r in range(world)]
+
+
+class _RawCuda:
+    """Minimal __cuda_array_interface__ holder so that torch can view memory owned by libavsep."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerMemoryCuda:
+    """avsep_shared_alloc / avsep_shared_open / avsep_copy_async of one engine (one GPU, one process)."""
+
+    def __init__(self, engine):
+        self.eng = engine
+        self.dev = torch.device("cuda", engine.device)
+
+    def alloc(self, nfloats: int):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self.eng._check(self.eng.lib.avsep_shared_alloc(self.eng.h, nfloats * 4, C.byref(ptr), handle), "avsep_shared_alloc")
+        return int(ptr.value), bytes(handle.raw)
+
+    def open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.eng._check(self.eng.lib.avsep_shared_open(self.eng.h, handle, C.byref(ptr)), "avsep_shared_open")
+        return int(ptr.value)
+
+    def view(self, ptr: int, shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return torch.as_tensor(_RawCuda(ptr, n), device=self.dev).view(*shape)
+
+    def empty(self, shape) -> torch.Tensor:
+        return torch.empty(*shape, device=self.dev, dtype=torch.float32)
+
+    def copy(self, dst_ptr: int, src_ptr: int, nfloats: int, stream):
+        self.eng._check(self.eng.lib.avsep_copy_async(self.eng.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nfloats * 4,
+                                                      C.c_void_p(stream.cuda_stream)), "avsep_copy_async")
+
+    # stream / event plumbing (torch is used for streams only)
+    def stream(self):
+        return torch.cuda.Stream(device=self.dev)
+
+    def current_stream(self):
+        return torch.cuda.current_stream(self.dev)
+
+    def event(self):
+        return torch.cuda.Event(enable_timing=False)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.dev)
+
+
+class ShardedForward:
+    """Root-scattered, root-gathered forward over ``world`` ranks.
+
+    forward_fn(mixed, frames, sep, masks): runs the model on one shard (tensors of the backend's device), stream-ordered
+    on the backend's current stream.  ``shapes``: dict with the per-utterance shapes ``mixed`` (F, T), ``frames``
+    (N, H, W), ``out`` (S, F, T).
+    """
+
+    def __init__(self, backend, forward_fn, per_rank_batch: int, shapes: dict, rank: int, world: int,
+                 n_input_sets: int = 1, group=None):
+        self.mem, self.fwd = backend, forward_fn
+        self.B, self.rank, self.world, self.group = int(per_rank_batch), int(rank), int(world), group
+        self.n_sets = int(n_input_sets)
+        self.shapes = {k: tuple(int(x) for x in v) for k, v in shapes.items()}
+        self.per = {k: _prod(v) for k, v in self.shapes.items()}        # floats per utterance
+        self.lo, self.hi = shard_slices(world, self.B)[rank]
+        G = world * self.B
+        names = [f"in{s}.{k}" for s in range(self.n_sets) for k in ("mixed", "frames")] + \
+                [f"out{o}.{k}" for o in range(2) for k in ("sep", "masks")]
+        sizes = {n: G * self.per["mixed" if n.endswith("mixed") else "frames" if n.endswith("frames") else "out"]
+                 for n in names}
+        self.ptr = {}
+        if rank == 0:
+            handles = {}
+            for n in names:
+                self.ptr[n], handles[n] = self.mem.alloc(sizes[n])
+            box = [handles]
+        else:
+            box = [None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if rank != 0:
+            for n in names:
+                self.ptr[n] = self.mem.open(box[0][n])
+        # root: tensor views of the global buffers (what its producer fills / its consumer reads)
+        self.root_in, self.root_out = [], []
+        if rank == 0:
+            for s in range(self.n_sets):
+                self.root_in.append((self.mem.view(self.ptr[f"in{s}.mixed"], (G,) + self.shapes["mixed"]),
+                                     self.mem.view(self.ptr[f"in{s}.frames"], (G,) + self.shapes["frames"])))
+            for o in range(2):
+                self.root_out.append((self.mem.view(self.ptr[f"out{o}.sep"], (G,) + self.shapes["out"]),
+                                      self.mem.view(self.ptr[f"out{o}.masks"], (G,) + self.shapes["out"])))
+        else:
+            B = self.B
+            self.loc_in = [(self.mem.empty((B,) + self.shapes["mixed"]), self.mem.empty((B,) + self.shapes["frames"]))
+                           for _ in range(2)]
+            self.loc_out = [(self.mem.empty((B,) + self.shapes["out"]), self.mem.empty((B,) + self.shapes["out"]))
+                            for _ in range(2)]
+            self.s_in, self.s_out = self.mem.stream(), self.mem.stream()
+            self.ev_in_ready = [self.mem.event() for _ in range(2)]
+            self.ev_fwd_done = [self.mem.event() for _ in range(2)]
+            self.ev_out_free = [self.mem.event() for _ in range(2)]
+            self.used = [False, False]
+        self.bytes_in_per_step = 4 * self.B * (self.per["mixed"] + self.per["frames"])     # per non-root rank
+        self.bytes_out_per_step = 4 * self.B * 2 * self.per["out"]
+
+    # ---- one step: scatter -> forward -> gather, all enqueued asynchronously -------------------------------------
+    def step(self, i: int):
+        s_set, b = i % self.n_sets, i & 1
+        if self.rank == 0:
+            m, f = self.root_in[s_set]
+            sep, masks = self.root_out[b]
+            self.fwd(m[self.lo:self.hi], f[self.lo:self.hi], sep[self.lo:self.hi], masks[self.lo:self.hi])
+            return
+        comp = self.mem.current_stream()
+        m, f = self.loc_in[b]
+        sep, masks = self.loc_out[b]
+        # scatter: this rank's shard of the root's inputs, once the forward that last read this buffer pair is done
+        if self.used[b]:
+            self.s_in.wait_event(self.ev_fwd_done[b])
+        off = self.lo
+        self.mem.copy(m.data_ptr(), self.ptr[f"in{s_set}.mixed"] + 4 * off * self.per["mixed"], self.B * self.per["mixed"], self.s_in)
+        self.mem.copy(f.data_ptr(), self.ptr[f"in{s_set}.frames"] + 4 * off * self.per["frames"], self.B * self.per["frames"], self.s_in)
+        self.ev_in_ready[b].record(self.s_in)
+        # forward on the shard, once its inputs have landed and the push that last read these outputs is done
+        comp.wait_event(self.ev_in_ready[b])
+        if self.used[b]:
+            comp.wait_event(self.ev_out_free[b])
+        self.fwd(m, f, sep, masks)
+        self.ev_fwd_done[b].record(comp)
+        # gather: push the shard's outputs into the root's global buffers
+        self.s_out.wait_event(self.ev_fwd_done[b])
+        self.mem.copy(self.ptr[f"out{b}.sep"] + 4 * off * self.per["out"], sep.data_ptr(), self.B * self.per["out"], self.s_out)
+        self.mem.copy(self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"], self.s_out)
+        self.ev_out_free[b].record(self.s_out)
+        self.used[b] = True
+
+    def finish(self):
+        """All enqueued scatters, forwards and gathers of every rank are complete when this returns."""
+        self.mem.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+
+def _prod(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n

@@ -140,6 +140,7 @@ struct avsep_handle {
     cudaEvent_t ev_start = nullptr, ev_end = nullptr;       // ev_end: last copy-out done
     cudaEvent_t ev_lane[3] = {nullptr, nullptr, nullptr};   // last kernels of this slot on each compute lane
   } slot[2];
+  std::vector<void*> shared_owned, shared_mapped;   // avsep_shared_alloc / avsep_shared_open
   float* synth_waves = nullptr;   // scratch of avsep_synth_batch
   size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -679,6 +680,8 @@ void avsep_destroy(avsep_handle* h) {
     for (cudaEvent_t e : sl.ev_lane)
       if (e) cudaEventDestroy(e);
   }
+  for (void* ptr : h->shared_mapped) cudaIpcCloseMemHandle(ptr);
+  for (void* ptr : h->shared_owned) cudaFree(ptr);
   if (h->synth_waves) cudaFree(h->synth_waves);
   if (h->host_ws) cudaFree(h->host_ws);
   for (auto& kv : h->snaps)
@@ -1145,6 +1148,72 @@ int avsep_istft(avsep_handle* h, const float* spec, const float* masks, int32_t 
 
 int64_t avsep_last_launch_count(const avsep_handle* h) { return h ? h->launches : 0; }
 
+// ---- batch sharding over the GPUs of one box: peer-mapped buffers + copy-engine transfers ----------
+int avsep_shared_alloc(avsep_handle* h, size_t bytes, void** dev_ptr, unsigned char handle_out[AVSEP_IPC_HANDLE_BYTES]) {
+  if (!h) return 1;
+  if (!dev_ptr || !handle_out || bytes == 0) return fail(h, "avsep_shared_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AVSEP_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  void* ptr = nullptr;
+  CUDA_OK(cudaMalloc(&ptr, bytes));       // a dedicated allocation: an IPC handle always names a whole cudaMalloc block
+  cudaIpcMemHandle_t ih;
+  const cudaError_t ce = cudaIpcGetMemHandle(&ih, ptr);
+  if (ce != cudaSuccess) {
+    cudaFree(ptr);
+    return fail(h, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(ce));
+  }
+  memcpy(handle_out, &ih, sizeof ih);
+  h->shared_owned.push_back(ptr);
+  *dev_ptr = ptr;
+  return 0;
+}
+
+int avsep_shared_free(avsep_handle* h, void* dev_ptr) {
+  if (!h) return 1;
+  for (size_t i = 0; i < h->shared_owned.size(); ++i)
+    if (h->shared_owned[i] == dev_ptr) {
+      CUDA_OK(cudaSetDevice(h->cfg.device));
+      h->shared_owned.erase(h->shared_owned.begin() + i);
+      CUDA_OK(cudaFree(dev_ptr));
+      return 0;
+    }
+  return fail(h, "avsep_shared_free: pointer was not allocated by avsep_shared_alloc on this handle");
+}
+
+int avsep_shared_open(avsep_handle* h, const unsigned char handle[AVSEP_IPC_HANDLE_BYTES], void** dev_ptr) {
+  if (!h) return 1;
+  if (!handle || !dev_ptr) return fail(h, "avsep_shared_open: bad argument");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, handle, sizeof ih);
+  void* ptr = nullptr;
+  CUDA_OK(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+  h->shared_mapped.push_back(ptr);
+  *dev_ptr = ptr;
+  return 0;
+}
+
+int avsep_shared_close(avsep_handle* h, void* dev_ptr) {
+  if (!h) return 1;
+  for (size_t i = 0; i < h->shared_mapped.size(); ++i)
+    if (h->shared_mapped[i] == dev_ptr) {
+      CUDA_OK(cudaSetDevice(h->cfg.device));
+      h->shared_mapped.erase(h->shared_mapped.begin() + i);
+      CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+      return 0;
+    }
+  return fail(h, "avsep_shared_close: pointer was not mapped by avsep_shared_open on this handle");
+}
+
+int avsep_copy_async(avsep_handle* h, void* dst, const void* src, size_t bytes, void* cuda_stream) {
+  if (!h) return 1;
+  if (!dst || !src) return fail(h, "avsep_copy_async: null buffer");
+  if (bytes == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
 // ---- sub-module forwards ------------------------------------------------------------------------
 int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int32_t T, float* out_BTd,
                         void* cuda_stream) {
@@ -1363,12 +1432,12 @@ int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, c
 
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
-  if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; return 0; }
+  if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "host_lanes") == 0) { h->host_lanes = value; return 0; }
   if (strcmp(name, "ffn_cg2") == 0) { h->ffn_cg2 = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "pdl") == 0) { h->pdl = value != 0; pdl_set(h->pdl && !h->profile); drop_graphs(h); return 0; }
-  if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; return 0; }
+  if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }

@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: AVSeparationTransformer.forward on SyntheticAVDataset-shaped input.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4] [--batch B] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one forward pass of the default model (BASELINE.json configs[1]: freq_bins=257, d_model=256, nhead=4,
-2 encoder + 2 fusion layers, 2 speakers, bf16 operands) over one batch of B=256 one-second utterances per GPU
-(1 s @ 8 kHz: T=63 STFT frames, N=50 lip frames of 32x32).  The batch shards across ranks with no data-path
-collective (weak scaling: per-GPU batch fixed); NCCL is used only for the barrier and the max-over-ranks time.
-Prints ONE JSON line (rank 0).  Metric: separated utterance-seconds per second = B_total * 1 s / forward time.
+One "step" = one forward pass over one batch of B utterances per GPU.  Default workload = BASELINE.json configs[1]
+(c2): default model (freq_bins=257, d_model=256, nhead=4, 2 encoder + 2 fusion layers, 2 speakers), bf16 operands,
+B=256 one-second utterances per GPU (1 s @ 8 kHz: T=63 STFT frames, N=50 lip frames of 32x32).  The other configs of
+BASELINE.json are selectable: c1 (same model, B=8), c3 (long form, 10 s @ 16 kHz: T=1251, N=500, B=32), c4 (scaled
+model d=512, 8 heads, 6+6 layers, 3 speakers, B=256).
+
+N = 1: `value` = forward with the inputs resident in HBM.
+N > 1: `value` = the north-star data path: the root (rank 0) holds the global batch, every rank pulls its
+shard of the inputs over NVLink, runs the forward, and pushes `separated` + `masks` (fp32) back into the root's global
+buffers -- scatter and gather inside the timed region, executed by the copy engines on peer memory
+(avsep_b200/sharded.py).  The no-traffic variant (every rank's shard stays on its GPU) is reported beside it as
+`sharded_no_traffic`.  Weak scaling: the per-GPU batch is fixed.
+Prints ONE JSON line (rank 0).  Metric: separated utterance-seconds per second = B_total * clip seconds / time.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -30,61 +39,96 @@ for _p in (ROOT, PKG):
 
 METRIC = "separated utterance-sec/sec"
 UNIT = "utt-s/s"
-MODEL = dict(freq_bins=257, d_model=256, nhead=4, num_encoder_layers=2, num_fusion_layers=2, num_speakers=2)
+DEFAULT_MODEL = dict(freq_bins=257, d_model=256, nhead=4, num_encoder_layers=2, num_fusion_layers=2, num_speakers=2)
+SCALED_MODEL = dict(freq_bins=257, d_model=512, nhead=8, num_encoder_layers=6, num_fusion_layers=6, num_speakers=3)
+# BASELINE.json configs; (T, N) follow dataset.py:63-65,114 (T = 1 + samples // hop, N = 25 fps x seconds x 2 speakers)
+CONFIGS = {
+    "c1": dict(name="configs[0]: demo default, B=8", model=DEFAULT_MODEL, batch=8, T=63, N=50, hw=32, seconds=1.0,
+               cpu_sample=8, audio="1 s @ 8 kHz"),
+    "c2": dict(name="configs[1]: default model, B=256 throughput batch", model=DEFAULT_MODEL, batch=256, T=63, N=50,
+               hw=32, seconds=1.0, cpu_sample=32, audio="1 s @ 8 kHz"),
+    "c3": dict(name="configs[2]: long form", model=DEFAULT_MODEL, batch=32, T=1251, N=500, hw=32, seconds=10.0,
+               cpu_sample=4, audio="10 s @ 16 kHz"),
+    "c4": dict(name="configs[3]: scaled model (d=512, 8 heads, 6+6 layers, 3 speakers)", model=SCALED_MODEL, batch=256,
+               T=63, N=50, hw=32, seconds=1.0, cpu_sample=8, audio="1 s @ 8 kHz"),
+}
+# module-level view of the active config (tests and tools import these names)
+MODEL = dict(DEFAULT_MODEL)
 CLIP_SECONDS = 1.0
-T_FRAMES, N_FRAMES, FRAME_HW = 63, 50, 32          # dataset.py:63-65,114 at 8 kHz / 1 s / hop 128 / 25 fps x 2 speakers
-CPU_SAMPLE_B = 32                                  # CPU throughput is flat beyond B~32
+T_FRAMES, N_FRAMES, FRAME_HW = 63, 50, 32
+CPU_SAMPLE_B = 32
 
 
-def workload_name(batch):
-    return (f"configs[1]: default model (F=257,d=256,H=4,2+2 layers,S=2), B={batch}/GPU, 1 s @ 8 kHz "
-            f"(T={T_FRAMES}, N={N_FRAMES}, {FRAME_HW}x{FRAME_HW}), SyntheticAVDataset-shaped")
+def select_config(key):
+    global MODEL, CLIP_SECONDS, T_FRAMES, N_FRAMES, FRAME_HW, CPU_SAMPLE_B
+    c = CONFIGS[key]
+    MODEL = dict(c["model"])
+    CLIP_SECONDS, T_FRAMES, N_FRAMES, FRAME_HW, CPU_SAMPLE_B = c["seconds"], c["T"], c["N"], c["hw"], c["cpu_sample"]
+    return c
+
+
+def workload_name(batch, key="c2"):
+    c, m = CONFIGS[key], CONFIGS[key]["model"]
+    return (f"{c['name']} (F={m['freq_bins']},d={m['d_model']},H={m['nhead']},{m['num_encoder_layers']}+"
+            f"{m['num_fusion_layers']} layers,S={m['num_speakers']}), B={batch}/GPU, {c['audio']} "
+            f"(T={c['T']}, N={c['N']}, {c['hw']}x{c['hw']}), SyntheticAVDataset-shaped")
 
 
 # ----------------------------------------------------------------------------------------------
-# clocks
+# clocks: in-process NVML sampling on a thread (a 50 ms nvidia-smi loop misses a 13 ms timed region)
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons = index, [], None, set()
+        self.h, self.err, self._stop, self._thr = None, None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                                  # pragma: no cover - no NVML on the build box
+            self.err = f"NVML unavailable ({e})"
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            try:
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for name, bit in self.REASONS:
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception as e:                                  # pragma: no cover
+            self.err = str(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        def loop():
+            while not self._stop.is_set():
+                self.sample()
+                time.sleep(0.001)
+        self._stop.clear()
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def report(self, how):
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+               "samples": len(self.sm), "reasons": sorted(self.reasons), "how": how}
+        if self.err:
+            out["note"] = self.err
+        return out
 
 
 def measured_peaks():
@@ -97,12 +141,26 @@ def measured_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
 
 
+def source_hash():
+    """Identifies the kernel sources of the build being timed (profiles/traffic.json is only valid for its own build)."""
+    h = hashlib.sha256()
+    csrc = os.path.join(PKG, "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 # ----------------------------------------------------------------------------------------------
-# algorithmic work per kernel class, per forward of B utterances (SURVEY.md section 8d formulas)
+# algorithmic work per kernel class, per forward of B utterances (SURVEY.md section 8d formulas; DESIGN.md section 4)
 # ----------------------------------------------------------------------------------------------
-def kernel_work(B):
-    d, F, S = MODEL["d_model"], MODEL["freq_bins"], MODEL["num_speakers"]
-    Le, Lf, T, N = MODEL["num_encoder_layers"], MODEL["num_fusion_layers"], T_FRAMES, N_FRAMES
+def kernel_work(B, model=None, T=None, N=None):
+    m = MODEL if model is None else model
+    T = T_FRAMES if T is None else T
+    N = N_FRAMES if N is None else N
+    d, F, S = m["d_model"], m["freq_bins"], m["num_speakers"]
+    Le, Lf = m["num_encoder_layers"], m["num_fusion_layers"]
     Ma, Mv = B * T, B * N
     rows_enc = Le * (Ma + Mv)
     cnn_per_frame = 2 * 256 * 32 * 9 + 2 * 64 * 64 * 288 + 2 * 16 * 128 * 576
@@ -115,17 +173,24 @@ def kernel_work(B):
         "visual_cnn": Mv * cnn_per_frame, "gemm.frame_proj": Mv * 2 * 128 * d,
         "gemm.dec0": Ma * 2 * 2 * d * d, "gemm.dec3_tail": Ma * 2 * S * F * 2 * d,
     }
-    flops["ffn.fused"] = flops["gemm.ffn1"] + flops["gemm.ffn2"]     # linear1 + act + linear2 + residual + LN in one kernel
-    n_ln = 2 + 2 * Le * 2 + 2 * Lf            # launches per forward
-    ln_rows = (1 + 2 * Le) * Ma + (1 + 2 * Le) * Mv + 2 * Lf * Ma
+    base_total = sum(flops.values())
+    # fused kernels = sums of the classes they contain (each class is still counted once in the total)
+    flops["ffn.fused"] = flops["gemm.ffn1"] + flops["gemm.ffn2"]
+    per_row_layer = 2 * 3 * d * d + 2 * d * d + 2 * 2 * 4 * d * d            # qkv + out_proj + ffn1 + ffn2 per row
+    flops["layer.audio_enc"] = Le * (Ma * per_row_layer + B * 4 * d * T * T)
+    flops["layer.visual_enc"] = Le * (Mv * per_row_layer + B * 4 * d * N * N)
+    per_row_fus = 2 * d * d + 2 * d * d + 2 * 2 * 4 * d * d                  # q + out_proj + ffn1 + ffn2 per row
+    flops["layer.fusion"] = Lf * (Ma * per_row_fus + B * 4 * d * T * T)
     bytes_ = {
         # x (fp32) + y (fp32) in, x (fp32) + normalised operand (bf16) out = 14 B per element
-        "add_layernorm": ln_rows * d * 14,
+        "add_layernorm": 14 * d,      # per row; multiplied by the rows of the launches below
         # masks + separated fp32 out, mixed fp32 in, bf16 A operand in
         "gemm.dec3_tail": Ma * S * F * 8 + B * F * T * 4 + Ma * 2 * d * 2,
         "prep_audio": B * F * T * 4 + B * (T + 2) * ((F + 7) // 8 * 8) * 2,
     }
-    return flops, bytes_, n_ln
+    ln_rows = (1 + 2 * Le) * Ma + (1 + 2 * Le) * Mv + 2 * Lf * Ma
+    bytes_["add_layernorm"] = ln_rows * d * 14
+    return flops, bytes_, base_total
 
 
 def shard_bounds(rank, world, per_rank_batch):
@@ -133,9 +198,10 @@ def shard_bounds(rank, world, per_rank_batch):
     return rank * per_rank_batch, (rank + 1) * per_rank_batch
 
 
-def throughput(world, per_rank_batch, ms_per_step):
+def throughput(world, per_rank_batch, ms_per_step, clip_seconds=None):
     """Whole-job utterance-seconds per second from the slowest rank's step time."""
-    return world * per_rank_batch * CLIP_SECONDS / (ms_per_step * 1e-3)
+    cs = CLIP_SECONDS if clip_seconds is None else clip_seconds
+    return world * per_rank_batch * cs / (ms_per_step * 1e-3)
 
 
 def max_over_ranks_cpu(x):
@@ -148,38 +214,58 @@ def max_over_ranks_cpu(x):
 
 
 def total_flops(B):
-    return sum(v for k, v in kernel_work(B)[0].items() if k != "ffn.fused")   # ffn.fused = ffn1 + ffn2, counted once
+    return kernel_work(B)[2]
 
 
 # ----------------------------------------------------------------------------------------------
-# the reference's CPU implementation (oracle port) -- the ONLY place bench.py touches oracle/
+# the reference's own CPU implementation -- the ONLY place bench.py touches oracle/
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_throughput(state, mixed, frames, min_seconds=10.0, max_reps=8):
+def make_cpu_reference(state):
+    """Returns (kind, forward(mixed, frames)).  kind "reference": the UNMODIFIED reference modules staged under
+    oracle/_ref by oracle/make_ref.py (model.py:227-276), eval mode, no_grad; kind "port": the oracle's restatement on
+    the same torch CPU operators, used only when oracle/_ref is absent."""
     import torch
+    from oracle import make_ref
+    P = {k: v.detach().cpu() for k, v in state.items()}
+    if make_ref.ref_available():
+        ref = make_ref.load_reference_model_module()
+        model = ref.AVSeparationTransformer(**MODEL)
+        model.load_state_dict(P, strict=True)
+        model.eval()
+
+        def fwd(mixed, frames):
+            with torch.no_grad():
+                return model(mixed, frames)
+        return "reference", fwd
     from oracle import avsep_oracle_torch as otorch
     from oracle.weights import ModelConfig
     cfg = ModelConfig(**MODEL)
+    return "port", (lambda mixed, frames: otorch.forward(P, cfg, mixed, frames))
+
+
+def cpu_reference_throughput(state, mixed, frames, min_seconds=10.0, max_reps=8):
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    P = {k: v.detach().cpu() for k, v in state.items()}
-    otorch.forward(P, cfg, mixed, frames)            # warm-up
+    kind, fwd = make_cpu_reference(state)
+    fwd(mixed, frames)            # warm-up
     times = []
     t_all = time.perf_counter()
     while len(times) < max_reps and (time.perf_counter() - t_all < min_seconds or len(times) < 3):
         t0 = time.perf_counter()
-        otorch.forward(P, cfg, mixed, frames)
+        fwd(mixed, frames)
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return mixed.shape[0] * CLIP_SECONDS / best, cores, best, len(times)
+    return mixed.shape[0] * CLIP_SECONDS / best, cores, best, len(times), kind
 
 
-def build_state(seed=0):
+def build_state(seed=0, precision="bf16"):
     """Random-init weights of the architecture (torch default init, as the reference constructs them), with
     non-trivial BatchNorm statistics.  Uses only torch.nn parameter containers -- no kernels involved."""
     import torch
     from avsep_b200 import AVSeparationTransformer
     torch.manual_seed(seed)
-    model = AVSeparationTransformer(**MODEL, precision="bf16")
+    model = AVSeparationTransformer(**MODEL, precision=precision)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for name, buf in model.named_buffers():
@@ -191,7 +277,7 @@ def build_state(seed=0):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU forward (oracle port on torch CPU ops, all host threads)."""
+    """--impl reference: the reference's own CPU forward on all host threads, a bounded sample of the workload."""
     if rank != 0:
         return
     import torch
@@ -199,26 +285,25 @@ def run_reference(args, rank, world):
     model = build_state()
     state = model.state_dict()
     mixed, frames = synthetic_batch(CPU_SAMPLE_B, MODEL["freq_bins"], T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=100)
-    from oracle import avsep_oracle_torch as otorch
-    from oracle.weights import ModelConfig
-    cfg = ModelConfig(**MODEL)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    P = {k: v.detach().cpu() for k, v in state.items()}
+    kind, fwd = make_cpu_reference(state)
     for _ in range(max(1, min(args.warmup, 3))):
-        otorch.forward(P, cfg, mixed, frames)
+        fwd(mixed, frames)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        otorch.forward(P, cfg, mixed, frames)
+        fwd(mixed, frames)
     dt = time.perf_counter() - t0
     value = args.steps * CPU_SAMPLE_B * CLIP_SECONDS / dt
-    sample = f"B={CPU_SAMPLE_B} utterances of the same workload per step (CPU throughput is flat beyond B~32)"
+    sample = (f"B={CPU_SAMPLE_B} utterances of the same workload per step (CPU throughput is flat beyond B~32); "
+              + ("the unmodified reference modules (oracle/_ref, model.py:227-276), eval mode, no_grad" if kind == "reference"
+                 else "oracle port on the same torch CPU operators (oracle/_ref not staged)"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args.batch, args.config), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -246,6 +331,7 @@ def run_ours(args, rank, local_rank, world):
     # Everything except the final JSON line goes to stderr (NCCL / torchrun print to stdout on their own).
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from avsep_b200.synth import synthetic_batch
@@ -272,51 +358,159 @@ def run_ours(args, rank, local_rank, world):
 
     B = args.batch
     F, S = MODEL["freq_bins"], MODEL["num_speakers"]
+    T, N, HW = T_FRAMES, N_FRAMES, FRAME_HW
     model = build_state().to(dev)
     model.prepack(dev)
     eng = model.engine
-    # rotating input sets: inputs (69 MB) + outputs (133 MB) + activations (~350 MB) per step already exceed the
-    # 126 MB L2; three distinct input sets make sure no step re-reads the previous step's inputs from L2.
-    n_sets = 3
-    lo, hi = shard_bounds(rank, world, B)     # this rank's utterances of the global batch; seeds differ per shard
-    sets = [synthetic_batch(hi - lo, F, T_FRAMES, N_FRAMES, FRAME_HW, FRAME_HW, seed=100003 * i + lo, device=dev)
-            for i in range(n_sets)]
-    sep = torch.empty((B, S, F, T_FRAMES), device=dev)
-    masks = torch.empty_like(sep)
-    import ctypes as C
     stream = torch.cuda.current_stream()
+    st = C.c_void_p(stream.cuda_stream)
 
-    def step(i):
-        mixed, frames = sets[i % n_sets]
-        rc = eng.lib.avsep_forward(eng.h, mixed.data_ptr(), frames.data_ptr(), B, T_FRAMES, N_FRAMES, FRAME_HW,
-                                   FRAME_HW, sep.data_ptr(), masks.data_ptr(), None, 0,
-                                   C.c_void_p(stream.cuda_stream))
+    def fwd_raw(mixed, frames, sep, masks, b=None):
+        rc = eng.lib.avsep_forward(eng.h, mixed.data_ptr(), frames.data_ptr(), mixed.shape[0] if b is None else b, T, N,
+                                   HW, HW, sep.data_ptr(), masks.data_ptr(), None, 0, st)
         if rc != 0:
             raise RuntimeError(eng.lib.avsep_last_error(eng.h).decode())
 
+    # rotating input sets: inputs + outputs + activations per step already exceed the 126 MB L2 at B=256; three distinct
+    # input sets make sure no step re-reads the previous step's inputs from L2.
+    n_sets = 3
+    lo, hi = shard_bounds(rank, world, B)     # this rank's utterances of the global batch; seeds differ per shard
+    sets = [synthetic_batch(hi - lo, F, T, N, HW, HW, seed=100003 * i + lo, device=dev) for i in range(n_sets)]
+    sep = torch.empty((B, S, F, T), device=dev)
+    masks = torch.empty_like(sep)
+
+    def step(i):
+        fwd_raw(sets[i % n_sets][0], sets[i % n_sets][1], sep, masks)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.start()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        if sampler is not None:
+            sampler.stop()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         step(i)
     launches_per_step = eng.launch_count()
-    barrier()
-    sampler = ClockSampler(torch.cuda.current_device() if rank == 0 else 0)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / args.steps
+    ms_sharded = timed(step, args.steps, 0, sampler)
+
+    # ---- N > 1 headline: scatter from the root, forward, gather to the root (copy engines over NVLink peer memory) ----
+    sharded_entry, sg = None, None
+    if world > 1:
+        from avsep_b200.sharded import PeerMemoryCuda, ShardedForward
+        shapes = dict(mixed=(F, T), frames=(N, HW, HW), out=(S, F, T))
+        sg = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets)
+        if rank == 0:
+            for s_i, (gm, gf) in enumerate(sg.root_in):
+                for r in range(world):
+                    m_r, f_r = synthetic_batch(B, F, T, N, HW, HW, seed=100003 * s_i + r * B, device=dev)
+                    gm[r * B:(r + 1) * B].copy_(m_r)
+                    gf[r * B:(r + 1) * B].copy_(f_r)
+        barrier()
+
+        def sg_timed(steps, warmup):
+            for i in range(warmup):
+                sg.step(i)
+            sg.finish()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                sg.step(i)
+            if rank != 0:
+                stream.wait_stream(sg.s_in)
+                stream.wait_stream(sg.s_out)      # this rank's last push is inside its timed interval
+            e1.record(stream)
+            sg.finish()
+            wall = time.perf_counter() - t0
+            return max_over_ranks(e0.elapsed_time(e1)) / steps, max_over_ranks(wall * 1e3) / steps
+
+        ms_sg, ms_sg_wall = sg_timed(args.steps, max(args.warmup, 4))
+        # verify the gathered result on the root: shard r of the last step == the root's own forward of those inputs
+        verified = None
+        if rank == 0:
+            i_last = args.steps - 1
+            gm, gf = sg.root_in[i_last % n_sets]
+            gsep, gmasks = sg.root_out[i_last & 1]
+            verified = True
+            for r in sorted({0, 1, world - 1}):
+                fwd_raw(gm[r * B:(r + 1) * B], gf[r * B:(r + 1) * B], sep, masks)
+                torch.cuda.synchronize()
+                verified = verified and bool(torch.equal(gsep[r * B:(r + 1) * B], sep)) and \
+                    bool(torch.equal(gmasks[r * B:(r + 1) * B], masks))
+        barrier()
+        sharded_entry = {"ms_per_step": round(ms_sharded, 4), "value": throughput(world, B, ms_sharded),
+                         "what": "every rank's shard stays on its GPU: inputs generated per rank, outputs not gathered"}
+        ms_per_step = max(ms_sg, ms_sg_wall)     # device time of the slowest rank; wall clock as the cross-rank check
+    else:
+        ms_per_step = ms_sharded
     value = throughput(world, B, ms_per_step)
+    if rank == 0 and len(sampler.sm) < 5:
+        # a short timed region can fall between NVML samples: probe the same steps for ~150 ms right after it
+        sampler.start()
+        t0 = time.perf_counter()
+        i = 0
+        while time.perf_counter() - t0 < 0.15:
+            step(i)
+            i += 1
+            if i % 16 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        sampler.stop()
+        clocks = sampler.report("NVML in-process, 1 ms period: timed region + the same steps for 150 ms right after it")
+    elif rank == 0:
+        clocks = sampler.report("NVML in-process, 1 ms period, during the timed region")
+    else:
+        clocks = None
+    barrier()
+
+    # ---- python_api: the drop-in module call `model(mixed, frames)` (what a user of the reference writes) -------------
+    def python_api_ms(bsz, steps):
+        ms_in = [(m[:bsz].contiguous(), f[:bsz].contiguous()) for m, f in sets]
+        for i in range(6):
+            model(*ms_in[i % n_sets])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            out = model(*ms_in[i % n_sets])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        del out
+        ms_py = e0.elapsed_time(e1) / steps
+        o_s, o_m = torch.empty((bsz, S, F, T), device=dev), torch.empty((bsz, S, F, T), device=dev)
+        for i in range(6):
+            fwd_raw(ms_in[i % n_sets][0], ms_in[i % n_sets][1], o_s, o_m)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(steps):
+            fwd_raw(ms_in[i % n_sets][0], ms_in[i % n_sets][1], o_s, o_m)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return ms_py, e0.elapsed_time(e1) / steps
+
+    python_api = None
+    if world == 1:
+        python_api = {}
+        for bsz in sorted({min(8, B), B}):
+            ms_py, ms_c = python_api_ms(bsz, max(20, min(args.steps, 100)))
+            python_api[f"B={bsz}"] = {"module_call_ms": round(ms_py, 4), "c_abi_ms": round(ms_c, 4),
+                                      "ratio": round(ms_py / ms_c, 3), "value": throughput(1, bsz, ms_py)}
 
     # ---- e2e: the public host-buffer call; pinned inputs H2D and results D2H every step -----------------
     h_sets = [(m.cpu().pin_memory(), f.cpu().pin_memory()) for m, f in sets[:2]]
-    h_out = [(torch.empty((B, S, F, T_FRAMES)).pin_memory(), torch.empty((B, S, F, T_FRAMES)).pin_memory())
-             for _ in range(2)]
+    h_out = [(torch.empty((B, S, F, T)).pin_memory(), torch.empty((B, S, F, T)).pin_memory()) for _ in range(2)]
     e2e_steps = max(4, min(args.steps, 20))
 
     def e2e_run(n):
@@ -345,81 +539,84 @@ def run_ours(args, rank, local_rank, world):
         eng.forward_host(h_sets[i % 2][0], h_sets[i % 2][1], h_out[0][0], h_out[0][1])
     e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    h_sep = h_out[0][0]
-    h_masks = h_out[0][1]
     e2e_stream_value = world * B * CLIP_SECONDS * e2e_steps / e2e_s
     e2e_sync_value = world * B * CLIP_SECONDS * 4 / e2e_sync_s
-    # both are the repo's public host-buffer API; report the faster form (on one GPU the streaming form is PCIe-bound
-    # and ~30 % ahead; with 8 ranks sharing one host the copies of all ranks contend and the forms are close)
     e2e_value = max(e2e_stream_value, e2e_sync_value)
     h2d = (h_sets[0][0].numel() + h_sets[0][1].numel()) * 4
-    d2h = (h_sep.numel() + h_masks.numel()) * 4
+    d2h = (h_out[0][0].numel() + h_out[0][1].numel()) * 4
+    # host <-> device copy ceiling of this box, measured the way the e2e path copies (one cudaMemcpyAsync per buffer
+    # per direction, both directions at once, every rank at the same time): names the link the e2e number sits on
+    cp_in, cp_out = torch.cuda.Stream(), torch.cuda.Stream()
+    d_in = [torch.empty_like(t, device=dev) for t in h_sets[0]]
 
-    # ---- N > 1: the same steps with the outputs collected on rank 0 (the headline keeps every rank's
-    # outputs on its own GPU; a consumer that wants them in one place pays an NCCL gather over NVLink).  Two wire
-    # formats: masks + separated in fp32 (what the reference returns), and masks only in bf16 (rank 0 holds the
-    # mixture and can rebuild `separated = masks * mixed`); each measured back to back and with the gather of step i
-    # overlapped with the kernels of step i+1 (two output buffer sets).
-    gathered = None
+    def copy_round():
+        with torch.cuda.stream(cp_in):
+            for d_t, h_t in zip(d_in, h_sets[0]):
+                d_t.copy_(h_t, non_blocking=True)
+        with torch.cuda.stream(cp_out):
+            h_out[0][0].copy_(sep, non_blocking=True)
+            h_out[0][1].copy_(masks, non_blocking=True)
+
+    for _ in range(2):
+        copy_round()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(6):
+        copy_round()
+    torch.cuda.synchronize()
+    copy_s = max_over_ranks(time.perf_counter() - t0) / 6
+    barrier()
+    host_link = {"h2d_gbs_per_rank": round(h2d / copy_s / 1e9, 1), "d2h_gbs_per_rank": round(d2h / copy_s / 1e9, 1),
+                 "bidirectional_copy_ms_per_step": round(copy_s * 1e3, 3), "ranks_concurrent": world,
+                 "ceiling_value": world * B * CLIP_SECONDS / copy_s,
+                 "what": "pinned-memory copies of one step's inputs and outputs, both directions at once, all ranks at once"}
+
+    # ---- N > 1 side entries -----------------------------------------------------------------------------------------
+    extras_multi = None
     if world > 1:
-        gathered = {}
+        extras_multi = {}
+        # NCCL variant of the same data path (dist.scatter of the inputs, dist.gather of masks + separated, fp32)
+        G = world * B
         sep2, masks2 = torch.empty_like(sep), torch.empty_like(masks)
-        out_sets = [(sep, masks), (sep2, masks2)]
+        loc_m, loc_f = torch.empty((B, F, T), device=dev), torch.empty((B, N, HW, HW), device=dev)
+        if rank == 0:
+            gm, gf = sg.root_in[0]
+            gsep, gmasks = sg.root_out[0]
+            sc_m, sc_f = list(gm.view(world, B, F, T).unbind(0)), list(gf.view(world, B, N, HW, HW).unbind(0))
+            ga_s, ga_m = list(gsep.view(world, B, S, F, T).unbind(0)), list(gmasks.view(world, B, S, F, T).unbind(0))
+        else:
+            sc_m = sc_f = ga_s = ga_m = None
 
-        def step_into(i, o):
-            mixed, frames = sets[i % n_sets]
-            rc = eng.lib.avsep_forward(eng.h, mixed.data_ptr(), frames.data_ptr(), B, T_FRAMES, N_FRAMES, FRAME_HW,
-                                       FRAME_HW, out_sets[o][0].data_ptr(), out_sets[o][1].data_ptr(), None, 0,
-                                       C.c_void_p(stream.cuda_stream))
-            if rc != 0:
-                raise RuntimeError(eng.lib.avsep_last_error(eng.h).decode())
+        def nccl_step(i):
+            dist.scatter(loc_m, sc_m, src=0)
+            dist.scatter(loc_f, sc_f, src=0)
+            fwd_raw(loc_m, loc_f, sep2, masks2)
+            dist.gather(sep2, ga_s, dst=0)
+            dist.gather(masks2, ga_m, dst=0)
 
-        wires = (("masks+separated fp32", lambda o: (out_sets[o][1], out_sets[o][0])),
-                 ("masks bf16", lambda o: (out_sets[o][1].to(torch.bfloat16),)))
-        for tag, pick in wires:
-            for overlapped in (False, True):
-                # destination lists on rank 0, one per output buffer set
-                dst = [[[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in pick(o)] for o in (0, 1)]
-                pending = [None, None]
-
-                def gstep(i):
-                    o = i & 1 if overlapped else 0
-                    if pending[o] is not None:                 # the gather that last read this buffer set
-                        for w in pending[o]:
-                            w.wait()
-                    step_into(i, o)
-                    works = [dist.gather(t, gl, dst=0, async_op=True) for t, gl in zip(pick(o), dst[o])]
-                    if overlapped:
-                        pending[o] = works                     # the next step (other buffer set) runs under it
-                    else:
-                        for w in works:
-                            w.wait()
-
-                def drain():
-                    for o in (0, 1):
-                        if pending[o] is not None:
-                            for w in pending[o]:
-                                w.wait()
-                            pending[o] = None
-
-                for i in range(4):
-                    gstep(i)
-                drain()
-                barrier()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n_g = max(6, min(args.steps, 50))
-                g0.record(stream)
-                for i in range(n_g):
-                    gstep(i)
-                drain()
-                g1.record(stream)
-                barrier()
-                g_ms = max_over_ranks(g0.elapsed_time(g1)) / n_g
-                gathered[tag + (", overlapped with the next step" if overlapped else "")] = {
-                    "ms_per_step": round(g_ms, 4), "value": throughput(world, B, g_ms),
-                    "bytes_into_rank0_per_step": sum(t.numel() * t.element_size() for t in pick(0)) * (world - 1)}
-                del dst
-        del sep2, masks2
+        n_g = max(6, min(args.steps, 30))
+        ms_nccl = timed(nccl_step, n_g, 3)
+        extras_multi["nccl_scatter_gather_fp32"] = {
+            "ms_per_step": round(ms_nccl, 4), "value": throughput(world, B, ms_nccl),
+            "what": "same data path with dist.scatter / dist.gather (NCCL send/recv kernels, in stream order, no overlap)"}
+        # strong scaling of configs[1] as BASELINE.md states it: B=256 in total, 256/N per GPU (no traffic)
+        if B % world == 0 and B // world >= 1:
+            bs = B // world
+            o_s, o_m = torch.empty((bs, S, F, T), device=dev), torch.empty((bs, S, F, T), device=dev)
+            ins = [(m[:bs].contiguous(), f[:bs].contiguous()) for m, f in sets]
+            ms_strong = timed(lambda i: fwd_raw(ins[i % n_sets][0], ins[i % n_sets][1], o_s, o_m), 50, 6)
+            extras_multi["strong_scaling_global_batch"] = {
+                "global_batch": B, "per_gpu_batch": bs, "ms_per_step": round(ms_strong, 4),
+                "value": throughput(world, bs, ms_strong),
+                "what": "BASELINE.md reading of configs[1]: the fixed global batch split over the GPUs, outputs stay sharded"}
+        sweep = {}
+        for bs in (8, 64, 1024):                       # configs[4]: per-GPU batch sweep (no traffic), this N
+            ins = [synthetic_batch(bs, F, T, N, HW, HW, seed=7 + lo, device=dev)]
+            o_s, o_m = torch.empty((bs, S, F, T), device=dev), torch.empty((bs, S, F, T), device=dev)
+            ms_b = timed(lambda i: fwd_raw(ins[0][0], ins[0][1], o_s, o_m), 30, 6)
+            sweep[f"B={bs}"] = {"ms_per_step": round(ms_b, 4), "value": throughput(world, bs, ms_b)}
+            del ins, o_s, o_m
+        extras_multi["per_gpu_batch_sweep"] = sweep
 
     # ---- per-kernel pass (same steps again, every launch bracketed by CUDA events on the launching stream) ----
     eng.set_profile(True)
@@ -437,7 +634,7 @@ def run_ours(args, rank, local_rank, world):
         return
 
     peaks = measured_peaks()
-    flops, bytes_, _ = kernel_work(B)
+    flops, bytes_, flops_total = kernel_work(B)
     tot_ms = sum(v[1] for v in prof.values()) or 1.0
     breakdown = {}
     for label, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
@@ -446,23 +643,30 @@ def run_ours(args, rank, local_rank, world):
                  "share": round(ms / tot_ms, 4)}
         if label in flops and label != "gemm.dec3_tail":
             entry["tflops"] = round(flops[label] / (per_step_ms * 1e-3) / 1e12, 2)
-            entry["frac_of_tensor_peak"] = round(entry["tflops"] / peaks["tensor_sustained"], 4)
+            entry["frac_of_tensor_peak"] = round(entry["tflops"] / peaks["tensor_burst"], 4)
         if label in bytes_:
             entry["gbs"] = round(bytes_[label] / (per_step_ms * 1e-3) / 1e9, 1)
             entry["frac_of_hbm_peak"] = round(entry["gbs"] / peaks["hbm"], 4)
         breakdown[label] = entry
     top = next(iter(breakdown))
     te = breakdown[top]
-    traffic = None      # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    # DRAM bytes per launch of the dominant kernel from the ncu --set full capture of THIS build (the capture records
+    # the hash of the kernel sources it was taken from; a stale capture is not reported)
+    traffic, traffic_note = None, "no ncu capture recorded for this build"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and B == 256:
+    if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top, {}).get("traffic")
+            tj = json.load(f)
+        if tj.get("src_hash") == source_hash() and tj.get("batch") == B and tj.get("config") == args.config:
+            traffic = tj.get("kernels", {}).get(top, {}).get("traffic")
+            traffic_note = tj.get("source")
+        else:
+            traffic_note = "profiles/traffic.json was captured from a different build / workload"
     n_top = max(1, te["launches_per_step"])
     if "tflops" in te:
-        roofline = {"kernel": top, "bound": "tensor", "achieved": te["tflops"], "peak": peaks["tensor_sustained"],
-                    "unit": "TFLOP/s", "frac": round(te["tflops"] / peaks["tensor_sustained"], 4), "traffic": traffic,
-                    "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)",
+        roofline = {"kernel": top, "bound": "tensor", "achieved": te["tflops"], "peak": peaks["tensor_burst"],
+                    "unit": "TFLOP/s", "frac": round(te["tflops"] / peaks["tensor_burst"], 4), "traffic": traffic,
+                    "peak_source": peaks["source"] + " (burst bf16: every launch is timed alone, behind a spin kernel)",
                     "launch_ms": round(te["ms_per_step"] / n_top, 4),
                     "algorithmic_flops_per_launch": flops[top] / n_top}
     else:
@@ -470,84 +674,92 @@ def run_ours(args, rank, local_rank, world):
                     "frac": round(te["gbs"] / peaks["hbm"], 4), "traffic": traffic, "peak_source": peaks["source"],
                     "launch_ms": round(te["ms_per_step"] / n_top, 4),
                     "algorithmic_bytes_per_launch": bytes_[top] / n_top}
+    roofline["traffic_source"] = traffic_note
+    roofline["whole_step"] = {"model_tflops": round(flops_total / (ms_sharded * 1e-3) / 1e12, 2),
+                              "frac_of_tensor_peak": round(flops_total / (ms_sharded * 1e-3) / 1e12 / peaks["tensor_burst"], 4)}
 
-    # Secondary limiter of the GEMM-class kernels (tools/tma_rate.cu): a B200 SM ingests TMA boxes from L2 at
-    # 41.4 B/clk = 81 GB/s whatever the number of boxes in flight or of SMs streaming (12 TB/s chip-wide).  The fused
-    # FFN re-streams W1 + W2 (1 MB) for every 128-row tile, plus the A tile (64 KB) and the fp32 residual (128 KB).
-    if top == "ffn.fused":
-        d = MODEL["d_model"]
-        tiles = sum((m + 127) // 128 for m in ([B * T_FRAMES] * (MODEL["num_encoder_layers"] + MODEL["num_fusion_layers"])
-                                                + [B * N_FRAMES] * MODEL["num_encoder_layers"]))
-        per_tile = 2 * 4 * d * d * 2 + 128 * d * 2 + 128 * d * 4
-        sms_busy = min(148, max(1, tiles // n_top))
-        gbs_per_sm = tiles * per_tile / (te["ms_per_step"] * 1e-3) / 1e9 / sms_busy
-        roofline["operand_stream"] = {"what": "TMA ingest L2 -> shared memory per SM, whole kernel incl. prologue and epilogue",
-                                      "achieved_gb_s_per_sm": round(gbs_per_sm, 1), "peak_gb_s_per_sm": 81.0,
-                                      "frac": round(gbs_per_sm / 81.0, 3), "peak_source": "tools/tma_rate.cu on this pool's B200"}
-
+    cfg_entry = {"workload": workload_name(B, args.config), "config": args.config, "global_batch": world * B,
+                 "rank_cpu_affinity_cores": numa_cores,
+                 "l2": f"{n_sets} rotating input sets; per-step footprint (inputs+outputs+activations) > 126 MB L2"
+                       if B * T >= 4096 else f"{n_sets} rotating input sets (small batch: the working set fits L2, as it does in use)"}
+    if world > 1:
+        cfg_entry["parallelism"] = (f"batch-sharded x{world}: inputs scattered from rank 0, separated+masks (fp32) gathered "
+                                    "to rank 0 inside the timed region, copy engines over NVLink peer memory")
+    else:
+        cfg_entry["parallelism"] = "batch-sharded x1"
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(B), "global_batch": world * B, "parallelism": f"batch-sharded x{world}", "rank_cpu_affinity_cores": numa_cores,
-                   "l2": f"{n_sets} rotating input sets; per-step footprint (inputs+outputs+activations) > 126 MB L2"},
-        "clocks": clocks,
+        "dtype": "bf16", "data": "synthetic", "config": cfg_entry, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
                 "api": ("avsep_forward_host_async on two I/O slots + avsep_host_wait" if e2e_stream_value >= e2e_sync_value
                         else "avsep_forward_host (one call per batch)") +
                        " (pinned host buffers; every step's H2D and D2H inside the timed region)",
-                "streaming_value": e2e_stream_value, "sync_call_value": e2e_sync_value},
+                "streaming_value": e2e_stream_value, "sync_call_value": e2e_sync_value, "host_link": host_link},
         "gpu_launches": launches_per_step * args.steps,
-        "gflop_per_step": total_flops(B) / 1e9,
-        "model_tflops": round(total_flops(B) / (ms_per_step * 1e-3) / 1e12, 2),
+        "gflop_per_step": flops_total / 1e9,
+        "model_tflops": round(flops_total / (ms_sharded * 1e-3) / 1e12, 2),
         "roofline": roofline,
         "kernels": breakdown,
     }
-    if gathered is not None:
-        out["outputs_gathered_to_rank0"] = gathered
-    if world == 1:
+    if python_api is not None:
+        out["python_api"] = python_api
+    if world > 1:
+        out["sharded_no_traffic"] = sharded_entry
+        out["scatter_gather"] = {
+            "ms_per_step_device": round(ms_sg, 4), "ms_per_step_wall": round(ms_sg_wall, 4),
+            "bytes_out_of_rank0_per_step": sg.bytes_in_per_step * (world - 1),
+            "bytes_into_rank0_per_step": sg.bytes_out_per_step * (world - 1),
+            "rank0_egress_gbs": round(sg.bytes_in_per_step * (world - 1) / (ms_per_step * 1e-3) / 1e9, 1),
+            "rank0_ingress_gbs": round(sg.bytes_out_per_step * (world - 1) / (ms_per_step * 1e-3) / 1e9, 1),
+            "gathered_equals_local_forward": verified,
+            "note": "the root's NVLink ports carry every other rank's inputs out and outputs in: once a step is shorter "
+                    "than those transfers the 8-GPU value is bound by one GPU's NVLink bandwidth, not by the kernels"}
+        out.update(extras_multi)
+    if world == 1 and args.config in ("c1", "c2"):
         # The same workload waveform to waveform: STFT of the 1 s mixture, forward on its magnitude,
         # masks applied to the complex mixture, inverse STFT -- three C-ABI calls per step, buffers preallocated.
         n_fft, hop, L = 2 * (F - 1), 128, int(8000 * CLIP_SECONDS)
         g = torch.Generator(device=dev).manual_seed(7)
         waves_in = [0.3 * torch.randn(B, L, device=dev, generator=g) for _ in range(n_sets)]
-        spec = torch.empty(B, F, T_FRAMES, device=dev, dtype=torch.complex64)
-        mag = torch.empty(B, F, T_FRAMES, device=dev)
+        spec = torch.empty(B, F, T, device=dev, dtype=torch.complex64)
+        mag = torch.empty(B, F, T, device=dev)
         waves_out = torch.empty(B, S, L, device=dev)
-        st = C.c_void_p(stream.cuda_stream)
 
         def wstep(i):
             frames = sets[i % n_sets][1]
             rc = eng.lib.avsep_stft(eng.h, waves_in[i % n_sets].data_ptr(), B, L, n_fft, hop, spec.data_ptr(),
                                     mag.data_ptr(), st)
-            rc = rc or eng.lib.avsep_forward(eng.h, mag.data_ptr(), frames.data_ptr(), B, T_FRAMES, N_FRAMES, FRAME_HW,
-                                             FRAME_HW, sep.data_ptr(), masks.data_ptr(), None, 0, st)
-            rc = rc or eng.lib.avsep_istft(eng.h, spec.data_ptr(), masks.data_ptr(), B, S, T_FRAMES, n_fft, hop, L,
+            rc = rc or eng.lib.avsep_forward(eng.h, mag.data_ptr(), frames.data_ptr(), B, T, N, HW, HW, sep.data_ptr(),
+                                             masks.data_ptr(), None, 0, st)
+            rc = rc or eng.lib.avsep_istft(eng.h, spec.data_ptr(), masks.data_ptr(), B, S, T, n_fft, hop, L,
                                            waves_out.data_ptr(), st)
             if rc != 0:
                 raise RuntimeError(eng.lib.avsep_last_error(eng.h).decode())
 
         w_steps = max(4, min(args.steps, 50))
-        for i in range(3):
-            wstep(i)
-        torch.cuda.synchronize()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record(stream)
-        for i in range(w_steps):
-            wstep(i)
-        w1.record(stream)
-        torch.cuda.synchronize()
-        w_ms = w0.elapsed_time(w1) / w_steps
+        w_ms = timed(wstep, w_steps, 3)
         out["waveform_to_waveform"] = {"ms_per_step": round(w_ms, 4), "value": throughput(1, B, w_ms), "unit": UNIT,
                                        "steps": w_steps, "samples_per_utterance": L,
                                        "calls": "avsep_stft -> avsep_forward -> avsep_istft, inputs resident"}
+    if world == 1 and args.config == "c2" and not args.no_sweep:
+        sweep = {}
+        for bs in (1, 8, 64, 1024):                    # configs[4]: per-GPU batch sweep
+            ins = synthetic_batch(bs, F, T, N, HW, HW, seed=7, device=dev)
+            o_s, o_m = torch.empty((bs, S, F, T), device=dev), torch.empty((bs, S, F, T), device=dev)
+            ms_b = timed(lambda i: fwd_raw(ins[0], ins[1], o_s, o_m), 30, 6)
+            sweep[f"B={bs}"] = {"ms_per_step": round(ms_b, 4), "value": throughput(1, bs, ms_b)}
+        out["per_gpu_batch_sweep"] = sweep
     if world == 1 and not args.no_cpu_baseline:
-        m_cpu, f_cpu = sets[0][0][:CPU_SAMPLE_B].cpu(), sets[0][1][:CPU_SAMPLE_B].cpu()
-        v, cores, best, reps = cpu_reference_throughput(model.state_dict(), m_cpu, f_cpu)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"first {CPU_SAMPLE_B} utterances of the same batch, best of {reps} forwards "
-                                         f"({best * 1e3:.0f} ms each), torch CPU ops, {cores} threads"}
+        nb = min(CPU_SAMPLE_B, B)
+        m_cpu, f_cpu = sets[0][0][:nb].cpu(), sets[0][1][:nb].cpu()
+        v, cores, best, reps, kind = cpu_reference_throughput(model.state_dict(), m_cpu, f_cpu)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"first {nb} utterances of the same batch, best of {reps} forwards "
+                                         f"({best * 1e3:.0f} ms each), "
+                                         + ("the unmodified reference modules (oracle/_ref)" if kind == "reference"
+                                            else "oracle port on torch CPU ops") + f", {cores} threads"}
     os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
@@ -558,11 +770,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (default c2 = configs[1])")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU per step (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfg = select_config(args.config)
+    if args.batch is None:
+        args.batch = cfg["batch"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -571,7 +788,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--batch", str(args.batch)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               "--config", args.config, "--batch", str(args.batch)] + \
+              (["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (["--no-sweep"] if args.no_sweep else [])
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)

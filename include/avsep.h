@@ -224,6 +224,25 @@ AVSEP_API int avsep_stft(avsep_handle* h, const float* waves, int32_t B, int32_t
 AVSEP_API int avsep_istft(avsep_handle* h, const float* spec, const float* masks, int32_t B, int32_t S, int32_t T,
                           int32_t n_fft, int32_t hop_length, int32_t L, float* waves, void* cuda_stream);
 
+/* ---- batch sharding over the GPUs of one box (BASELINE.json north_star: "inputs scattered and
+ * separated/masks gathered over NVLink") -------------------------------------------------------------------------
+ * The path shards by utterance with no collective inside the model (model.py has no op that mixes batch elements in
+ * eval mode), so the only inter-GPU traffic is the scatter of the root's inputs and the gather of the outputs.  One
+ * process per GPU: the root allocates its global input / output buffers with avsep_shared_alloc, which also returns a
+ * 64-byte inter-process handle (cudaIpcMemHandle_t); every other rank maps them with avsep_shared_open and moves its
+ * shard with avsep_copy_async, a stream-ordered copy that the copy engines execute over NVLink / NVSwitch peer
+ * memory (no SM is taken from the forward kernels, unlike a collective's send/recv CTAs).
+ * Ownership: memory from avsep_shared_alloc is freed with avsep_shared_free by the allocating process, mappings from
+ * avsep_shared_open are released with avsep_shared_close; both are also released by avsep_destroy. */
+#define AVSEP_IPC_HANDLE_BYTES 64
+AVSEP_API int avsep_shared_alloc(avsep_handle* h, size_t bytes, void** dev_ptr,
+                                 unsigned char handle_out[AVSEP_IPC_HANDLE_BYTES]);
+AVSEP_API int avsep_shared_free(avsep_handle* h, void* dev_ptr);
+AVSEP_API int avsep_shared_open(avsep_handle* h, const unsigned char handle[AVSEP_IPC_HANDLE_BYTES], void** dev_ptr);
+AVSEP_API int avsep_shared_close(avsep_handle* h, void* dev_ptr);
+/* dst / src: any mix of this device's memory, peer memory mapped with avsep_shared_open, or pinned host memory. */
+AVSEP_API int avsep_copy_async(avsep_handle* h, void* dst, const void* src, size_t bytes, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

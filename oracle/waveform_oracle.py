@@ -6,10 +6,11 @@ and tests/golden/make_waveform_golden.py, never by the product path.
                    PINNED: |stft_complex(x)| is checked against the real `_stft` of the reference
                    (tests/golden/waveform_stft.npz, generator tests/golden/make_waveform_golden.py).
   * istft_masked   weighted overlap-add inverse, y[n] = sum_i w[n-i*hop] irfft(m_i X_i)[n-i*hop] / sum_i w^2[n-i*hop].
-                   PARITY UNPINNED against the reference: the reference has no inverse (README.md:140 lists phase /
-                   iSTFT reconstruction as missing).  Anchored instead on identities: istft(stft(x)) == x for n >= 1,
-                   linearity in the masks (masks summing to 1 give waveforms summing to the mixture), and a direct
-                   O(n_fft^2) inverse DFT (`irfft_direct`) for small sizes.
+                   The reference has no inverse (README.md:140 lists phase / iSTFT reconstruction as missing), so
+                   this is PINNED on the named third-party algorithm instead: scipy.signal.istft with the reference's
+                   analysis window / hop and boundary=False (tests/test_waveform_oracle.py::
+                   test_inverse_is_scipy_signal_istft, <= 1e-9 relative), plus the identities istft(stft(x)) == x,
+                   linearity in the masks, and a direct O(n_fft^2) inverse DFT (`irfft_direct`) for small sizes.
 """
 from __future__ import annotations
 

@@ -1,6 +1,6 @@
 """Generate golden input/output vectors from the REAL reference (build container only).
 
-    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+    python tests/golden/make_golden.py [case ...]  # writes tests/golden/*.npz (all cases, or the named ones)
 
 The reference is a Python package at /root/reference/src (read-only, absent on the GPU box).
 It is imported under an alias, loaded with ``oracle.weights.make_state_dict`` (numpy RNG,
@@ -41,6 +41,9 @@ CASES = {
     "c3_long":    ("default", 1, 1251, 500, 32, 32, "dataset", 5, 5, 2.0, (4, 5)),
     # C4: scaled model d=512, H=8, 6+6 layers, 3 speakers
     "c4_scaled":  ("scaled", 1, 63, 50, 32, 32, "dataset", 6, 6, 2.0, (1, 1)),
+    # C1 at a batch that takes the large-batch schedules of the B=256 benchmark (>= 2048 rows: fused transformer
+    # layers / fused FFN, multi-group CNN, multi-tile GEMMs); outputs stored subsampled
+    "c1_batch64": ("default", 64, 63, 50, 32, 32, "dataset", 7, 7, 2.0, (4, 3)),
 }
 
 STAGES = ("audio_embed", "audio_enc", "visual_pool", "visual_embed", "visual_enc", "visual_interp", "fused")
@@ -91,7 +94,14 @@ def main():
     summary = {}
     # README.md:60 known answer: the d_model=128 demo model has 1,612,738 parameters
     assert num_parameters(ModelConfig(257, 128, 4, 2, 2, 2)) == 1612738
+    only = set(sys.argv[1:])
+    spath = os.path.join(out_dir, "SUMMARY.json")
+    if only and os.path.exists(spath):
+        with open(spath) as f:
+            summary = json.load(f)
     for name, (cname, B, T, N, Hh, Ww, kind, wseed, iseed, gain, (sf, st)) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = CONFIGS[cname]
         P = make_state_dict(cfg, seed=wseed, gain=gain)
         mixed, frames = make_inputs(cfg, B, T, N, Hh, Ww, seed=iseed, kind=kind)

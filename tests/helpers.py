@@ -8,7 +8,7 @@ import torch
 from oracle.weights import CONFIGS, make_inputs, make_state_dict
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ("tiny_up", "tiny_down", "c1_dataset", "c1_randn", "c3_long", "c4_scaled")
+GOLDEN_CASES = ("tiny_up", "tiny_down", "c1_dataset", "c1_randn", "c3_long", "c4_scaled", "c1_batch64")
 STAGES = ("audio_embed", "audio_enc", "visual_pool", "visual_embed", "visual_enc", "fused")
 
 # Stated tolerances (BASELINE.json north_star): 1e-2 abs for the bf16 path, 1e-3 for fp32/TF32.

@@ -13,11 +13,11 @@ BASE = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
 def _latest(pattern):
     files = glob.glob(os.path.join(ROOT, "profiles", pattern))
     assert files, pattern
-    return max(files, key=lambda f: int(re.search(r"r1_v(\d+)_", f).group(1)))
+    return max(files, key=lambda f: tuple(int(x) for x in re.search(r"r(\d+)_v(\d+)_", f).groups()))
 
 
 def test_single_gpu_line_has_every_contract_key():
-    d = json.load(open(_latest("r1_v*_bench.json")))
+    d = json.load(open(_latest("r[0-9]_v*_bench.json")))
     assert BASE | {"cpu_baseline"} <= set(d)
     assert d["metric"] == "separated utterance-sec/sec" and d["unit"] == "utt-s/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic"
@@ -35,14 +35,14 @@ def test_single_gpu_line_has_every_contract_key():
 
 
 def test_reference_arm_line():
-    d = json.load(open(_latest("r1_v*_bench_reference_arm.json")))
+    d = json.load(open(_latest("r[0-9]_v*_bench_reference_arm.json")))
     assert d["impl"] == "reference" and d["metric"] == "separated utterance-sec/sec"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
 
 
 def test_multi_gpu_line_is_whole_job_throughput():
-    d = json.load(open(_latest("r1_v*_bench_n8.json")))
+    d = json.load(open(_latest("r[0-9]_v*_bench_n8.json")))
     assert BASE <= set(d) and d["n_gpus"] == 8 and d["config"]["global_batch"] == 8 * 256
     assert abs(d["value"] - 8 * 256 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
     assert "outputs_gathered_to_rank0" in d

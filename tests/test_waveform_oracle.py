@@ -59,3 +59,33 @@ def test_fast_inverse_agrees_with_the_direct_dft():
     b = wo.istft_masked(spec, m, L, n_fft, hop, direct=True)
     np.testing.assert_allclose(a, b, rtol=0, atol=1e-12)
     assert a[:, 0].tolist() == [0.0, 0.0] and a[:, L - 1].tolist() == [0.0, 0.0]   # both window end points are 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_inverse_is_scipy_signal_istft(name):
+    """Pin of the inverse on a named third-party algorithm (the reference has none, README.md:140):
+    scipy.signal.istft with the reference's analysis window (np.hanning(n_fft), dataset.py:124), hop and no boundary
+    extension is the same weighted overlap-add -- irfft of every column, times the window, summed at i*hop, divided by
+    the summed squared window where that is > 1e-10.  scipy's transform pair carries a 1/sum(window) scaling
+    (scaling='spectrum'), which is undone on the input."""
+    from scipy import signal
+    z = np.load(GOLD)
+    n_fft, hop = (int(v) for v in z[name + "_geom"])
+    x = z[name + "_wave"]
+    spec = wo.stft_complex(x, n_fft, hop)
+    rng = np.random.default_rng(11)
+    masks = rng.uniform(0, 1, (2,) + spec.shape)
+    win = np.hanning(n_fft)
+    L = len(x)
+    ours = wo.istft_masked(spec, masks, L, n_fft, hop)
+    import warnings
+    for s in range(2):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")              # NOLA warning: np.hanning's end points are 0 (sample 0 has no mass)
+            _, ref = signal.istft((masks[s] * spec.astype(np.complex128)) / win.sum(), window=win, nperseg=n_fft,
+                                  noverlap=n_fft - hop, nfft=n_fft, input_onesided=True, boundary=False)
+        ref = ref[:L]
+        wss = wo.window_sum_squares(L, n_fft, hop)
+        live = wss > 1e-10                               # scipy leaves samples with no window mass un-normalised (= 0 here)
+        np.testing.assert_allclose(ours[s][live], ref[live], rtol=0, atol=1e-9 * max(1.0, np.abs(ref[live]).max()))
+        assert np.all(ours[s][~live] == 0.0)

@@ -35,6 +35,38 @@ __global__ void __launch_bounds__(64, 1) tma_rate_kernel(const __grid_constant__
   }
 }
 
+// Same ring, filled by 1-D bulk copies (cp.async.bulk, no tensor map): the source is a contiguous image of the
+// shared-memory tile (weights can be prepacked pre-swizzled, so the copy does not need the TMA's address generation).
+template <int SLOTS, int BYTES>
+__global__ void __launch_bounds__(64, 1) bulk1d_rate_kernel(const uint8_t* src, int boxes_per_mb, int own, int reps,
+                                                            long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[SLOTS];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SLOTS; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const size_t base = own ? static_cast<size_t>(blockIdx.x) * boxes_per_mb * BOX : 0;
+    const int per_mb = boxes_per_mb * BOX / BYTES;
+    const long long t0 = clock64();
+    for (int i = 0; i < reps + SLOTS; ++i) {
+      const int slot = i % SLOTS;
+      if (i >= SLOTS) mbar_wait(&full[slot], ((i / SLOTS) - 1) & 1);
+      if (i < reps) {
+        mbar_arrive_expect_tx(&full[slot], BYTES);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem + slot * BYTES)), "l"(src + base + static_cast<size_t>(i % per_mb) * BYTES),
+                       "r"(BYTES), "r"(smem_u32(&full[slot]))
+                     : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+}
+
 int main() {
   const int n_sm = 148, boxes_per_mb = 64;                 // 64 boxes of [128 rows x 64 bf16] = 1 MB
   const size_t rows = static_cast<size_t>(n_sm) * boxes_per_mb * 128;
@@ -79,5 +111,25 @@ int main() {
   }
   run(tma_rate_kernel<8>, 8, 1, 74);
   run(tma_rate_kernel<8>, 8, 1, 148);
+  auto run1d = [&](auto kern, int slots, int bytes, int own, int ctas) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, slots * bytes + 1024);
+    const int r1 = reps * BOX / bytes;
+    for (int it = 0; it < 2; ++it) {
+      kern<<<ctas, 64, slots * bytes + 1024>>>(static_cast<const uint8_t*>(buf), boxes_per_mb, own, r1, out);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
+    }
+    double worst = 0;
+    for (int i = 0; i < ctas; ++i) worst = out[i] > worst ? out[i] : worst;
+    const double bpc = double(r1) * bytes / worst;
+    printf("1-D bulk copies of %5d B, %2d in flight, %s 1 MB, %3d CTAs: %.1f B/clk/SM  (%.0f GB/s/SM, %.2f TB/s aggregate)\n",
+           bytes, slots, own ? "own " : "same", ctas, bpc, bpc * clk_khz * 1e-6, bpc * clk_khz * 1e-6 * ctas * 1e-3);
+  };
+  for (int ctas : {1, 148}) {
+    run1d(bulk1d_rate_kernel<4, 16384>, 4, 16384, 0, ctas);
+    run1d(bulk1d_rate_kernel<8, 16384>, 8, 16384, 0, ctas);
+    run1d(bulk1d_rate_kernel<4, 32768>, 4, 32768, 0, ctas);
+    run1d(bulk1d_rate_kernel<16, 4096>, 16, 4096, 0, ctas);
+  }
+  run1d(bulk1d_rate_kernel<8, 16384>, 8, 16384, 1, 148);
   return 0;
 }
