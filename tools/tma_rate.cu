@@ -67,6 +67,39 @@ __global__ void __launch_bounds__(64, 1) bulk1d_rate_kernel(const uint8_t* src, 
   }
 }
 
+// P producer warps, each streaming its own ring of SLOTS x BYTES with 1-D bulk copies (is the per-instruction cost of
+// ~370 clk a property of the issuing thread or of the SM's copy engine?)
+template <int P, int SLOTS, int BYTES>
+__global__ void __launch_bounds__(32 * P, 1) bulk1d_multi_kernel(const uint8_t* src, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[P * SLOTS];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P * SLOTS; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    uint8_t* ring = smem + w * SLOTS * BYTES;
+    uint64_t* bar = full + w * SLOTS;
+    const int per_mb = (1 << 20) / BYTES;
+    const long long t0 = clock64();
+    for (int i = 0; i < reps + SLOTS; ++i) {
+      const int slot = i % SLOTS;
+      if (i >= SLOTS) mbar_wait(&bar[slot], ((i / SLOTS) - 1) & 1);
+      if (i < reps) {
+        mbar_arrive_expect_tx(&bar[slot], BYTES);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(ring + slot * BYTES)), "l"(src + static_cast<size_t>((i + w * 7) % per_mb) * BYTES),
+                       "r"(BYTES), "r"(smem_u32(&bar[slot]))
+                     : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * P + w] = t1 - t0;
+  }
+}
+
 int main() {
   const int n_sm = 148, boxes_per_mb = 64;                 // 64 boxes of [128 rows x 64 bf16] = 1 MB
   const size_t rows = static_cast<size_t>(n_sm) * boxes_per_mb * 128;
@@ -131,5 +164,33 @@ int main() {
     run1d(bulk1d_rate_kernel<16, 4096>, 16, 4096, 0, ctas);
   }
   run1d(bulk1d_rate_kernel<8, 16384>, 8, 16384, 1, 148);
+  for (int ctas : {1, 148}) {
+    run1d(bulk1d_rate_kernel<3, 65536>, 3, 65536, 0, ctas);
+    run1d(bulk1d_rate_kernel<2, 65536>, 2, 65536, 0, ctas);
+    run1d(bulk1d_rate_kernel<6, 32768>, 6, 32768, 0, ctas);
+    run1d(bulk1d_rate_kernel<2, 32768>, 2, 32768, 0, ctas);
+  }
+  long long* outm;
+  cudaMallocManaged(&outm, n_sm * 4 * sizeof(long long));
+  auto runm = [&](auto kern, int producers, int slots, int bytes, int ctas) {
+    const int smem_bytes = producers * slots * bytes + 1024;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const int r1 = reps * BOX / bytes / producers;
+    for (int it = 0; it < 2; ++it) {
+      kern<<<ctas, 32 * producers, smem_bytes>>>(static_cast<const uint8_t*>(buf), r1, outm);
+      if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); exit(1); }
+    }
+    double worst = 0;
+    for (int i = 0; i < ctas * producers; ++i) worst = outm[i] > worst ? outm[i] : worst;
+    const double bpc = double(r1) * bytes * producers / worst;
+    printf("%d producer warps x %d copies of %5d B in flight, %3d CTAs: %.1f B/clk/SM  (%.2f TB/s aggregate)\n", producers,
+           slots, bytes, ctas, bpc, bpc * clk_khz * 1e-6 * ctas * 1e-3);
+  };
+  for (int ctas : {1, 148}) {
+    runm(bulk1d_multi_kernel<2, 4, 16384>, 2, 4, 16384, ctas);
+    runm(bulk1d_multi_kernel<4, 2, 16384>, 4, 2, 16384, ctas);
+    runm(bulk1d_multi_kernel<2, 2, 32768>, 2, 2, 32768, ctas);
+    runm(bulk1d_multi_kernel<4, 3, 8192>, 4, 3, 8192, ctas);
+  }
   return 0;
 }
