@@ -94,6 +94,7 @@ struct Workspace {   // carved from one base pointer; all offsets 1 KB aligned
   // visual side
   void *pooled, *v_op, *qkv_v, *attn_v, *ffn_v;
   float *x_v, *y_v, *kvn;
+  void* kvb;   // fused fusion stack: K|V rows of every fusion layer, projected from the interpolated visual rows (bf16)
 };
 
 }  // namespace
@@ -127,6 +128,10 @@ struct avsep_handle {
   bool cnn_tc = true;     // tensor-core (tcgen05) CNN for 32x32 frames on the bf16 path
   std::vector<EncLayerW> enc_a, enc_v;
   std::vector<FusLayerW> fus;
+  // prepacked weight streams / vector blocks of the fused transformer-stack kernel (null when the config cannot use it)
+  const uint8_t *xs_a = nullptr, *xs_v = nullptr, *xs_f = nullptr;
+  const float *xv_a = nullptr, *xv_v = nullptr, *xv_f = nullptr;
+  bool fuse_stack = true;   // whole encoder / fusion stacks in one persistent kernel (d_model = 256, 4 heads, bf16, len <= 128)
   // cached library-owned workspace
   void* own_ws = nullptr;
   size_t own_ws_bytes = 0;
@@ -241,6 +246,7 @@ size_t carve_workspace(const avsep_handle* h, Workspace& w, uint8_t* base, int B
   w.attn_v = take(Mv * d * os);
   w.ffn_v = take(Mv * 4 * d * os);
   w.kvn = static_cast<float*>(take(Mv * h->cfg.num_fusion_layers * 2 * d * 4));
+  w.kvb = take(Ma * h->cfg.num_fusion_layers * 2 * d * os);
   w.bytes = off;
   return off;
 }
@@ -356,6 +362,26 @@ int linear_resid_ln(avsep_handle* h, cudaStream_t s, const char* label, const vo
   return gemm_resid_ln(h, s, label, p, e, x, x, g, b, out_op, M, y);
 }
 
+bool stack_fusable(const avsep_handle* h, int len) {
+  return h->fuse_stack && h->xs_a != nullptr && xformer_stack_usable(h->cfg.precision, h->cfg.d_model, h->cfg.nhead, len);
+}
+
+// A whole stack in one kernel (xformer_stack_sm100.cu).  which: 0 audio encoder, 1 visual encoder, 2 fusion.
+int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, float* out_x, void* out_op,
+              const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L) {
+  StackProblem sp{};
+  sp.x_in = x_in; sp.out_x = out_x; sp.out_op = out_op; sp.fin_gamma = fin_g; sp.fin_beta = fin_b;
+  sp.wstream = which == 0 ? h->xs_a : which == 1 ? h->xs_v : h->xs_f;
+  sp.vecs = which == 0 ? h->xv_a : which == 1 ? h->xv_v : h->xv_f;
+  sp.n_layers = which == 2 ? h->cfg.num_fusion_layers : h->cfg.num_encoder_layers;
+  sp.cross = which == 2;
+  sp.kv = kv; sp.kv_ld = kv_ld;
+  sp.B = B; sp.L = L;
+  sp.act = which == 2 ? ACT_GELU : ACT_RELU;
+  CKL(which == 0 ? "layer.audio_enc" : which == 1 ? "layer.visual_enc" : "layer.fusion", launch_xformer_stack(s, sp, h->num_sms));
+  return 0;
+}
+
 // nn.TransformerEncoderLayer x L (pre-norm, ReLU FFN; model.py:48-52,59; torch transformer.py:946-950).
 // In: x (fp32 residual stream), a_op = LN_{layer0.norm1}(x).  Out: x, a_op = LN_{final}(x) (or cast when final_g == null).
 int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>& layers, int B, int L, float* x,
@@ -390,7 +416,9 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
 
 // AudioEncoder up to (not including) the transformer: Conv1d+ReLU x2, +PE (model.py:56-58), then the first
 // layer's LayerNorm: x_a (fp32) and a_op = LN_{g,b}(x_a).
-int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* g, const float* b) {
+// x_only: the fused stack kernel computes the first LayerNorm itself, so only the fp32 residual rows are written.
+int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* g, const float* b,
+                   bool x_only = false) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, F = h->cfg.freq_bins, B = w.B, T = w.T, prec = h->cfg.precision;
   const int Map = B * (T + 2);
@@ -411,14 +439,20 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     GemmEpilogue e;
     e.bias = h->bc2; e.act = ACT_RELU; e.rowmap = ROW_PAD2COMPACT; e.Lp = T + 2;
     e.pe = h->pe_a;
-    if (gemm_resid_ln(h, s, "gemm.conv1d_2", p, e, nullptr, w.x_a, g, b, w.a_op, B * T, w.y_a)) return 1;
+    if (x_only) {
+      e.out_f32 = w.x_a; e.ld_f32 = d;
+      CKL("gemm.conv1d_2", launch_gemm(s, prec, p, e));
+    } else if (gemm_resid_ln(h, s, "gemm.conv1d_2", p, e, nullptr, w.x_a, g, b, w.a_op, B * T, w.y_a)) {
+      return 1;
+    }
   }
   return snapshot(h, s, "audio_embed", w.x_a, static_cast<size_t>(B) * T * d, false);
 }
 
 // VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110), then the
 // first layer's LayerNorm: x_v (fp32) and v_op = LN_{g,b}(x_v).
-int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames, const float* g, const float* b) {
+int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames, const float* g, const float* b,
+                    bool x_only = false) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, N = w.N;
   const int Mv = B * N;
@@ -429,12 +463,31 @@ int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* 
   p.taps = 1;
   GemmEpilogue e;
   e.bias = h->bproj; e.pe = h->pe_v; e.pe_period = N;
-  if (gemm_resid_ln(h, s, "gemm.frame_proj", p, e, nullptr, w.x_v, g, b, w.v_op, Mv, w.y_v)) return 1;
+  if (x_only) {
+    e.out_f32 = w.x_v; e.ld_f32 = d;
+    CKL("gemm.frame_proj", launch_gemm(s, h->cfg.precision, p, e));
+  } else if (gemm_resid_ln(h, s, "gemm.frame_proj", p, e, nullptr, w.x_v, g, b, w.v_op, Mv, w.y_v)) {
+    return 1;
+  }
   return snapshot(h, s, "visual_embed", w.x_v, static_cast<size_t>(Mv) * d, false);
 }
 
 // CrossModalFusion (model.py:145-149,166-173).  In: x_a residual stream, a_op = LN_{layer0.norm1}(x_a),
 // v_op = visual rows (L_src per utterance).  Out: a_op = fusion.norm(x) in operand precision.
+// Fused variant (stack_fusable(T)): the visual rows are interpolated to the audio frame rate first, exactly where the
+// reference does it (model.py:114-116, before the K/V projection), the K|V rows of every fusion layer come from one GEMM
+// on those T rows (bf16), and the whole fusion stack runs in one kernel.  In: x_a (fp32 residual), x_v (fp32 visual
+// encoder output, L_src rows per utterance).  Out: a_op = fusion.norm(x) in bf16.
+int fusion_stack_fused(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
+  h->prof_stream = s;
+  const int d = h->cfg.d_model, B = w.B, T = w.T;
+  const int Ma = B * T, Lf = h->cfg.num_fusion_layers;
+  CKL("lerp_kv", launch_lerp_rows(s, w.x_v, d, B, L_src, T, d, w.attn_a, d));
+  if (linear(h, s, "gemm.cross_kv", w.attn_a, Ma, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, nullptr, w.kvb)) return 1;
+  if (run_stack(h, s, 2, w.x_a, h->debug ? w.x_a : nullptr, w.a_op, h->fng, h->fnb, w.kvb, Lf * 2 * d, B, T)) return 1;
+  return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
+}
+
 int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, H = h->cfg.nhead, B = w.B, T = w.T, prec = h->cfg.precision;
@@ -518,23 +571,36 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     CUDA_OK(cudaEventRecord(h->ev_fork, s));
     CUDA_OK(cudaStreamWaitEvent(sv, h->ev_fork, 0));
   }
+  const bool fa = stack_fusable(h, w.T), fv = stack_fusable(h, w.N);
+  const bool ff = fa && fv;            // the fused fusion stack reads the fp32 residual rows of both encoders
   // --- visual branch (enqueued first: its CNN is the longest kernel) ---
-  if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b)) return 1;
-  if (encoder_stack(h, sv, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr))
+  if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b, fv)) return 1;
+  if (fv) {
+    // out: x_v (fp32) for the interpolation in front of the K/V projection; v_op (bf16 cast) only for the unfused fusion
+    if (run_stack(h, sv, 1, w.x_v, w.x_v, ff ? nullptr : w.v_op, nullptr, nullptr, nullptr, 0, w.B, w.N)) return 1;
+  } else if (encoder_stack(h, sv, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) {
     return 1;
+  }
   if (snapshot(h, sv, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
   // --- audio branch ---
-  if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b)) return 1;
-  if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
-                    h->fus[0].n1b))
+  if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b, fa)) return 1;
+  if (fa) {
+    if (run_stack(h, s, 0, w.x_a, w.x_a, ff ? nullptr : w.a_op, h->fus[0].n1g, h->fus[0].n1b, nullptr, 0, w.B, w.T)) return 1;
+  } else if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
+                           h->fus[0].n1b)) {
     return 1;
+  }
   if (snapshot(h, s, "audio_enc", w.x_a, static_cast<size_t>(Ma) * d, false)) return 1;
   if (fork) {
     CUDA_OK(cudaEventRecord(h->ev_join, sv));
     CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
   }
   // --- fusion + decoder ---
-  if (fusion_stack(h, s, w, w.N)) return 1;
+  if (ff) {
+    if (fusion_stack_fused(h, s, w, w.N)) return 1;
+  } else if (fusion_stack(h, s, w, w.N)) {
+    return 1;
+  }
   return decoder_stage(h, s, w, mixed, separated, masks);
 }
 
@@ -884,6 +950,60 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     off["bdec0"] = ar.add_f32(b0->data.data(), 2 * d);
     off["bdec3"] = ar.add_f32(b3->data.data(), S * F);
   }
+  // --- fused transformer-stack kernel: weight streams in consumption order + per-layer vector blocks
+  const bool pack_stacks = xformer_stack_usable(h->cfg.precision, static_cast<int>(d), h->cfg.nhead, 1);
+  if (pack_stacks) {
+    const size_t vf = static_cast<size_t>(xformer_vec_floats());
+    for (int stack = 0; stack < 2; ++stack) {
+      const std::string pre = stack == 0 ? "audio_encoder" : "visual_encoder";
+      std::vector<uint8_t> stream(static_cast<size_t>(Le) * xformer_stream_bytes(false));
+      std::vector<float> vecs(static_cast<size_t>(Le) * vf);
+      for (int l = 0; l < Le; ++l) {
+        const std::string p = pre + ".transformer.layers." + std::to_string(l);
+        GETW(wqkv, p + ".self_attn.in_proj_weight", 3 * d, d);
+        GETW(bqkv, p + ".self_attn.in_proj_bias", 3 * d);
+        GETW(wo, p + ".self_attn.out_proj.weight", d, d);
+        GETW(bo, p + ".self_attn.out_proj.bias", d);
+        GETW(w1, p + ".linear1.weight", 4 * d, d);
+        GETW(b1, p + ".linear1.bias", 4 * d);
+        GETW(w2, p + ".linear2.weight", d, 4 * d);
+        GETW(b2, p + ".linear2.bias", d);
+        GETW(n1g, p + ".norm1.weight", d);
+        GETW(n1b, p + ".norm1.bias", d);
+        GETW(n2g, p + ".norm2.weight", d);
+        GETW(n2b, p + ".norm2.bias", d);
+        xformer_pack_self(wqkv->data.data(), wo->data.data(), w1->data.data(), w2->data.data(),
+                          stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(false));
+        xformer_pack_vecs(bqkv->data.data(), static_cast<int>(3 * d), bo->data.data(), b1->data.data(), b2->data.data(),
+                          n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data() + l * vf);
+      }
+      off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
+      off[stack == 0 ? "xv_a" : "xv_v"] = ar.add_f32(vecs.data(), vecs.size());
+    }
+    std::vector<uint8_t> stream(static_cast<size_t>(Lf) * xformer_stream_bytes(true));
+    std::vector<float> vecs(static_cast<size_t>(Lf) * vf);
+    for (int l = 0; l < Lf; ++l) {
+      const std::string p = "fusion.layers." + std::to_string(l);
+      GETW(win, p + ".cross_attn.in_proj_weight", 3 * d, d);
+      GETW(bin, p + ".cross_attn.in_proj_bias", 3 * d);
+      GETW(wo, p + ".cross_attn.out_proj.weight", d, d);
+      GETW(bo, p + ".cross_attn.out_proj.bias", d);
+      GETW(w1, p + ".ff.0.weight", 4 * d, d);
+      GETW(b1, p + ".ff.0.bias", 4 * d);
+      GETW(w2, p + ".ff.3.weight", d, 4 * d);
+      GETW(b2, p + ".ff.3.bias", d);
+      GETW(n1g, p + ".norm1.weight", d);
+      GETW(n1b, p + ".norm1.bias", d);
+      GETW(n2g, p + ".norm2.weight", d);
+      GETW(n2b, p + ".norm2.bias", d);
+      xformer_pack_cross(win->data.data(), wo->data.data(), w1->data.data(), w2->data.data(),
+                         stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(true));
+      xformer_pack_vecs(bin->data.data(), static_cast<int>(d), bo->data.data(), b1->data.data(), b2->data.data(),
+                        n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data() + l * vf);
+    }
+    off["xs_f"] = ar.add(stream.data(), stream.size());
+    off["xv_f"] = ar.add_f32(vecs.data(), vecs.size());
+  }
 #undef GETW
   // upload
   drop_graphs(h);
@@ -908,6 +1028,13 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->cnn.w3l = reinterpret_cast<const uint32_t*>(P("cw3l"));
   h->cnn_w2_slabs = static_cast<const uint8_t*>(P("tcw2"));
   h->cnn_w3_rows = static_cast<const uint8_t*>(P("tcw3"));
+  h->xs_a = h->xs_v = h->xs_f = nullptr;
+  h->xv_a = h->xv_v = h->xv_f = nullptr;
+  if (pack_stacks) {
+    h->xs_a = static_cast<const uint8_t*>(P("xs_a")); h->xs_v = static_cast<const uint8_t*>(P("xs_v"));
+    h->xs_f = static_cast<const uint8_t*>(P("xs_f"));
+    h->xv_a = PF("xv_a"); h->xv_v = PF("xv_v"); h->xv_f = PF("xv_f");
+  }
   h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();
   for (int stack = 0; stack < 2; ++stack)
     for (int l = 0; l < Le; ++l) {
@@ -1430,6 +1557,25 @@ int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, c
   return 0;
 }
 
+// One whole stack through the fused kernel (xformer_stack_sm100.cu) on the handle's weights.  which: 0 audio encoder,
+// 1 visual encoder, 2 fusion (kv = bf16 [B*L, num_fusion_layers*2*d] K|V rows).  x_in fp32 [B*L, d]; out_x fp32 and /
+// or out_op bf16 (final_ln != 0: the LayerNorm that follows the stack in the model -- fusion layer 0 norm1 after the
+// audio encoder, fusion.norm after the fusion stack; the visual encoder has none -- else a plain cast).
+int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, const void* kv, int32_t B, int32_t L,
+                             float* out_x, void* out_op, int32_t final_ln, void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "weights not finalized");
+  if (which < 0 || which > 2) return fail(h, "test_xformer_stack: which must be 0, 1 or 2");
+  if (h->xs_a == nullptr || !xformer_stack_usable(h->cfg.precision, h->cfg.d_model, h->cfg.nhead, L))
+    return fail(h, "test_xformer_stack: the fused stack kernel does not support this configuration");
+  const float *g = nullptr, *b = nullptr;
+  if (final_ln && which == 0) { g = h->fus[0].n1g; b = h->fus[0].n1b; }
+  if (final_ln && which == 2) { g = h->fng; b = h->fnb; }
+  h->prof_stream = static_cast<cudaStream_t>(cuda_stream);
+  return run_stack(h, static_cast<cudaStream_t>(cuda_stream), which, x_in, out_x, out_op, g, b, kv,
+                   h->cfg.num_fusion_layers * 2 * h->cfg.d_model, B, L);
+}
+
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (!h || !name) return 1;
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
@@ -1440,6 +1586,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "fuse_stack") == 0) { h->fuse_stack = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "attn_small") == 0) { attention_set_small(value != 0); drop_graphs(h); return 0; }

@@ -94,6 +94,31 @@ const char* launch_ffn_fused_cg2(cudaStream_t s, const void* a, const void* w1, 
                              const float* beta, void* out_op, int M, int num_sms,
                              unsigned long long* trace = nullptr);
 
+// A whole transformer stack in one persistent kernel (xformer_stack_sm100.cu): d_model = 256, 4 heads, bf16, sequences of
+// at most 128 rows.  The residual tile stays in tensor memory through every layer; weights stream as prepacked images.
+struct StackProblem {
+  const float* x_in;        // [B*L, 256] fp32 residual stream
+  float* out_x;             // [B*L, 256] fp32 residual after the stack (may alias x_in) or null
+  void* out_op;             // [B*L, 256] bf16: final LayerNorm (fin_gamma/fin_beta) or plain cast (fin_gamma == null), or null
+  const float *fin_gamma, *fin_beta;
+  const uint8_t* wstream;   // n_layers x xformer_stream_bytes(cross)
+  const float* vecs;        // n_layers x xformer_vec_floats()
+  int n_layers;
+  bool cross;               // false: self-attention encoder layers (ReLU); true: cross-attention fusion layers (GELU)
+  const void* kv;           // cross: bf16 [B*L, kv_ld] rows, layer l's K at columns [l*512, +256), V at [l*512+256, +256)
+  int kv_ld;
+  int B, L;
+  int act;
+};
+bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
+size_t xformer_stream_bytes(bool cross);
+int xformer_vec_floats();
+void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, uint8_t* dst);
+void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, uint8_t* dst);
+void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const float* b1, const float* b2, const float* n1g,
+                       const float* n1b, const float* n2g, const float* n2b, float* dst);
+const char* launch_xformer_stack(cudaStream_t s, const StackProblem& p, int num_sms);
+
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).
 // out_op is bf16 (PREC_BF16) or fp32 (PREC_TF32).
 const char* launch_add_layernorm(cudaStream_t s, int prec, const float* x, const float* y, const float* gamma,

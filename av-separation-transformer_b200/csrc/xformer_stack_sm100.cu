@@ -1,0 +1,837 @@
+// A whole transformer stack in one persistent kernel (d_model = 256, 4 heads of 64, hidden 1024, bf16 operands):
+//
+//   self  : nn.TransformerEncoderLayer x L (pre-norm, ReLU FFN)        model.py:48-52,59,97-101,111;
+//                                                                       torch/nn/modules/transformer.py:946-950
+//   cross : CrossAttentionLayer x L (audio queries, visual keys/values, erf-GELU FFN)   model.py:152-173
+//
+// One CTA owns a tile of whole utterances (U = floor(128 / len) of them: two 63-frame audio clips or two 50-frame
+// lip sequences = up to 128 rows) through EVERY layer of the stack.  The fp32 residual stream of the tile lives in
+// tensor memory (256 of the 512 columns) for the whole kernel: out_proj and linear2 accumulate straight onto it
+// (D += A B with D = the residual), so no residual ever goes through shared memory, L2 or HBM between sub-layers.
+// The only traffic in the steady state is the weight stream: 1.5 MB per layer, prepacked as 32 KB shared-memory
+// images in consumption order and pulled by 1-D bulk copies (tools/tma_rate.cu: 88 B/clk/SM with 32 KB copies against
+// 41 B/clk/SM for the 16 KB tensor boxes the stand-alone GEMM kernels use).
+//
+// Roles (18 warps): warp 0 lane 0 streams weights (3-slot ring) and the x / K / V tiles; warp 1 lane 0 issues every
+// tcgen05.mma; warps 2..17 are "row" warps: thread = (tile row r = TMEM lane, column part p of 4).
+//
+// Tensor memory map (columns): X [0,256) residual | W [256,512) work area:
+//   attention, per head h:  W[0,128)  Q_h|K_h accumulator -> S = Q K^T -> P (bf16 pairs, first 64 columns)
+//                           W[128,192) V_h accumulator -> O_h = P V accumulator
+//                           W[192,224) Q_h as a bf16 A operand | W[224,256) O_h / rowsum as a bf16 A operand
+//   FFN, per 128-wide hidden chunk j: W[(j&1)*128, +128) accumulator of linear1 -> H_j (bf16 pairs, first 64 columns),
+//                           which linear2 reads as its A operand while accumulating onto X.
+// Per head:  QKV_h = LN1(x) Wqkv_h^T (+bias) ; S = (Q scale) K^T ; block-diagonal softmax (an utterance attends only to
+// itself) ; O = P V / rowsum ; X += O Wo[:, h]^T.  The bias of out_proj / linear2 is added when the next LayerNorm
+// pass reads X (and written back), so X is always the true residual.
+//
+// Measured limits that shape the schedule (tools/tmem_rate.cu, tools/mma_rate.cu): tcgen05.ld drains tensor memory at
+// ~57 B/clk/SM whatever the number of warps, tcgen05.st fills it at > 500 B/clk; M128 N128 K16 = 64 clk.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+#include <vector>
+
+namespace avsep {
+
+namespace {
+
+constexpr int D = 256, HID = 1024, NH = 4, HDIM = 64, NCHUNK = 8;
+constexpr int SLAB = 16384;                       // 128 rows x 128 B
+constexpr int ITEM = 32768;                       // one weight item of the stream
+constexpr int NSLOT = 3;
+constexpr int OFF_A = 0;                          // LayerNorm output (A operand, 4 k-slabs); x / output staging slabs 0..3
+constexpr int OFF_RING = OFF_A + 4 * SLAB;        // weight ring; its first 64 KB double as staging slabs 4..7
+constexpr int OFF_KT = OFF_RING + NSLOT * ITEM;   // K_h tile [keys x 64] K-major
+constexpr int OFF_VT = OFF_KT + SLAB;             // V_h tile [keys x 64] (MN-major B operand of P V)
+constexpr int OFF_RED = OFF_VT + SLAB;            // 2 x [128 rows][4 parts] float2
+constexpr int VEC_BQKV = 0, VEC_BO = 768, VEC_B1 = 1024, VEC_B2 = 2048, VEC_N1G = 2304, VEC_N1B = 2560,
+              VEC_N2G = 2816, VEC_N2B = 3072, VEC_FLOATS = 3328;
+constexpr int OFF_VEC = OFF_RED + 2 * 4096;
+constexpr int OFF_PEND = OFF_VEC + VEC_FLOATS * 4;   // [256] bias carried into the next LayerNorm | final gamma | beta
+constexpr int OFF_BAR = OFF_PEND + 3 * 1024;
+constexpr int STACK_SMEM = OFF_BAR + 512;
+static_assert(STACK_SMEM <= 227 * 1024, "xformer_stack: shared memory budget exceeded");
+constexpr int STACK_THREADS = 32 * 18;
+constexpr int ITEMS_SELF = 48, ITEMS_CROSS = 40;
+
+constexpr uint32_t TM_X = 0, TM_W = 256;          // tensor-memory column bases
+constexpr uint32_t TW_S = 0, TW_V = 128, TW_QOP = 192, TW_OOP = 224;
+
+struct StackDev {
+  const uint8_t* wstream;       // n_layers x items x 32 KB, consumption order (see xformer_pack_*)
+  const float* vecs;            // n_layers x VEC_FLOATS
+  const float *fin_gamma, *fin_beta;
+  int n_layers, items_per_layer, cross;
+  int L, rows, M, n_tiles;      // rows per utterance, rows per tile (U * L), total rows
+  int act;
+  int out_x, out_op;
+  int kv_ld_layer;              // cross: column offset between layers in the K|V matrix (2 * D)
+  float qscale;
+};
+
+__device__ __forceinline__ uint32_t soff(int row, int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); }
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(STACK_THREADS, 1)
+xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_constant__ CUtensorMap tmXout,
+                     const __grid_constant__ CUtensorMap tmOp, const __grid_constant__ CUtensorMap tmKV,
+                     const StackDev p) {
+  extern __shared__ __align__(1024) uint8_t smem_stack[];
+  uint8_t* const smem = smem_stack;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;                 // [3]
+  uint64_t* w_empty = bars + 3;            // [3]
+  uint64_t* x_full = bars + 6;             // x tile staged
+  uint64_t* x_taken = bars + 7;            // (16) staging copied into tensor memory
+  uint64_t* stage_free = bars + 8;         // (4) output stores have read the staging slabs
+  uint64_t* a_ready = bars + 9;            // (16) LayerNorm output in smem, X updated
+  uint64_t* qkv_full = bars + 10;
+  uint64_t* qk_ready = bars + 11;          // (16)
+  uint64_t* s_full = bars + 12;
+  uint64_t* p_ready = bars + 13;           // (16)
+  uint64_t* o_full = bars + 14;
+  uint64_t* o_ready = bars + 15;           // (16)
+  uint64_t* kv_full = bars + 16;           // cross: K_h / V_h tiles landed
+  uint64_t* kv_empty = bars + 17;          // cross: P V of the head complete
+  uint64_t* attn_done = bars + 18;
+  uint64_t* acc1_full = bars + 19;         // [2]
+  uint64_t* h_full = bars + 21;            // [2] (16)
+  uint64_t* ffn_done = bars + 23;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
+  float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
+  float* pend = reinterpret_cast<float*>(smem + OFF_PEND);
+  float* fin_g = pend + 256;
+  float* fin_b = pend + 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmXin);
+    if (p.out_x) tma_prefetch_desc(&tmXout);
+    if (p.out_op) tma_prefetch_desc(&tmOp);
+    if (p.cross) tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(x_full, 1);
+    mbar_init(x_taken, 16);
+    mbar_init(stage_free, 4);
+    mbar_init(a_ready, 16);
+    mbar_init(qkv_full, 1);
+    mbar_init(qk_ready, 16);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 16);
+    mbar_init(o_full, 1);
+    mbar_init(o_ready, 16);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(attn_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&h_full[i], 16); }
+    mbar_init(ffn_done, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < D; i += STACK_THREADS) {
+    fin_g[i] = p.fin_gamma ? __ldg(p.fin_gamma + i) : 1.f;
+    fin_b[i] = p.fin_beta ? __ldg(p.fin_beta + i) : 0.f;
+  }
+  // K / V tiles: rows past the tile's utterances are never written by the TMA loads of the cross-attention path; they
+  // must be finite (P is 0 there, and 0 x NaN would poison real rows)
+  for (int i = threadIdx.x; i < 2 * SLAB / 16; i += STACK_THREADS)
+    *reinterpret_cast<uint4*>(smem + OFF_KT + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmX = tmem_base + TM_X, tmW = tmem_base + TM_W;
+  griddep_launch_dependents();
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: x tile, weight stream, (cross) K / V tiles ----------------
+      uint32_t wn = 0;          // weight items issued
+      uint32_t hn = 0;          // heads whose K/V tiles were issued (cross)
+      auto load_item = [&](const uint8_t* src) {
+        const uint32_t slot = wn % NSLOT, use = wn / NSLOT;
+        mbar_wait(&w_empty[slot], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&w_full[slot], ITEM);
+        bulk_load_1d(smem + OFF_RING + slot * ITEM, src, ITEM, &w_full[slot]);
+        ++wn;
+      };
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        const int row0 = tile * p.rows;
+        if (lt > 0) mbar_wait(stage_free, (lt - 1) & 1);
+        mbar_arrive_expect_tx(x_full, 8u * static_cast<uint32_t>(p.rows) * 128u);
+        for (int s = 0; s < 8; ++s) tma_load_2d(smem + OFF_A + s * SLAB, &tmXin, x_full, s * 32, row0);
+        mbar_wait(x_taken, lt & 1);            // staging (a_op + first two ring slots) is free again
+        for (int l = 0; l < p.n_layers; ++l) {
+          const uint8_t* src = p.wstream + static_cast<size_t>(l) * p.items_per_layer * ITEM;
+          if (!p.cross) {
+            for (int i = 0; i < 16; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
+            src += 16 * ITEM;
+          } else {
+            for (int h = 0; h < NH; ++h, ++hn) {
+              load_item(src + static_cast<size_t>(2 * h) * ITEM);                  // Wq_h
+              if (hn > 0) mbar_wait(kv_empty, (hn - 1) & 1);
+              mbar_arrive_expect_tx(kv_full, 2u * static_cast<uint32_t>(p.rows) * 128u);
+              tma_load_2d(smem + OFF_KT, &tmKV, kv_full, l * p.kv_ld_layer + h * HDIM, row0);
+              tma_load_2d(smem + OFF_VT, &tmKV, kv_full, l * p.kv_ld_layer + D + h * HDIM, row0);
+              load_item(src + static_cast<size_t>(2 * h + 1) * ITEM);              // Wo_h
+            }
+            src += 8 * ITEM;
+          }
+          for (int i = 0; i < 32; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t ID128 = umma_idesc(1u, 128, 128);
+      constexpr uint32_t ID64 = umma_idesc(1u, 128, 64);
+      constexpr uint32_t ID64_MN = umma_idesc(1u, 128, 64, 0, 1);      // B (= V) MN-major
+      uint32_t wn = 0, n_a = 0, n_h = 0, c1n = 0, c2n = 0;
+      uint32_t cur_slot = 0;
+      auto next_item = [&]() -> uint32_t {
+        cur_slot = wn % NSLOT;
+        mbar_wait(&w_full[cur_slot], (wn / NSLOT) & 1);
+        tc_fence_after();
+        ++wn;
+        return smem_u32(smem + OFF_RING + cur_slot * ITEM);
+      };
+      const uint32_t a_base = smem_u32(smem + OFF_A);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < p.n_layers; ++l) {
+          // ======== attention sub-layer ========
+          mbar_wait(a_ready, n_a & 1); ++n_a;
+          tc_fence_after();
+          for (int h = 0; h < NH; ++h, ++n_h) {
+            if (!p.cross) {
+              // Q_h | K_h : N = 128 into W[0,128)
+              for (int it = 0; it < 2; ++it) {
+                const uint32_t base = next_item();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int ks = 2 * it + half;
+                  const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&w_empty[cur_slot]);
+              }
+              // V_h : N = 64 into W[128,192)
+              {
+                const uint32_t base = next_item();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_f16(tmW + TW_V, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&w_empty[cur_slot]);
+              }
+            } else {
+              // Q_h : N = 64 into W[0,64)
+              const uint32_t base = next_item();
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[cur_slot]);
+            }
+            umma_commit(qkv_full);
+            // S = Q K^T : A = Q_h from tensor memory, B = K tile
+            mbar_wait(qk_ready, n_h & 1);
+            if (p.cross) mbar_wait(kv_full, n_h & 1);
+            tc_fence_after();
+            {
+              const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_KT), 1024);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_ts(tmW + TW_S, tmW + TW_QOP + kk * 8, kdesc + 2 * kk, ID128, kk != 0 ? 1u : 0u);
+            }
+            umma_commit(s_full);
+            // O = P V : A = P from tensor memory (K = 128 keys), B = V tile (MN-major)
+            mbar_wait(p_ready, n_h & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(smem + OFF_VT + ks * 2048), 1024, 1024);
+              umma_f16_ts(tmW + TW_V, tmW + TW_S + ks * 8, vdesc, ID64_MN, ks != 0 ? 1u : 0u);
+            }
+            umma_commit(o_full);
+            if (p.cross) umma_commit(kv_empty);
+            // X += O_h Wo[:, h*64 : (h+1)*64]^T : A = O_h from tensor memory, two 128-row halves of Wo
+            mbar_wait(o_ready, n_h & 1);
+            tc_fence_after();
+            {
+              const uint32_t base = next_item();
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint64_t bdesc = umma_desc_kmajor_sw128(base + hf * SLAB, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16_ts(tmX + hf * 128, tmW + TW_OOP + kk * 8, bdesc + 2 * kk, ID128, 1u);
+              }
+              umma_commit(&w_empty[cur_slot]);
+            }
+          }
+          umma_commit(attn_done);
+          // ======== feed-forward sub-layer ========
+          mbar_wait(a_ready, n_a & 1); ++n_a;
+          tc_fence_after();
+          for (int j = 0; j <= NCHUNK; ++j) {
+            if (j < NCHUNK) {
+              const uint32_t st = c1n & 1;
+              for (int it = 0; it < 2; ++it) {
+                const uint32_t base = next_item();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int ks = 2 * it + half;
+                  const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_f16(tmW + st * 128, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&w_empty[cur_slot]);
+              }
+              umma_commit(&acc1_full[st]);
+              ++c1n;
+            }
+            if (j >= 1) {
+              const uint32_t st2 = c2n & 1;
+              mbar_wait(&h_full[st2], (c2n >> 1) & 1);
+              tc_fence_after();
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t base = next_item();
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + hf * SLAB, 1024);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    umma_f16_ts(tmX + hf * 128, tmW + st2 * 128 + (ks * 4 + kk) * 8, bdesc + 2 * kk, ID128, 1u);
+                }
+                umma_commit(&w_empty[cur_slot]);
+              }
+              ++c2n;
+            }
+          }
+          umma_commit(ffn_done);
+        }
+      }
+    }
+  } else {
+    // ---------------- row warps: lane quarter q = warp % 4 (TMEM lanes 32q..32q+31), column part = (warp - 2) / 4 ----
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int etid = threadIdx.x - 64;                       // 0..511
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const bool elected = (warp == 2 + 4 * part) && (lane == 0);
+    // block-diagonal attention: row r attends keys [klo, khi) of its own utterance (padding rows attend each other)
+    const int klo = (r / p.L) * p.L;
+    const int khi = min(128, klo + p.L);
+    uint32_t nx = 0;                                         // exchanges through `red` so far (double buffered)
+    uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0;
+
+    auto exchange = [&](float2 mine, float2 (&all)[4]) {
+      float2* buf = red + (nx & 1) * 512 + r * 4;
+      ++nx;
+      buf[part] = mine;
+      named_bar_sync(1 + q, 128);
+      all[0] = buf[0]; all[1] = buf[1]; all[2] = buf[2]; all[3] = buf[3];
+    };
+    // vu[0..63] = X[r, 64 part .. +64) (+ bias, written back so that X stays the true residual); returns sum, sum of squares
+    auto read_x = [&](uint32_t (&vu)[64], const float* bias, bool write_back, float& sum, float& sq) {
+      tmem_ld_32x32b_x32(tmX + lane_sel + part * 64, reinterpret_cast<uint32_t(&)[32]>(vu[0]));
+      tmem_ld_32x32b_x32(tmX + lane_sel + part * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(vu[32]));
+      tmem_ld_wait();
+      if (bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + part * 64 + i);
+          vu[i] = __float_as_uint(__uint_as_float(vu[i]) + b4.x);
+          vu[i + 1] = __float_as_uint(__uint_as_float(vu[i + 1]) + b4.y);
+          vu[i + 2] = __float_as_uint(__uint_as_float(vu[i + 2]) + b4.z);
+          vu[i + 3] = __float_as_uint(__uint_as_float(vu[i + 3]) + b4.w);
+        }
+        if (write_back) {
+          tmem_st_32x32b_x32(tmX + lane_sel + part * 64, reinterpret_cast<const uint32_t(&)[32]>(vu[0]));
+          tmem_st_32x32b_x32(tmX + lane_sel + part * 64 + 32, reinterpret_cast<const uint32_t(&)[32]>(vu[32]));
+        }
+      }
+      sum = 0.f; sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float x = __uint_as_float(vu[i]);
+        sum += x;
+        sq = fmaf(x, x, sq);
+      }
+    };
+    // LayerNorm statistics of the full row from the part's (sum, sum of squares): merged over the 4 column parts
+    auto row_stats = [&](float sum, float sq, float& mean, float& rstd) {
+      const float mean_p = sum * (1.0f / 64.0f);
+      float2 all[4];
+      exchange(make_float2(mean_p, fmaxf(sq - sum * mean_p, 0.f)), all);
+      mean = 0.25f * ((all[0].x + all[1].x) + (all[2].x + all[3].x));
+      const float d0 = all[0].x - mean, d1 = all[1].x - mean, d2 = all[2].x - mean, d3 = all[3].x - mean;
+      const float m2 = (all[0].y + all[1].y) + (all[2].y + all[3].y) + 64.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+      rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+    };
+    // (v - mean) * rstd * g + b as bf16 -> k-slab `part` of the 128-row x 256-column operand image at `base`
+    // (128B-swizzled, K-major); eight columns at a time so that the row slice dies as it is stored
+    auto store_op_row = [&](const uint32_t (&vu)[64], float mean, float rstd, const float* g, const float* b,
+                            uint8_t* base) {
+      uint8_t* slab = base + part * SLAB;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(g + part * 64 + c * 8 + i);
+          const float4 b4 = *reinterpret_cast<const float4*>(b + part * 64 + c * 8 + i);
+          y[i] = fmaf((__uint_as_float(vu[c * 8 + i]) - mean) * rstd, g4.x, b4.x);
+          y[i + 1] = fmaf((__uint_as_float(vu[c * 8 + i + 1]) - mean) * rstd, g4.y, b4.y);
+          y[i + 2] = fmaf((__uint_as_float(vu[c * 8 + i + 2]) - mean) * rstd, g4.z, b4.z);
+          y[i + 3] = fmaf((__uint_as_float(vu[c * 8 + i + 3]) - mean) * rstd, g4.w, b4.w);
+        }
+        uint4 w;
+        w.x = pack_bf16x2(y[0], y[1]); w.y = pack_bf16x2(y[2], y[3]);
+        w.z = pack_bf16x2(y[4], y[5]); w.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(slab + soff(r, c)) = w;
+      }
+    };
+    auto ln_to_a = [&](const float* bias, const float* g, const float* b) {
+      uint32_t vu[64];
+      float sum, sq, mean, rstd;
+      read_x(vu, bias, true, sum, sq);
+      row_stats(sum, sq, mean, rstd);
+      store_op_row(vu, mean, rstd, g, b, smem + OFF_A);
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    };
+
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+      const int row0 = tile * p.rows;
+      // ---- residual tile: staging slabs (fp32, 32 columns each) -> tensor memory ----
+      mbar_wait(x_full, lt & 1);
+      {
+        uint32_t u[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint8_t* slab = smem + OFF_A + (part * 2 + c) * SLAB;
+          if (r < p.rows) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 w = *reinterpret_cast<const uint4*>(slab + soff(r, i));
+              u[4 * i] = w.x; u[4 * i + 1] = w.y; u[4 * i + 2] = w.z; u[4 * i + 3] = w.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = 0u;
+          }
+          tmem_st_32x32b_x32(tmX + lane_sel + part * 64 + c * 32, u);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_taken);
+      }
+      for (int l = 0; l < p.n_layers; ++l) {
+        // ---- per-layer vectors; the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
+        named_bar_sync(5, 512);
+        if (l > 0 && etid < D) pend[etid] = vec[VEC_B2 + etid];
+        named_bar_sync(5, 512);
+        {
+          const float* src = p.vecs + static_cast<size_t>(l) * VEC_FLOATS;
+          for (int i = etid; i < VEC_FLOATS; i += 512) vec[i] = __ldg(src + i);
+        }
+        named_bar_sync(5, 512);
+        tc_fence_after();
+        ln_to_a(l > 0 ? pend : nullptr, vec + VEC_N1G, vec + VEC_N1B);
+
+        // ======== attention ========
+        for (int h = 0; h < NH; ++h, ++n_h) {
+          // ---- Q (scaled, bf16, back into tensor memory as an A operand); K, V (bf16) into their shared-memory tiles
+          mbar_wait(qkv_full, n_h & 1);
+          tc_fence_after();
+          {
+            uint32_t a[16];
+            tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + part * 16, a);
+            tmem_ld_wait();
+            uint32_t qp[8];
+            const float* bq = vec + VEC_BQKV + h * HDIM + part * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              qp[i] = pack_bf16x2((__uint_as_float(a[2 * i]) + bq[2 * i]) * p.qscale,
+                                  (__uint_as_float(a[2 * i + 1]) + bq[2 * i + 1]) * p.qscale);
+            tmem_st_32x32b_x8(tmW + lane_sel + TW_QOP + part * 8, qp);
+            if (!p.cross) {
+              uint32_t kk[16], vv[16];
+              tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + 64 + part * 16, kk);
+              tmem_ld_32x32b_x16(tmW + lane_sel + TW_V + part * 16, vv);
+              tmem_ld_wait();
+              const float* bk = vec + VEC_BQKV + D + h * HDIM + part * 16;
+              const float* bv = vec + VEC_BQKV + 2 * D + h * HDIM + part * 16;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(kk[8 * c]) + bk[8 * c], __uint_as_float(kk[8 * c + 1]) + bk[8 * c + 1]);
+                w.y = pack_bf16x2(__uint_as_float(kk[8 * c + 2]) + bk[8 * c + 2], __uint_as_float(kk[8 * c + 3]) + bk[8 * c + 3]);
+                w.z = pack_bf16x2(__uint_as_float(kk[8 * c + 4]) + bk[8 * c + 4], __uint_as_float(kk[8 * c + 5]) + bk[8 * c + 5]);
+                w.w = pack_bf16x2(__uint_as_float(kk[8 * c + 6]) + bk[8 * c + 6], __uint_as_float(kk[8 * c + 7]) + bk[8 * c + 7]);
+                *reinterpret_cast<uint4*>(smem + OFF_KT + soff(r, part * 2 + c)) = w;
+                w.x = pack_bf16x2(__uint_as_float(vv[8 * c]) + bv[8 * c], __uint_as_float(vv[8 * c + 1]) + bv[8 * c + 1]);
+                w.y = pack_bf16x2(__uint_as_float(vv[8 * c + 2]) + bv[8 * c + 2], __uint_as_float(vv[8 * c + 3]) + bv[8 * c + 3]);
+                w.z = pack_bf16x2(__uint_as_float(vv[8 * c + 4]) + bv[8 * c + 4], __uint_as_float(vv[8 * c + 5]) + bv[8 * c + 5]);
+                w.w = pack_bf16x2(__uint_as_float(vv[8 * c + 6]) + bv[8 * c + 6], __uint_as_float(vv[8 * c + 7]) + bv[8 * c + 7]);
+                *reinterpret_cast<uint4*>(smem + OFF_VT + soff(r, part * 2 + c)) = w;
+              }
+              fence_proxy_async_smem();
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qk_ready);
+          }
+          // ---- softmax over the row's own utterance; P (bf16 pairs) over the first 64 columns of S ----
+          float inv_l;
+          mbar_wait(s_full, n_h & 1);
+          tc_fence_after();
+          {
+            const int c0 = part * 32;
+            const int lo_i = klo - c0, hi_i = khi - c0;      // this row's valid columns of the part: [lo_i, hi_i)
+            const bool any = __any_sync(0xffffffffu, (lo_i < 32) && (hi_i > 0));
+            uint32_t s[32];
+            float mx = -INFINITY;
+            if (any) {
+              tmem_ld_32x32b_x32(tmW + lane_sel + TW_S + c0, s);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {                 // masked scores become -inf: exp2 gives exactly 0 below
+                const float x = (i >= lo_i && i < hi_i) ? __uint_as_float(s[i]) : -INFINITY;
+                s[i] = __float_as_uint(x);
+                mx = fmaxf(mx, x);
+              }
+            }
+            float2 all[4];
+            exchange(make_float2(mx, 0.f), all);
+            const float m = fmaxf(fmaxf(all[0].x, all[1].x), fmaxf(all[2].x, all[3].x));   // finite: klo <= r < khi
+            float sum = 0.f;
+            uint32_t pp[16];
+            if (any) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float e0 = ex2_approx(__uint_as_float(s[2 * i]) - m);
+                const float e1 = ex2_approx(__uint_as_float(s[2 * i + 1]) - m);
+                sum += e0 + e1;
+                pp[i] = pack_bf16x2(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pp[i] = 0u;
+            }
+            exchange(make_float2(sum, 0.f), all);            // every part has read its S columns before this barrier
+            inv_l = 1.0f / ((all[0].x + all[1].x) + (all[2].x + all[3].x));
+            tmem_st_32x32b_x16(tmW + lane_sel + TW_S + part * 16, pp);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+          }
+          // ---- O_h / rowsum -> bf16 A operand of the out_proj slice ----
+          mbar_wait(o_full, n_h & 1);
+          tc_fence_after();
+          {
+            uint32_t o[16], op[8];
+            tmem_ld_32x32b_x16(tmW + lane_sel + TW_V + part * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              op[i] = pack_bf16x2(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+            tmem_st_32x32b_x8(tmW + lane_sel + TW_OOP + part * 8, op);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_ready);
+          }
+        }
+        // ======== x += out_proj bias; LayerNorm 2 ========
+        mbar_wait(attn_done, n_attn & 1); ++n_attn;
+        tc_fence_after();
+        ln_to_a(vec + VEC_BO, vec + VEC_N2G, vec + VEC_N2B);
+
+        // ======== feed-forward: bias + activation on each 128-wide hidden chunk, back into tensor memory as bf16 ====
+        for (int j = 0; j < NCHUNK; ++j, ++c1n) {
+          const uint32_t st = c1n & 1;
+          mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
+          tc_fence_after();
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
+          tmem_ld_wait();
+          float hv[32];
+          const float* bj = vec + VEC_B1 + j * 128 + part * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bj + i);
+            hv[i] = __uint_as_float(v[i]) + b4.x; hv[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+            hv[i + 2] = __uint_as_float(v[i + 2]) + b4.z; hv[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+          }
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = fmaxf(hv[i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = gelu_bf16_grade(hv[i]);
+          }
+          uint32_t hp[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) hp[i] = pack_bf16x2(hv[2 * i], hv[2 * i + 1]);
+          tc_fence_before();
+          named_bar_sync(1 + q, 128);          // the bf16 pairs alias fp32 columns the other parts of this quarter read
+          tc_fence_after();
+          tmem_st_32x32b_x16(tmW + lane_sel + st * 128 + part * 16, hp);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_full[st]);
+        }
+        mbar_wait(ffn_done, n_ffn & 1); ++n_ffn;
+        tc_fence_after();
+      }
+      // ---- stack output: x + last linear2 bias -> fp32 residual rows and / or (final LayerNorm | cast) bf16 rows ----
+      {
+        uint32_t vu[64];
+        float sum, sq, mean = 0.f, rstd = 1.f;
+        read_x(vu, vec + VEC_B2, false, sum, sq);
+        tc_fence_before();
+        if (p.out_x) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint8_t* slab = smem + OFF_A + (part * 2 + c) * SLAB;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint4*>(slab + soff(r, i)) =
+                  make_uint4(vu[c * 32 + 4 * i], vu[c * 32 + 4 * i + 1], vu[c * 32 + 4 * i + 2], vu[c * 32 + 4 * i + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(6 + part, 128);
+          if (elected) {
+            tma_store_2d(&tmXout, smem + OFF_A + (part * 2) * SLAB, part * 64, row0);
+            tma_store_2d(&tmXout, smem + OFF_A + (part * 2 + 1) * SLAB, part * 64 + 32, row0);
+            bulk_commit();
+          }
+        }
+        if (p.out_op) {
+          if (p.fin_gamma != nullptr) row_stats(sum, sq, mean, rstd);
+          if (p.out_x) {                        // the bf16 image reuses staging slabs 0..3: wait for every part's x stores
+            if (elected) bulk_wait_read0();
+            named_bar_sync(5, 512);
+          }
+          store_op_row(vu, mean, rstd, fin_g, fin_b, smem + OFF_A);      // cast only: mean 0, rstd 1, gamma 1, beta 0
+          fence_proxy_async_smem();
+          named_bar_sync(6 + part, 128);
+          if (elected) {
+            tma_store_2d(&tmOp, smem + OFF_A + part * SLAB, part * 64, row0);
+            bulk_commit();
+          }
+        }
+        if (elected) {
+          bulk_wait_read0();
+          mbar_arrive(stage_free);
+        }
+      }
+    }
+    if (elected) bulk_wait_read0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
+
+const char* enc2d(CUtensorMap* map, CUtensorMapDataType dt, int esz, const void* ptr, uint64_t inner, uint64_t outer,
+                  uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return "xformer_stack: pointer not 16-byte aligned";
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * esz};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  if (g_enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+      CUDA_SUCCESS)
+    return "xformer_stack: cuTensorMapEncodeTiled failed";
+  return nullptr;
+}
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// [nrows x 64] bf16 tile of W (row-major, leading dimension ld) starting at (row0, col0), written as the 128B-swizzled
+// K-major shared-memory image the UMMA descriptors expect (row r at r * 128 B, 16-byte chunk c at (c ^ (r & 7))).
+void put_tile(uint8_t* dst, const float* W, int ld, int row0, int nrows, int col0) {
+  for (int r = 0; r < nrows; ++r)
+    for (int k = 0; k < 64; ++k) {
+      const uint16_t b = f2bf(W[static_cast<size_t>(row0 + r) * ld + col0 + k]);
+      memcpy(dst + r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2, &b, 2);
+    }
+}
+
+void pack_ffn_items(uint8_t* dst, const float* w1, const float* w2) {
+  // issue order of the MMA thread: G1_0, G1_1, G2_0, G1_2, G2_1, ..., G1_7, G2_6, G2_7
+  auto g1 = [&](int j) {
+    for (int it = 0; it < 2; ++it, dst += ITEM)
+      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, w1, D, j * 128, 128, (2 * it + half) * 64);
+  };
+  auto g2 = [&](int j) {
+    for (int ks = 0; ks < 2; ++ks, dst += ITEM)
+      for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, w2, HID, hf * 128, 128, j * 128 + ks * 64);
+  };
+  for (int j = 0; j <= NCHUNK; ++j) {
+    if (j < NCHUNK) g1(j);
+    if (j >= 1) g2(j - 1);
+  }
+}
+
+}  // namespace
+
+size_t xformer_stream_bytes(bool cross) { return static_cast<size_t>(cross ? ITEMS_CROSS : ITEMS_SELF) * ITEM; }
+int xformer_vec_floats() { return VEC_FLOATS; }
+
+// in_proj_weight [768, 256] (q | k | v rows), out_proj [256, 256], linear1 [1024, 256], linear2 [256, 1024]
+void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, uint8_t* dst) {
+  memset(dst, 0, xformer_stream_bytes(false));
+  for (int h = 0; h < NH; ++h) {
+    for (int it = 0; it < 2; ++it, dst += ITEM)
+      for (int half = 0; half < 2; ++half) {
+        const int col0 = (2 * it + half) * 64;
+        put_tile(dst + half * SLAB, wqkv, D, h * HDIM, 64, col0);                    // Q_h rows
+        put_tile(dst + half * SLAB + 64 * 128, wqkv, D, D + h * HDIM, 64, col0);     // K_h rows
+      }
+    for (int ks = 0; ks < 4; ++ks) put_tile(dst + ks * 8192, wqkv, D, 2 * D + h * HDIM, 64, ks * 64);   // V_h
+    dst += ITEM;
+    for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, wo, D, hf * 128, 128, h * HDIM);
+    dst += ITEM;
+  }
+  pack_ffn_items(dst, w1, w2);
+}
+
+// wq = rows [0, 256) of the packed in_proj_weight of nn.MultiheadAttention (model.py:155; functional.py:5847-5865)
+void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, uint8_t* dst) {
+  memset(dst, 0, xformer_stream_bytes(true));
+  for (int h = 0; h < NH; ++h) {
+    for (int ks = 0; ks < 4; ++ks) put_tile(dst + ks * 8192, wq, D, h * HDIM, 64, ks * 64);
+    dst += ITEM;
+    for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, wo, D, hf * 128, 128, h * HDIM);
+    dst += ITEM;
+  }
+  pack_ffn_items(dst, w1, w2);
+}
+
+void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const float* b1, const float* b2, const float* n1g,
+                       const float* n1b, const float* n2g, const float* n2b, float* dst) {
+  memset(dst, 0, sizeof(float) * VEC_FLOATS);
+  memcpy(dst + VEC_BQKV, bqkv, sizeof(float) * n_bqkv);
+  memcpy(dst + VEC_BO, bo, sizeof(float) * D);
+  memcpy(dst + VEC_B1, b1, sizeof(float) * HID);
+  memcpy(dst + VEC_B2, b2, sizeof(float) * D);
+  memcpy(dst + VEC_N1G, n1g, sizeof(float) * D);
+  memcpy(dst + VEC_N1B, n1b, sizeof(float) * D);
+  memcpy(dst + VEC_N2G, n2g, sizeof(float) * D);
+  memcpy(dst + VEC_N2B, n2b, sizeof(float) * D);
+}
+
+bool xformer_stack_usable(int prec, int d_model, int nhead, int len) {
+  return prec == PREC_BF16 && d_model == D && nhead == NH && len >= 1 && len <= 128;
+}
+
+const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num_sms) {
+  if (sp.B <= 0 || sp.L <= 0 || sp.L > 128 || sp.n_layers <= 0) return "xformer_stack: bad problem";
+  if (!sp.out_x && !sp.out_op) return "xformer_stack: no output requested";
+  if (g_enc == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || fn == nullptr)
+      return "xformer_stack: cuTensorMapEncodeTiled entry point not found";
+    if (cudaFuncSetAttribute(xformer_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STACK_SMEM) != cudaSuccess)
+      return "xformer_stack: cudaFuncSetAttribute failed";
+    g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const int U = 128 / sp.L, rows = U * sp.L;
+  const int M = sp.B * sp.L;
+  const int n_tiles = (sp.B + U - 1) / U;
+  CUtensorMap tin, tout, top, tkv;
+  if (const char* e = enc2d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.x_in, D, M, D, 32, rows)) return e;
+  tout = tin; top = tin; tkv = tin;
+  if (sp.out_x)
+    if (const char* e = enc2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.out_x, D, M, D, 32, rows)) return e;
+  if (sp.out_op)
+    if (const char* e = enc2d(&top, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.out_op, D, M, D, 64, rows)) return e;
+  if (sp.cross) {
+    if (sp.kv == nullptr || sp.kv_ld < sp.n_layers * 2 * D) return "xformer_stack: cross-attention needs the K|V rows";
+    if (const char* e = enc2d(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.kv, sp.kv_ld, M, sp.kv_ld, 64, rows)) return e;
+  }
+  StackDev d{};
+  d.wstream = sp.wstream; d.vecs = sp.vecs; d.fin_gamma = sp.fin_gamma; d.fin_beta = sp.fin_beta;
+  d.n_layers = sp.n_layers; d.items_per_layer = sp.cross ? ITEMS_CROSS : ITEMS_SELF; d.cross = sp.cross ? 1 : 0;
+  d.L = sp.L; d.rows = rows; d.M = M; d.n_tiles = n_tiles;
+  d.act = sp.act; d.out_x = sp.out_x != nullptr; d.out_op = sp.out_op != nullptr;
+  d.kv_ld_layer = 2 * D;
+  d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
+  const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  if (launch_pdl(xformer_stack_kernel, dim3(grid), dim3(STACK_THREADS), STACK_SMEM, s, tin, tout, top, tkv, d) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return "xformer_stack: launch failed";
+  }
+  return nullptr;
+}
+
+}  // namespace avsep

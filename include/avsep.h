@@ -224,6 +224,13 @@ AVSEP_API int avsep_stft(avsep_handle* h, const float* waves, int32_t B, int32_t
 AVSEP_API int avsep_istft(avsep_handle* h, const float* spec, const float* masks, int32_t B, int32_t S, int32_t T,
                           int32_t n_fft, int32_t hop_length, int32_t L, float* waves, void* cuda_stream);
 
+/* Test hook: one whole transformer stack through the fused kernel (csrc/xformer_stack_sm100.cu) on the handle's
+ * weights.  which: 0 = AudioEncoder.transformer (model.py:48-52,59), 1 = VisualEncoder.transformer (model.py:97-101,111),
+ * 2 = CrossModalFusion.layers (+ .norm when final_ln) (model.py:145-149,166-173) with kv = bf16 [B*L, Lf*2*d] rows holding
+ * every layer's projected K | V.  x_in fp32 [B*L, d]; out_x fp32 / out_op bf16 [B*L, d], either may be NULL. */
+AVSEP_API int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, const void* kv, int32_t B,
+                                       int32_t L, float* out_x, void* out_op, int32_t final_ln, void* cuda_stream);
+
 /* ---- batch sharding over the GPUs of one box (BASELINE.json north_star: "inputs scattered and
  * separated/masks gathered over NVLink") -------------------------------------------------------------------------
  * The path shards by utterance with no collective inside the model (model.py has no op that mixes batch elements in
