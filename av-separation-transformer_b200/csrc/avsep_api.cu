@@ -368,8 +368,9 @@ bool stack_fusable(const avsep_handle* h, int len) {
 
 // A whole stack in one kernel (xformer_stack_sm100.cu).  which: 0 audio encoder, 1 visual encoder, 2 fusion.
 int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, float* out_x, void* out_op,
-              const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L) {
+              const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L, long long* trace = nullptr) {
   StackProblem sp{};
+  sp.trace = trace;
   sp.x_in = x_in; sp.out_x = out_x; sp.out_op = out_op; sp.fin_gamma = fin_g; sp.fin_beta = fin_b;
   sp.wstream = which == 0 ? h->xs_a : which == 1 ? h->xs_v : h->xs_f;
   sp.vecs = which == 0 ? h->xv_a : which == 1 ? h->xv_v : h->xv_f;
@@ -1562,7 +1563,7 @@ int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, c
 // or out_op bf16 (final_ln != 0: the LayerNorm that follows the stack in the model -- fusion layer 0 norm1 after the
 // audio encoder, fusion.norm after the fusion stack; the visual encoder has none -- else a plain cast).
 int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, const void* kv, int32_t B, int32_t L,
-                             float* out_x, void* out_op, int32_t final_ln, void* cuda_stream) {
+                             float* out_x, void* out_op, int32_t final_ln, long long* trace_dev, void* cuda_stream) {
   if (!h) return 1;
   if (!h->finalized) return fail(h, "weights not finalized");
   if (which < 0 || which > 2) return fail(h, "test_xformer_stack: which must be 0, 1 or 2");
@@ -1573,7 +1574,7 @@ int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, 
   if (final_ln && which == 2) { g = h->fng; b = h->fnb; }
   h->prof_stream = static_cast<cudaStream_t>(cuda_stream);
   return run_stack(h, static_cast<cudaStream_t>(cuda_stream), which, x_in, out_x, out_op, g, b, kv,
-                   h->cfg.num_fusion_layers * 2 * h->cfg.d_model, B, L);
+                   h->cfg.num_fusion_layers * 2 * h->cfg.d_model, B, L, trace_dev);
 }
 
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {

@@ -109,6 +109,7 @@ struct StackProblem {
   int kv_ld;
   int B, L;
   int act;
+  long long* trace = nullptr;   // optional [grid][256] clock64 stamps (debug)
 };
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
 size_t xformer_stream_bytes(bool cross);

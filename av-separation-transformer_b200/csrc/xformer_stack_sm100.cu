@@ -71,7 +71,11 @@ struct StackDev {
   int out_x, out_op;
   int kv_ld_layer;              // cross: column offset between layers in the K|V matrix (2 * D)
   float qscale;
+  long long* trace;             // optional [grid][256] clock64 stamps of the CTA's first tile (debug), else null:
+                                //   row thread (warp 2 lane 0) in [0,128), MMA thread in [128,256); see tools/stack_trace.py
 };
+
+#define XTRACE(slot) do { if (p.trace != nullptr && lt == 0 && (slot) < 128) p.trace[blockIdx.x * 256 + trace_base + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t soff(int row, int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); }
 
@@ -224,12 +228,18 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         return smem_u32(smem + OFF_RING + cur_slot * ITEM);
       };
       const uint32_t a_base = smem_u32(smem + OFF_A);
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      constexpr int trace_base = 128;
+      int lt = 0;
+      XTRACE(0);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
         for (int l = 0; l < p.n_layers; ++l) {
+          const int tb = 1 + l * 60;               // MMA-thread stamps of layer l: tb + 0 LN1 seen; per head 6; FFN per chunk 3
           // ======== attention sub-layer ========
           mbar_wait(a_ready, n_a & 1); ++n_a;
           tc_fence_after();
+          XTRACE(tb);
           for (int h = 0; h < NH; ++h, ++n_h) {
+            const int th = tb + 1 + h * 6;
             if (!p.cross) {
               // Q_h | K_h : N = 128 into W[0,128)
               for (int it = 0; it < 2; ++it) {
@@ -272,10 +282,12 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               umma_commit(&w_empty[cur_slot]);
             }
             umma_commit(qkv_full);
+            XTRACE(th);                                     // QKV_h issued
             // S = Q K^T : A = Q_h from tensor memory, B = K tile
             mbar_wait(qk_ready, n_h & 1);
             if (p.cross) mbar_wait(kv_full, n_h & 1);
             tc_fence_after();
+            XTRACE(th + 1);                                 // qk_ready seen
             {
               const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_KT), 1024);
 #pragma unroll
@@ -286,6 +298,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             // O = P V : A = P from tensor memory (K = 128 keys), B = V tile (MN-major)
             mbar_wait(p_ready, n_h & 1);
             tc_fence_after();
+            XTRACE(th + 2);                                 // p_ready seen
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(smem + OFF_VT + ks * 2048), 1024, 1024);
@@ -296,6 +309,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             // X += O_h Wo[:, h*64 : (h+1)*64]^T : A = O_h from tensor memory, two 128-row halves of Wo
             mbar_wait(o_ready, n_h & 1);
             tc_fence_after();
+            XTRACE(th + 3);                                 // o_ready seen
             {
               const uint32_t base = next_item();
 #pragma unroll
@@ -309,9 +323,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             }
           }
           umma_commit(attn_done);
+          XTRACE(tb + 25);                                  // attention issued
           // ======== feed-forward sub-layer ========
           mbar_wait(a_ready, n_a & 1); ++n_a;
           tc_fence_after();
+          XTRACE(tb + 26);                                  // LN2 seen
           for (int j = 0; j <= NCHUNK; ++j) {
             if (j < NCHUNK) {
               const uint32_t st = c1n & 1;
@@ -329,12 +345,14 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
                 umma_commit(&w_empty[cur_slot]);
               }
               umma_commit(&acc1_full[st]);
+              XTRACE(tb + 27 + 3 * j);                      // G1_j issued
               ++c1n;
             }
             if (j >= 1) {
               const uint32_t st2 = c2n & 1;
               mbar_wait(&h_full[st2], (c2n >> 1) & 1);
               tc_fence_after();
+              XTRACE(tb + 28 + 3 * (j - 1));                // H_{j-1} seen
               for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t base = next_item();
 #pragma unroll
@@ -346,6 +364,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
                 }
                 umma_commit(&w_empty[cur_slot]);
               }
+              XTRACE(tb + 29 + 3 * (j - 1));                // G2_{j-1} issued
               ++c2n;
             }
           }
@@ -365,6 +384,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     const int khi = min(128, klo + p.L);
     uint32_t nx = 0;                                         // exchanges through `red` so far (double buffered)
     uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0;
+    const int trace_base = (threadIdx.x == 64) ? 0 : 1024;   // only the first row thread stamps
 
     auto exchange = [&](float2 mine, float2 (&all)[4]) {
       float2* buf = red + (nx & 1) * 512 + r * 4;
@@ -450,7 +470,9 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
       const int row0 = tile * p.rows;
       // ---- residual tile: staging slabs (fp32, 32 columns each) -> tensor memory ----
+      XTRACE(0);
       mbar_wait(x_full, lt & 1);
+      XTRACE(1);                                             // x staged
       {
         uint32_t u[32];
 #pragma unroll
@@ -484,13 +506,18 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         }
         named_bar_sync(5, 512);
         tc_fence_after();
+        const int tb = 2 + l * 60;     // row-thread stamps of layer l: +0 LN1 start, +1 LN1 done; per head 6; +26.. FFN
+        XTRACE(tb);
         ln_to_a(l > 0 ? pend : nullptr, vec + VEC_N1G, vec + VEC_N1B);
+        XTRACE(tb + 1);
 
         // ======== attention ========
         for (int h = 0; h < NH; ++h, ++n_h) {
           // ---- Q (scaled, bf16, back into tensor memory as an A operand); K, V (bf16) into their shared-memory tiles
+          const int th = tb + 2 + h * 6;
           mbar_wait(qkv_full, n_h & 1);
           tc_fence_after();
+          XTRACE(th);                                        // QKV_h accumulators complete
           {
             uint32_t a[16];
             tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + part * 16, a);
@@ -530,10 +557,12 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(qk_ready);
           }
+          XTRACE(th + 1);                                    // Q / K / V operands written
           // ---- softmax over the row's own utterance; P (bf16 pairs) over the first 64 columns of S ----
           float inv_l;
           mbar_wait(s_full, n_h & 1);
           tc_fence_after();
+          XTRACE(th + 2);                                    // S complete
           {
             const int c0 = part * 32;
             const int lo_i = klo - c0, hi_i = khi - c0;      // this row's valid columns of the part: [lo_i, hi_i)
@@ -575,9 +604,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
           }
+          XTRACE(th + 3);                                    // P written
           // ---- O_h / rowsum -> bf16 A operand of the out_proj slice ----
           mbar_wait(o_full, n_h & 1);
           tc_fence_after();
+          XTRACE(th + 4);                                    // O complete
           {
             uint32_t o[16], op[8];
             tmem_ld_32x32b_x16(tmW + lane_sel + TW_V + part * 16, o);
@@ -591,17 +622,21 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(o_ready);
           }
+          XTRACE(th + 5);                                    // O operand written
         }
         // ======== x += out_proj bias; LayerNorm 2 ========
         mbar_wait(attn_done, n_attn & 1); ++n_attn;
         tc_fence_after();
+        XTRACE(tb + 26);                                     // attention complete
         ln_to_a(vec + VEC_BO, vec + VEC_N2G, vec + VEC_N2B);
+        XTRACE(tb + 27);                                     // LN2 done
 
         // ======== feed-forward: bias + activation on each 128-wide hidden chunk, back into tensor memory as bf16 ====
         for (int j = 0; j < NCHUNK; ++j, ++c1n) {
           const uint32_t st = c1n & 1;
           mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
           tc_fence_after();
+          XTRACE(tb + 28 + 2 * j);                           // acc1_j complete
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
           tmem_ld_wait();
@@ -631,9 +666,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&h_full[st]);
+          XTRACE(tb + 29 + 2 * j);                           // H_j written
         }
         mbar_wait(ffn_done, n_ffn & 1); ++n_ffn;
         tc_fence_after();
+        XTRACE(tb + 44);                                     // FFN complete
       }
       // ---- stack output: x + last linear2 bias -> fp32 residual rows and / or (final LayerNorm | cast) bf16 rows ----
       {
@@ -676,6 +713,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           bulk_wait_read0();
           mbar_arrive(stage_free);
         }
+        XTRACE(127);                                         // tile done
       }
     }
     if (elected) bulk_wait_read0();
@@ -825,6 +863,7 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   d.act = sp.act; d.out_x = sp.out_x != nullptr; d.out_op = sp.out_op != nullptr;
   d.kv_ld_layer = 2 * D;
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
+  d.trace = sp.trace;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   if (launch_pdl(xformer_stack_kernel, dim3(grid), dim3(STACK_THREADS), STACK_SMEM, s, tin, tout, top, tkv, d) !=
       cudaSuccess) {

@@ -229,7 +229,8 @@ AVSEP_API int avsep_istft(avsep_handle* h, const float* spec, const float* masks
  * 2 = CrossModalFusion.layers (+ .norm when final_ln) (model.py:145-149,166-173) with kv = bf16 [B*L, Lf*2*d] rows holding
  * every layer's projected K | V.  x_in fp32 [B*L, d]; out_x fp32 / out_op bf16 [B*L, d], either may be NULL. */
 AVSEP_API int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, const void* kv, int32_t B,
-                                       int32_t L, float* out_x, void* out_op, int32_t final_ln, void* cuda_stream);
+                                       int32_t L, float* out_x, void* out_op, int32_t final_ln, long long* trace_dev,
+                                       void* cuda_stream);   /* trace_dev: NULL or [grid][256] clock stamps (tools/stack_trace.py) */
 
 /* ---- batch sharding over the GPUs of one box (BASELINE.json north_star: "inputs scattered and
  * separated/masks gathered over NVLink") -------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def _run(eng, which, x, kv, B, L, want_x, want_op, final_ln):
     out_op = torch.full((B * L, x.shape[-1]), float("nan"), device=dev, dtype=torch.bfloat16) if want_op else None
     rc = eng.lib.avsep_test_xformer_stack(eng.h, which, xd.data_ptr(), kvd.data_ptr() if kvd is not None else None, B, L,
                                           out_x.data_ptr() if want_x else None, out_op.data_ptr() if want_op else None,
-                                          1 if final_ln else 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                          1 if final_ln else 0, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, eng.lib.avsep_last_error(eng.h).decode()
     torch.cuda.synchronize()
     return (out_x.cpu().numpy() if want_x else None), (out_op.float().cpu().numpy() if want_op else None)
