@@ -130,7 +130,6 @@ struct avsep_handle {
   std::vector<FusLayerW> fus;
   // prepacked weight streams / vector blocks of the fused transformer-stack kernel (null when the config cannot use it)
   const uint8_t *xs_a = nullptr, *xs_v = nullptr, *xs_f = nullptr;
-  const float *xv_a = nullptr, *xv_v = nullptr, *xv_f = nullptr;
   bool fuse_stack = true;   // whole encoder / fusion stacks in one persistent kernel (d_model = 256, 4 heads, bf16, len <= 128)
   // cached library-owned workspace
   void* own_ws = nullptr;
@@ -373,7 +372,6 @@ int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, flo
   sp.trace = trace;
   sp.x_in = x_in; sp.out_x = out_x; sp.out_op = out_op; sp.fin_gamma = fin_g; sp.fin_beta = fin_b;
   sp.wstream = which == 0 ? h->xs_a : which == 1 ? h->xs_v : h->xs_f;
-  sp.vecs = which == 0 ? h->xv_a : which == 1 ? h->xv_v : h->xv_f;
   sp.n_layers = which == 2 ? h->cfg.num_fusion_layers : h->cfg.num_encoder_layers;
   sp.cross = which == 2;
   sp.kv = kv; sp.kv_ld = kv_ld;
@@ -958,7 +956,7 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     for (int stack = 0; stack < 2; ++stack) {
       const std::string pre = stack == 0 ? "audio_encoder" : "visual_encoder";
       std::vector<uint8_t> stream(static_cast<size_t>(Le) * xformer_stream_bytes(false));
-      std::vector<float> vecs(static_cast<size_t>(Le) * vf);
+      std::vector<float> vecs(vf);
       for (int l = 0; l < Le; ++l) {
         const std::string p = pre + ".transformer.layers." + std::to_string(l);
         GETW(wqkv, p + ".self_attn.in_proj_weight", 3 * d, d);
@@ -973,16 +971,15 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
         GETW(n1b, p + ".norm1.bias", d);
         GETW(n2g, p + ".norm2.weight", d);
         GETW(n2b, p + ".norm2.bias", d);
-        xformer_pack_self(wqkv->data.data(), wo->data.data(), w1->data.data(), w2->data.data(),
-                          stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(false));
         xformer_pack_vecs(bqkv->data.data(), static_cast<int>(3 * d), bo->data.data(), b1->data.data(), b2->data.data(),
-                          n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data() + l * vf);
+                          n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data());
+        xformer_pack_self(wqkv->data.data(), wo->data.data(), w1->data.data(), w2->data.data(), vecs.data(),
+                          stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(false));
       }
       off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
-      off[stack == 0 ? "xv_a" : "xv_v"] = ar.add_f32(vecs.data(), vecs.size());
     }
     std::vector<uint8_t> stream(static_cast<size_t>(Lf) * xformer_stream_bytes(true));
-    std::vector<float> vecs(static_cast<size_t>(Lf) * vf);
+    std::vector<float> vecs(vf);
     for (int l = 0; l < Lf; ++l) {
       const std::string p = "fusion.layers." + std::to_string(l);
       GETW(win, p + ".cross_attn.in_proj_weight", 3 * d, d);
@@ -997,13 +994,12 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       GETW(n1b, p + ".norm1.bias", d);
       GETW(n2g, p + ".norm2.weight", d);
       GETW(n2b, p + ".norm2.bias", d);
-      xformer_pack_cross(win->data.data(), wo->data.data(), w1->data.data(), w2->data.data(),
-                         stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(true));
       xformer_pack_vecs(bin->data.data(), static_cast<int>(d), bo->data.data(), b1->data.data(), b2->data.data(),
-                        n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data() + l * vf);
+                        n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data());
+      xformer_pack_cross(win->data.data(), wo->data.data(), w1->data.data(), w2->data.data(), vecs.data(),
+                         stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(true));
     }
     off["xs_f"] = ar.add(stream.data(), stream.size());
-    off["xv_f"] = ar.add_f32(vecs.data(), vecs.size());
   }
 #undef GETW
   // upload
@@ -1030,11 +1026,9 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->cnn_w2_slabs = static_cast<const uint8_t*>(P("tcw2"));
   h->cnn_w3_rows = static_cast<const uint8_t*>(P("tcw3"));
   h->xs_a = h->xs_v = h->xs_f = nullptr;
-  h->xv_a = h->xv_v = h->xv_f = nullptr;
   if (pack_stacks) {
     h->xs_a = static_cast<const uint8_t*>(P("xs_a")); h->xs_v = static_cast<const uint8_t*>(P("xs_v"));
     h->xs_f = static_cast<const uint8_t*>(P("xs_f"));
-    h->xv_a = PF("xv_a"); h->xv_v = PF("xv_v"); h->xv_f = PF("xv_f");
   }
   h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();
   for (int stack = 0; stack < 2; ++stack)

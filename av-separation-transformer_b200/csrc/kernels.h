@@ -101,8 +101,7 @@ struct StackProblem {
   float* out_x;             // [B*L, 256] fp32 residual after the stack (may alias x_in) or null
   void* out_op;             // [B*L, 256] bf16: final LayerNorm (fin_gamma/fin_beta) or plain cast (fin_gamma == null), or null
   const float *fin_gamma, *fin_beta;
-  const uint8_t* wstream;   // n_layers x xformer_stream_bytes(cross)
-  const float* vecs;        // n_layers x xformer_vec_floats()
+  const uint8_t* wstream;   // n_layers x xformer_stream_bytes(cross): per layer a vector block, then the weight items
   int n_layers;
   bool cross;               // false: self-attention encoder layers (ReLU); true: cross-attention fusion layers (GELU)
   const void* kv;           // cross: bf16 [B*L, kv_ld] rows, layer l's K at columns [l*512, +256), V at [l*512+256, +256)
@@ -114,8 +113,10 @@ struct StackProblem {
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
 size_t xformer_stream_bytes(bool cross);
 int xformer_vec_floats();
-void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, uint8_t* dst);
-void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, uint8_t* dst);
+void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, const float* vecs,
+                       uint8_t* dst);   // vecs: xformer_vec_floats() values from xformer_pack_vecs
+void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, const float* vecs,
+                        uint8_t* dst);
 void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const float* b1, const float* b2, const float* n1g,
                        const float* n1b, const float* n2g, const float* n2b, float* dst);
 const char* launch_xformer_stack(cudaStream_t s, const StackProblem& p, int num_sms);

@@ -4,8 +4,9 @@
 //                                                                       torch/nn/modules/transformer.py:946-950
 //   cross : CrossAttentionLayer x L (audio queries, visual keys/values, erf-GELU FFN)   model.py:152-173
 //
-// One CTA owns a tile of whole utterances (U = floor(128 / len) of them: two 63-frame audio clips or two 50-frame
-// lip sequences = up to 128 rows) through EVERY layer of the stack.  The fp32 residual stream of the tile lives in
+// One CTA owns a tile of whole utterances (U = 2 for 33..64 rows each: two 63-frame audio clips or two 50-frame lip
+// sequences; U is a power of two and utterance u sits at tile rows [u * 128/U, +len), so the attention blocks line up
+// with 32-column parts) through EVERY layer of the stack.  The fp32 residual stream of the tile lives in
 // tensor memory (256 of the 512 columns) for the whole kernel: out_proj and linear2 accumulate straight onto it
 // (D += A B with D = the residual), so no residual ever goes through shared memory, L2 or HBM between sub-layers.
 // The only traffic in the steady state is the weight stream: 1.5 MB per layer, prepacked as 32 KB shared-memory
@@ -48,6 +49,7 @@ constexpr int OFF_RING = OFF_A + 4 * SLAB;        // weight ring; its first 64 K
 constexpr int OFF_KT = OFF_RING + NSLOT * ITEM;   // K_h tile [keys x 64] K-major
 constexpr int OFF_VT = OFF_KT + SLAB;             // V_h tile [keys x 64] (MN-major B operand of P V)
 constexpr int OFF_RED = OFF_VT + SLAB;            // 2 x [128 rows][4 parts] float2
+// per-layer vector block = first item of every layer in the weight stream
 constexpr int VEC_BQKV = 0, VEC_BO = 768, VEC_B1 = 1024, VEC_B2 = 2048, VEC_N1G = 2304, VEC_N1B = 2560,
               VEC_N2G = 2816, VEC_N2B = 3072, VEC_FLOATS = 3328;
 constexpr int OFF_VEC = OFF_RED + 2 * 4096;
@@ -56,17 +58,16 @@ constexpr int OFF_BAR = OFF_PEND + 3 * 1024;
 constexpr int STACK_SMEM = OFF_BAR + 512;
 static_assert(STACK_SMEM <= 227 * 1024, "xformer_stack: shared memory budget exceeded");
 constexpr int STACK_THREADS = 32 * 18;
-constexpr int ITEMS_SELF = 48, ITEMS_CROSS = 40;
+constexpr int ITEMS_SELF = 49, ITEMS_CROSS = 41;   // vector block + weights
 
 constexpr uint32_t TM_X = 0, TM_W = 256;          // tensor-memory column bases
 constexpr uint32_t TW_S = 0, TW_V = 128, TW_QOP = 192, TW_OOP = 224;
 
 struct StackDev {
   const uint8_t* wstream;       // n_layers x items x 32 KB, consumption order (see xformer_pack_*)
-  const float* vecs;            // n_layers x VEC_FLOATS
   const float *fin_gamma, *fin_beta;
   int n_layers, items_per_layer, cross;
-  int L, rows, M, n_tiles;      // rows per utterance, rows per tile (U * L), total rows
+  int L, U, stride, B, n_tiles; // rows per utterance, utterances per tile, tile rows per utterance slot (128 / U)
   int act;
   int out_x, out_op;
   int kv_ld_layer;              // cross: column offset between layers in the K|V matrix (2 * D)
@@ -111,8 +112,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   uint64_t* x_taken = bars + 7;            // (16) staging copied into tensor memory
   uint64_t* stage_free = bars + 8;         // (4) output stores have read the staging slabs
   uint64_t* a_ready = bars + 9;            // (16) LayerNorm output in smem, X updated
-  uint64_t* qkv_full = bars + 10;
-  uint64_t* qk_ready = bars + 11;          // (16)
+  uint64_t* qk_full = bars + 10;           // Q_h | K_h accumulators complete
+  uint64_t* qop_ready = bars + 11;         // (16) Q operand in tensor memory, K tile in shared memory
   uint64_t* s_full = bars + 12;
   uint64_t* p_ready = bars + 13;           // (16)
   uint64_t* o_full = bars + 14;
@@ -123,7 +124,9 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   uint64_t* acc1_full = bars + 19;         // [2]
   uint64_t* h_full = bars + 21;            // [2] (16)
   uint64_t* ffn_done = bars + 23;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* v_full = bars + 24;            // self: V_h accumulator complete
+  uint64_t* v_ready = bars + 25;           // (16) self: V tile in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
   float* pend = reinterpret_cast<float*>(smem + OFF_PEND);
@@ -142,8 +145,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     mbar_init(x_taken, 16);
     mbar_init(stage_free, 4);
     mbar_init(a_ready, 16);
-    mbar_init(qkv_full, 1);
-    mbar_init(qk_ready, 16);
+    mbar_init(qk_full, 1);
+    mbar_init(qop_ready, 16);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 16);
     mbar_init(o_full, 1);
@@ -153,14 +156,16 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     mbar_init(attn_done, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&h_full[i], 16); }
     mbar_init(ffn_done, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_ready, 16);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < D; i += STACK_THREADS) {
     fin_g[i] = p.fin_gamma ? __ldg(p.fin_gamma + i) : 1.f;
     fin_b[i] = p.fin_beta ? __ldg(p.fin_beta + i) : 0.f;
   }
-  // K / V tiles: rows past the tile's utterances are never written by the TMA loads of the cross-attention path; they
-  // must be finite (P is 0 there, and 0 x NaN would poison real rows)
+  // K / V tiles: rows the TMA loads of the cross-attention path never write (past an utterance's length) must be
+  // finite: P is 0 there, and 0 x NaN would poison real rows
   for (int i = threadIdx.x; i < 2 * SLAB / 16; i += STACK_THREADS)
     *reinterpret_cast<uint4*>(smem + OFF_KT + i * 16) = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
@@ -175,9 +180,10 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- producer: x tile, weight stream, (cross) K / V tiles ----------------
-      uint32_t wn = 0;          // weight items issued
+      // ---------------- producer: x tile, weight stream (incl. the per-layer vector block), (cross) K / V tiles ------
+      uint32_t wn = 0;          // stream items issued
       uint32_t hn = 0;          // heads whose K/V tiles were issued (cross)
+      const uint32_t box_bytes = static_cast<uint32_t>(p.L) * 128u;
       auto load_item = [&](const uint8_t* src) {
         const uint32_t slot = wn % NSLOT, use = wn / NSLOT;
         mbar_wait(&w_empty[slot], (use & 1) ^ 1);
@@ -187,24 +193,40 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       };
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-        const int row0 = tile * p.rows;
+        const int utt0 = tile * p.U;
+        auto load_kv = [&](int l, int h) {
+          if (hn > 0) mbar_wait(kv_empty, (hn - 1) & 1);
+          mbar_arrive_expect_tx(kv_full, 2u * p.U * box_bytes);
+          for (int u = 0; u < p.U; ++u) {
+            tma_load_2d(smem + OFF_KT + u * p.stride * 128, &tmKV, kv_full, l * p.kv_ld_layer + h * HDIM, (utt0 + u) * p.L);
+            tma_load_2d(smem + OFF_VT + u * p.stride * 128, &tmKV, kv_full, l * p.kv_ld_layer + D + h * HDIM, (utt0 + u) * p.L);
+          }
+          ++hn;
+        };
         if (lt > 0) mbar_wait(stage_free, (lt - 1) & 1);
-        mbar_arrive_expect_tx(x_full, 8u * static_cast<uint32_t>(p.rows) * 128u);
-        for (int s = 0; s < 8; ++s) tma_load_2d(smem + OFF_A + s * SLAB, &tmXin, x_full, s * 32, row0);
+        mbar_arrive_expect_tx(x_full, 8u * p.U * box_bytes);
+        for (int s = 0; s < 8; ++s)
+          for (int u = 0; u < p.U; ++u)
+            tma_load_2d(smem + OFF_A + s * SLAB + u * p.stride * 128, &tmXin, x_full, s * 32, (utt0 + u) * p.L);
         mbar_wait(x_taken, lt & 1);            // staging (a_op + first two ring slots) is free again
         for (int l = 0; l < p.n_layers; ++l) {
           const uint8_t* src = p.wstream + static_cast<size_t>(l) * p.items_per_layer * ITEM;
+          load_item(src);                      // vector block
+          src += ITEM;
           if (!p.cross) {
             for (int i = 0; i < 16; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
             src += 16 * ITEM;
           } else {
-            for (int h = 0; h < NH; ++h, ++hn) {
-              load_item(src + static_cast<size_t>(2 * h) * ITEM);                  // Wq_h
-              if (hn > 0) mbar_wait(kv_empty, (hn - 1) & 1);
-              mbar_arrive_expect_tx(kv_full, 2u * static_cast<uint32_t>(p.rows) * 128u);
-              tma_load_2d(smem + OFF_KT, &tmKV, kv_full, l * p.kv_ld_layer + h * HDIM, row0);
-              tma_load_2d(smem + OFF_VT, &tmKV, kv_full, l * p.kv_ld_layer + D + h * HDIM, row0);
-              load_item(src + static_cast<size_t>(2 * h + 1) * ITEM);              // Wo_h
+            // consumption order: Q_0 | per head h: Q_{h+1}, Wo_h ; K/V tiles of head h+1 once P V of head h is done
+            load_item(src);
+            load_kv(l, 0);
+            int it = 1;
+            for (int h = 0; h < NH; ++h) {
+              if (h + 1 < NH) {
+                load_item(src + static_cast<size_t>(it++) * ITEM);
+                load_kv(l, h + 1);
+              }
+              load_item(src + static_cast<size_t>(it++) * ITEM);
             }
             src += 8 * ITEM;
           }
@@ -228,66 +250,70 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         return smem_u32(smem + OFF_RING + cur_slot * ITEM);
       };
       const uint32_t a_base = smem_u32(smem + OFF_A);
+      // Q_h | K_h (self: N = 128 into W[0,128), two items) or Q_h (cross: N = 64 into W[0,64), one item)
+      auto issue_qk = [&]() {
+        if (!p.cross) {
+          for (int it = 0; it < 2; ++it) {
+            const uint32_t base = next_item();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int ks = 2 * it + half;
+              const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+              const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&w_empty[cur_slot]);
+          }
+        } else {
+          const uint32_t base = next_item();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&w_empty[cur_slot]);
+        }
+        umma_commit(qk_full);
+      };
+      // V_h : N = 64 into W[128,192) (self-attention); its epilogue runs under the S = Q K^T round trip
+      auto issue_v = [&]() {
+        const uint32_t base = next_item();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(tmW + TW_V, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&w_empty[cur_slot]);
+        umma_commit(v_full);
+      };
       constexpr int trace_base = 128;
       int lt = 0;
       XTRACE(0);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
         for (int l = 0; l < p.n_layers; ++l) {
           const int tb = 1 + l * 60;               // MMA-thread stamps of layer l: tb + 0 LN1 seen; per head 6; FFN per chunk 3
+          ++wn;                                    // the layer's vector block is consumed by the row warps
           // ======== attention sub-layer ========
           mbar_wait(a_ready, n_a & 1); ++n_a;
           tc_fence_after();
           XTRACE(tb);
+          issue_qk();
+          if (!p.cross) issue_v();
           for (int h = 0; h < NH; ++h, ++n_h) {
             const int th = tb + 1 + h * 6;
-            if (!p.cross) {
-              // Q_h | K_h : N = 128 into W[0,128)
-              for (int it = 0; it < 2; ++it) {
-                const uint32_t base = next_item();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                  const int ks = 2 * it + half;
-                  const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
-                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
-                }
-                umma_commit(&w_empty[cur_slot]);
-              }
-              // V_h : N = 64 into W[128,192)
-              {
-                const uint32_t base = next_item();
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
-                  const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_f16(tmW + TW_V, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
-                }
-                umma_commit(&w_empty[cur_slot]);
-              }
-            } else {
-              // Q_h : N = 64 into W[0,64)
-              const uint32_t base = next_item();
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
-                const uint64_t bdesc = umma_desc_kmajor_sw128(base + ks * 8192, 1024);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_f16(tmW + TW_S, adesc + 2 * kk, bdesc + 2 * kk, ID64, (ks | kk) != 0 ? 1u : 0u);
-              }
-              umma_commit(&w_empty[cur_slot]);
-            }
-            umma_commit(qkv_full);
-            XTRACE(th);                                     // QKV_h issued
             // S = Q K^T : A = Q_h from tensor memory, B = K tile
-            mbar_wait(qk_ready, n_h & 1);
+            mbar_wait(qop_ready, n_h & 1);
             if (p.cross) mbar_wait(kv_full, n_h & 1);
             tc_fence_after();
-            XTRACE(th + 1);                                 // qk_ready seen
+            XTRACE(th);                                     // Q operand / K tile seen
             {
               const uint64_t kdesc = umma_desc_kmajor_sw128(smem_u32(smem + OFF_KT), 1024);
 #pragma unroll
@@ -295,10 +321,12 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
                 umma_f16_ts(tmW + TW_S, tmW + TW_QOP + kk * 8, kdesc + 2 * kk, ID128, kk != 0 ? 1u : 0u);
             }
             umma_commit(s_full);
+            XTRACE(th + 1);                                 // S_h issued
             // O = P V : A = P from tensor memory (K = 128 keys), B = V tile (MN-major)
             mbar_wait(p_ready, n_h & 1);
+            if (!p.cross) mbar_wait(v_ready, n_h & 1);
             tc_fence_after();
-            XTRACE(th + 2);                                 // p_ready seen
+            XTRACE(th + 2);                                 // P and V seen
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t vdesc = umma_desc_mnmajor_sw128(smem_u32(smem + OFF_VT + ks * 2048), 1024, 1024);
@@ -306,6 +334,9 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             }
             umma_commit(o_full);
             if (p.cross) umma_commit(kv_empty);
+            // the next head's Q | K projection runs under this head's output epilogue (W[0,128) is free once P V has
+            // read P: the tensor pipe executes in issue order)
+            if (h + 1 < NH) issue_qk();
             // X += O_h Wo[:, h*64 : (h+1)*64]^T : A = O_h from tensor memory, two 128-row halves of Wo
             mbar_wait(o_ready, n_h & 1);
             tc_fence_after();
@@ -321,6 +352,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               }
               umma_commit(&w_empty[cur_slot]);
             }
+            // W[128,192) is free again (the output epilogue has drained O_h): the next head's V projection
+            if (!p.cross && h + 1 < NH) issue_v();
           }
           umma_commit(attn_done);
           XTRACE(tb + 25);                                  // attention issued
@@ -379,11 +412,13 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     const int etid = threadIdx.x - 64;                       // 0..511
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const bool elected = (warp == 2 + 4 * part) && (lane == 0);
-    // block-diagonal attention: row r attends keys [klo, khi) of its own utterance (padding rows attend each other)
-    const int klo = (r / p.L) * p.L;
-    const int khi = min(128, klo + p.L);
+    // block-diagonal attention: row r attends the keys [klo, klo + L) of its own utterance slot
+    const int klo = (r / p.stride) * p.stride;
+    const bool row_valid = (r - klo) < p.L;                  // tile rows past the utterance's length are padding
+    // this row's valid score columns within the part: [lo_i, hi_i)
+    const int lo_i = klo - part * 32, hi_i = klo + p.L - part * 32;
     uint32_t nx = 0;                                         // exchanges through `red` so far (double buffered)
-    uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0;
+    uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0, n_layer = 0;
     const int trace_base = (threadIdx.x == 64) ? 0 : 1024;   // only the first row thread stamps
 
     auto exchange = [&](float2 mine, float2 (&all)[4]) {
@@ -468,7 +503,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
 
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
-      const int row0 = tile * p.rows;
+      const int utt0 = tile * p.U;
       // ---- residual tile: staging slabs (fp32, 32 columns each) -> tensor memory ----
       XTRACE(0);
       mbar_wait(x_full, lt & 1);
@@ -478,7 +513,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const uint8_t* slab = smem + OFF_A + (part * 2 + c) * SLAB;
-          if (r < p.rows) {
+          if (row_valid) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 w = *reinterpret_cast<const uint4*>(slab + soff(r, i));
@@ -495,16 +530,22 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(x_taken);
       }
-      for (int l = 0; l < p.n_layers; ++l) {
-        // ---- per-layer vectors; the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
-        named_bar_sync(5, 512);
+      for (int l = 0; l < p.n_layers; ++l, ++n_layer) {
+        // ---- per-layer vectors: first item of the layer in the weight stream (it was prefetched under the previous
+        // layer's FFN); the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
+        const uint32_t vn = n_layer * static_cast<uint32_t>(p.items_per_layer);
+        const uint32_t vslot = vn % NSLOT;
+        named_bar_sync(5, 512);                              // every row warp is done with the previous vectors
         if (l > 0 && etid < D) pend[etid] = vec[VEC_B2 + etid];
+        mbar_wait(&w_full[vslot], (vn / NSLOT) & 1);
         named_bar_sync(5, 512);
         {
-          const float* src = p.vecs + static_cast<size_t>(l) * VEC_FLOATS;
-          for (int i = etid; i < VEC_FLOATS; i += 512) vec[i] = __ldg(src + i);
+          const float4* src = reinterpret_cast<const float4*>(smem + OFF_RING + vslot * ITEM);
+          float4* dst = reinterpret_cast<float4*>(vec);
+          for (int i = etid; i < VEC_FLOATS / 4; i += 512) dst[i] = src[i];
         }
         named_bar_sync(5, 512);
+        if (etid == 0) mbar_arrive(&w_empty[vslot]);
         tc_fence_after();
         const int tb = 2 + l * 60;     // row-thread stamps of layer l: +0 LN1 start, +1 LN1 done; per head 6; +26.. FFN
         XTRACE(tb);
@@ -513,11 +554,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
 
         // ======== attention ========
         for (int h = 0; h < NH; ++h, ++n_h) {
-          // ---- Q (scaled, bf16, back into tensor memory as an A operand); K, V (bf16) into their shared-memory tiles
           const int th = tb + 2 + h * 6;
-          mbar_wait(qkv_full, n_h & 1);
+          // ---- Q (scaled, bf16, back into tensor memory as an A operand); K (bf16) into its shared-memory tile ----
+          mbar_wait(qk_full, n_h & 1);
           tc_fence_after();
-          XTRACE(th);                                        // QKV_h accumulators complete
+          XTRACE(th);                                        // Q_h | K_h accumulators complete
           {
             uint32_t a[16];
             tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + part * 16, a);
@@ -530,74 +571,129 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
                                   (__uint_as_float(a[2 * i + 1]) + bq[2 * i + 1]) * p.qscale);
             tmem_st_32x32b_x8(tmW + lane_sel + TW_QOP + part * 8, qp);
             if (!p.cross) {
-              uint32_t kk[16], vv[16];
-              tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + 64 + part * 16, kk);
-              tmem_ld_32x32b_x16(tmW + lane_sel + TW_V + part * 16, vv);
+              tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + 64 + part * 16, a);
               tmem_ld_wait();
               const float* bk = vec + VEC_BQKV + D + h * HDIM + part * 16;
-              const float* bv = vec + VEC_BQKV + 2 * D + h * HDIM + part * 16;
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 uint4 w;
-                w.x = pack_bf16x2(__uint_as_float(kk[8 * c]) + bk[8 * c], __uint_as_float(kk[8 * c + 1]) + bk[8 * c + 1]);
-                w.y = pack_bf16x2(__uint_as_float(kk[8 * c + 2]) + bk[8 * c + 2], __uint_as_float(kk[8 * c + 3]) + bk[8 * c + 3]);
-                w.z = pack_bf16x2(__uint_as_float(kk[8 * c + 4]) + bk[8 * c + 4], __uint_as_float(kk[8 * c + 5]) + bk[8 * c + 5]);
-                w.w = pack_bf16x2(__uint_as_float(kk[8 * c + 6]) + bk[8 * c + 6], __uint_as_float(kk[8 * c + 7]) + bk[8 * c + 7]);
+                w.x = pack_bf16x2(__uint_as_float(a[8 * c]) + bk[8 * c], __uint_as_float(a[8 * c + 1]) + bk[8 * c + 1]);
+                w.y = pack_bf16x2(__uint_as_float(a[8 * c + 2]) + bk[8 * c + 2], __uint_as_float(a[8 * c + 3]) + bk[8 * c + 3]);
+                w.z = pack_bf16x2(__uint_as_float(a[8 * c + 4]) + bk[8 * c + 4], __uint_as_float(a[8 * c + 5]) + bk[8 * c + 5]);
+                w.w = pack_bf16x2(__uint_as_float(a[8 * c + 6]) + bk[8 * c + 6], __uint_as_float(a[8 * c + 7]) + bk[8 * c + 7]);
                 *reinterpret_cast<uint4*>(smem + OFF_KT + soff(r, part * 2 + c)) = w;
-                w.x = pack_bf16x2(__uint_as_float(vv[8 * c]) + bv[8 * c], __uint_as_float(vv[8 * c + 1]) + bv[8 * c + 1]);
-                w.y = pack_bf16x2(__uint_as_float(vv[8 * c + 2]) + bv[8 * c + 2], __uint_as_float(vv[8 * c + 3]) + bv[8 * c + 3]);
-                w.z = pack_bf16x2(__uint_as_float(vv[8 * c + 4]) + bv[8 * c + 4], __uint_as_float(vv[8 * c + 5]) + bv[8 * c + 5]);
-                w.w = pack_bf16x2(__uint_as_float(vv[8 * c + 6]) + bv[8 * c + 6], __uint_as_float(vv[8 * c + 7]) + bv[8 * c + 7]);
-                *reinterpret_cast<uint4*>(smem + OFF_VT + soff(r, part * 2 + c)) = w;
               }
               fence_proxy_async_smem();
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(qk_ready);
+            if (lane == 0) mbar_arrive(qop_ready);
           }
-          XTRACE(th + 1);                                    // Q / K / V operands written
-          // ---- softmax over the row's own utterance; P (bf16 pairs) over the first 64 columns of S ----
+          XTRACE(th + 1);                                    // Q operand / K tile written
+          // ---- V_h (bf16) into its shared-memory tile (self-attention; cross-attention gets it by TMA) ----
+          if (!p.cross) {
+            mbar_wait(v_full, n_h & 1);
+            tc_fence_after();
+            uint32_t a[16];
+            tmem_ld_32x32b_x16(tmW + lane_sel + TW_V + part * 16, a);
+            tmem_ld_wait();
+            const float* bv = vec + VEC_BQKV + 2 * D + h * HDIM + part * 16;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(a[8 * c]) + bv[8 * c], __uint_as_float(a[8 * c + 1]) + bv[8 * c + 1]);
+              w.y = pack_bf16x2(__uint_as_float(a[8 * c + 2]) + bv[8 * c + 2], __uint_as_float(a[8 * c + 3]) + bv[8 * c + 3]);
+              w.z = pack_bf16x2(__uint_as_float(a[8 * c + 4]) + bv[8 * c + 4], __uint_as_float(a[8 * c + 5]) + bv[8 * c + 5]);
+              w.w = pack_bf16x2(__uint_as_float(a[8 * c + 6]) + bv[8 * c + 6], __uint_as_float(a[8 * c + 7]) + bv[8 * c + 7]);
+              *reinterpret_cast<uint4*>(smem + OFF_VT + soff(r, part * 2 + c)) = w;
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v_ready);
+          }
+          // ---- softmax over the row's own utterance; P (bf16 pairs) over the first 64 columns of S.  Every part
+          // normalises by its own maximum first; one exchange of (max, sum) then gives the row maximum, the row sum
+          // and the factor 2^(own max - row max) that rescales the part's probabilities ----
           float inv_l;
           mbar_wait(s_full, n_h & 1);
           tc_fence_after();
           XTRACE(th + 2);                                    // S complete
-          {
-            const int c0 = part * 32;
-            const int lo_i = klo - c0, hi_i = khi - c0;      // this row's valid columns of the part: [lo_i, hi_i)
+          if (p.stride == 64) {
+            // two utterance slots of 64 rows: the row's 64 candidate keys split into four 16-column parts, so that all
+            // 16 row warps work (columns klo + 16 part .. +16; valid while < klo + L)
+            const int nval = p.L - part * 16;                // valid columns of this part: [0, nval)
+            uint32_t s[16];
+            tmem_ld_32x32b_x16(tmW + lane_sel + TW_S + klo + part * 16, s);
+            tmem_ld_wait();
+            float e[16];
+            float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              e[i] = (i < nval) ? __uint_as_float(s[i]) : -INFINITY;
+              mx = fmaxf(mx, e[i]);
+            }
+            const float mref = (mx == -INFINITY) ? 0.f : mx;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              e[i] = ex2_approx(e[i] - mref);
+              sum += e[i];
+            }
+            float2 all[4];
+            exchange(make_float2(mx, sum), all);             // every part has read its S columns before this barrier
+            const float m = fmaxf(fmaxf(all[0].x, all[1].x), fmaxf(all[2].x, all[3].x));
+            const float l_row = (all[0].y * ex2_approx(all[0].x - m) + all[1].y * ex2_approx(all[1].x - m)) +
+                                (all[2].y * ex2_approx(all[2].x - m) + all[3].y * ex2_approx(all[3].x - m));
+            inv_l = 1.0f / l_row;
+            const float f = ex2_approx(mx - m);
+            uint32_t pp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pp[i] = pack_bf16x2(e[2 * i] * f, e[2 * i + 1] * f);
+            // P of the OTHER utterance slot's keys is zero for this row: each part clears its share of those 32 packed
+            // columns as well (the P V contraction runs over all 128 keys)
+            const uint32_t zz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st_32x32b_x8(tmW + lane_sel + TW_S + (klo >> 1) + part * 8, pp);
+            tmem_st_32x32b_x8(tmW + lane_sel + TW_S + ((klo ^ 64) >> 1) + part * 8, zz);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+          } else {
             const bool any = __any_sync(0xffffffffu, (lo_i < 32) && (hi_i > 0));
-            uint32_t s[32];
-            float mx = -INFINITY;
+            float e[32];
+            float mx = -INFINITY, sum = 0.f;
             if (any) {
-              tmem_ld_32x32b_x32(tmW + lane_sel + TW_S + c0, s);
+              uint32_t s[32];
+              tmem_ld_32x32b_x32(tmW + lane_sel + TW_S + part * 32, s);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) {                 // masked scores become -inf: exp2 gives exactly 0 below
-                const float x = (i >= lo_i && i < hi_i) ? __uint_as_float(s[i]) : -INFINITY;
-                s[i] = __float_as_uint(x);
-                mx = fmaxf(mx, x);
+                e[i] = (i >= lo_i && i < hi_i) ? __uint_as_float(s[i]) : -INFINITY;
+                mx = fmaxf(mx, e[i]);
+              }
+              const float mref = (mx == -INFINITY) ? 0.f : mx;       // a row with no valid column in this part
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                e[i] = ex2_approx(e[i] - mref);
+                sum += e[i];
               }
             }
             float2 all[4];
-            exchange(make_float2(mx, 0.f), all);
-            const float m = fmaxf(fmaxf(all[0].x, all[1].x), fmaxf(all[2].x, all[3].x));   // finite: klo <= r < khi
-            float sum = 0.f;
+            exchange(make_float2(mx, sum), all);             // every part has read its S columns before this barrier
+            const float m = fmaxf(fmaxf(all[0].x, all[1].x), fmaxf(all[2].x, all[3].x));   // finite: the row has valid keys
+            const float l_row = (all[0].y * ex2_approx(all[0].x - m) + all[1].y * ex2_approx(all[1].x - m)) +
+                                (all[2].y * ex2_approx(all[2].x - m) + all[3].y * ex2_approx(all[3].x - m));
+            inv_l = 1.0f / l_row;
             uint32_t pp[16];
             if (any) {
+              const float f = ex2_approx(mx - m);            // 0 when this part holds no valid column of the row
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float e0 = ex2_approx(__uint_as_float(s[2 * i]) - m);
-                const float e1 = ex2_approx(__uint_as_float(s[2 * i + 1]) - m);
-                sum += e0 + e1;
-                pp[i] = pack_bf16x2(e0, e1);
-              }
+              for (int i = 0; i < 16; ++i) pp[i] = pack_bf16x2(e[2 * i] * f, e[2 * i + 1] * f);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) pp[i] = 0u;
             }
-            exchange(make_float2(sum, 0.f), all);            // every part has read its S columns before this barrier
-            inv_l = 1.0f / ((all[0].x + all[1].x) + (all[2].x + all[3].x));
             tmem_st_32x32b_x16(tmW + lane_sel + TW_S + part * 16, pp);
             tmem_st_wait();
             tc_fence_before();
@@ -690,8 +786,10 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           fence_proxy_async_smem();
           named_bar_sync(6 + part, 128);
           if (elected) {
-            tma_store_2d(&tmXout, smem + OFF_A + (part * 2) * SLAB, part * 64, row0);
-            tma_store_2d(&tmXout, smem + OFF_A + (part * 2 + 1) * SLAB, part * 64 + 32, row0);
+            for (int u = 0; u < p.U; ++u) {
+              tma_store_2d(&tmXout, smem + OFF_A + (part * 2) * SLAB + u * p.stride * 128, part * 64, (utt0 + u) * p.L);
+              tma_store_2d(&tmXout, smem + OFF_A + (part * 2 + 1) * SLAB + u * p.stride * 128, part * 64 + 32, (utt0 + u) * p.L);
+            }
             bulk_commit();
           }
         }
@@ -705,7 +803,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           fence_proxy_async_smem();
           named_bar_sync(6 + part, 128);
           if (elected) {
-            tma_store_2d(&tmOp, smem + OFF_A + part * SLAB, part * 64, row0);
+            for (int u = 0; u < p.U; ++u)
+              tma_store_2d(&tmOp, smem + OFF_A + part * SLAB + u * p.stride * 128, part * 64, (utt0 + u) * p.L);
             bulk_commit();
           }
         }
@@ -782,30 +881,51 @@ void pack_ffn_items(uint8_t* dst, const float* w1, const float* w2) {
 size_t xformer_stream_bytes(bool cross) { return static_cast<size_t>(cross ? ITEMS_CROSS : ITEMS_SELF) * ITEM; }
 int xformer_vec_floats() { return VEC_FLOATS; }
 
+// Stream of one self-attention layer, in the order the kernel consumes it: vector block | Q_0|K_0 (2 items), V_0 | per
+// head h: Q_{h+1}|K_{h+1} (2 items, h < 3), Wo_h, V_{h+1} (h < 3) | FFN items.
 // in_proj_weight [768, 256] (q | k | v rows), out_proj [256, 256], linear1 [1024, 256], linear2 [256, 1024]
-void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, uint8_t* dst) {
+void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, const float* w2, const float* vecs,
+                       uint8_t* dst) {
   memset(dst, 0, xformer_stream_bytes(false));
-  for (int h = 0; h < NH; ++h) {
+  memcpy(dst, vecs, sizeof(float) * VEC_FLOATS);
+  dst += ITEM;
+  auto qk = [&](int h) {
     for (int it = 0; it < 2; ++it, dst += ITEM)
       for (int half = 0; half < 2; ++half) {
         const int col0 = (2 * it + half) * 64;
         put_tile(dst + half * SLAB, wqkv, D, h * HDIM, 64, col0);                    // Q_h rows
         put_tile(dst + half * SLAB + 64 * 128, wqkv, D, D + h * HDIM, 64, col0);     // K_h rows
       }
-    for (int ks = 0; ks < 4; ++ks) put_tile(dst + ks * 8192, wqkv, D, 2 * D + h * HDIM, 64, ks * 64);   // V_h
+  };
+  auto vh = [&](int h) {
+    for (int ks = 0; ks < 4; ++ks) put_tile(dst + ks * 8192, wqkv, D, 2 * D + h * HDIM, 64, ks * 64);
     dst += ITEM;
+  };
+  qk(0);
+  vh(0);
+  for (int h = 0; h < NH; ++h) {
+    if (h + 1 < NH) qk(h + 1);
     for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, wo, D, hf * 128, 128, h * HDIM);
     dst += ITEM;
+    if (h + 1 < NH) vh(h + 1);
   }
   pack_ffn_items(dst, w1, w2);
 }
 
+// Cross-attention layer: vector block | Q_0 | per head h: Q_{h+1} (h < 3), Wo_h | FFN items.
 // wq = rows [0, 256) of the packed in_proj_weight of nn.MultiheadAttention (model.py:155; functional.py:5847-5865)
-void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, uint8_t* dst) {
+void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, const float* vecs,
+                        uint8_t* dst) {
   memset(dst, 0, xformer_stream_bytes(true));
-  for (int h = 0; h < NH; ++h) {
+  memcpy(dst, vecs, sizeof(float) * VEC_FLOATS);
+  dst += ITEM;
+  auto qh = [&](int h) {
     for (int ks = 0; ks < 4; ++ks) put_tile(dst + ks * 8192, wq, D, h * HDIM, 64, ks * 64);
     dst += ITEM;
+  };
+  qh(0);
+  for (int h = 0; h < NH; ++h) {
+    if (h + 1 < NH) qh(h + 1);
     for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, wo, D, hf * 128, 128, h * HDIM);
     dst += ITEM;
   }
@@ -842,24 +962,26 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
       return "xformer_stack: cudaFuncSetAttribute failed";
     g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  const int U = 128 / sp.L, rows = U * sp.L;
+  int U = 1;                                   // utterances per tile: the largest power of two with U * L <= 128
+  while (U < 16 && 2 * U * sp.L <= 128) U *= 2;
+  const int stride = 128 / U;
   const int M = sp.B * sp.L;
   const int n_tiles = (sp.B + U - 1) / U;
   CUtensorMap tin, tout, top, tkv;
-  if (const char* e = enc2d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.x_in, D, M, D, 32, rows)) return e;
+  if (const char* e = enc2d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.x_in, D, M, D, 32, sp.L)) return e;
   tout = tin; top = tin; tkv = tin;
   if (sp.out_x)
-    if (const char* e = enc2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.out_x, D, M, D, 32, rows)) return e;
+    if (const char* e = enc2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.out_x, D, M, D, 32, sp.L)) return e;
   if (sp.out_op)
-    if (const char* e = enc2d(&top, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.out_op, D, M, D, 64, rows)) return e;
+    if (const char* e = enc2d(&top, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.out_op, D, M, D, 64, sp.L)) return e;
   if (sp.cross) {
     if (sp.kv == nullptr || sp.kv_ld < sp.n_layers * 2 * D) return "xformer_stack: cross-attention needs the K|V rows";
-    if (const char* e = enc2d(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.kv, sp.kv_ld, M, sp.kv_ld, 64, rows)) return e;
+    if (const char* e = enc2d(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.kv, sp.kv_ld, M, sp.kv_ld, 64, sp.L)) return e;
   }
   StackDev d{};
-  d.wstream = sp.wstream; d.vecs = sp.vecs; d.fin_gamma = sp.fin_gamma; d.fin_beta = sp.fin_beta;
+  d.wstream = sp.wstream; d.fin_gamma = sp.fin_gamma; d.fin_beta = sp.fin_beta;
   d.n_layers = sp.n_layers; d.items_per_layer = sp.cross ? ITEMS_CROSS : ITEMS_SELF; d.cross = sp.cross ? 1 : 0;
-  d.L = sp.L; d.rows = rows; d.M = M; d.n_tiles = n_tiles;
+  d.L = sp.L; d.U = U; d.stride = stride; d.B = sp.B; d.n_tiles = n_tiles;
   d.act = sp.act; d.out_x = sp.out_x != nullptr; d.out_op = sp.out_op != nullptr;
   d.kv_ld_layer = 2 * D;
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)

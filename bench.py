@@ -478,8 +478,9 @@ def run_ours(args, rank, local_rank, world):
     # ---- python_api: the drop-in module call `model(mixed, frames)` (what a user of the reference writes) -------------
     def python_api_ms(bsz, steps):
         ms_in = [(m[:bsz].contiguous(), f[:bsz].contiguous()) for m, f in sets]
-        for i in range(6):
-            model(*ms_in[i % n_sets])
+        keep = None
+        for i in range(36):        # every (input set, output block) pair is seen often enough to be graph-captured
+            keep = model(*ms_in[i % n_sets])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)

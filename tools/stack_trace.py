@@ -33,7 +33,9 @@ def main():
     x = torch.randn(B * L, d, device="cuda")
     kv = torch.randn(B * L, 1024, device="cuda").to(torch.bfloat16) if args.which == 2 else None
     out = torch.empty(B * L, d, device="cuda", dtype=torch.bfloat16)
-    U = 128 // L
+    U = 1
+    while U < 16 and 2 * U * L <= 128:
+        U *= 2
     grid = min(148, (B + U - 1) // U)
     trace = torch.zeros(grid * 256, device="cuda", dtype=torch.int64)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -75,7 +77,7 @@ def main():
         rl += [(tb, f"L{l} LN1 start"), (tb + 1, f"L{l} LN1 done")]
         for h in range(4):
             th = tb + 2 + h * 6
-            rl += [(th, f"L{l} h{h} QKV acc complete"), (th + 1, f"L{l} h{h} Q/K/V operands"), (th + 2, f"L{l} h{h} S complete"),
+            rl += [(th, f"L{l} h{h} Q|K acc complete"), (th + 1, f"L{l} h{h} Q op / K tile"), (th + 2, f"L{l} h{h} S complete"),
                    (th + 3, f"L{l} h{h} P written"), (th + 4, f"L{l} h{h} O complete"), (th + 5, f"L{l} h{h} O operand")]
         rl += [(tb + 26, f"L{l} attention complete"), (tb + 27, f"L{l} LN2 done")]
         for j in range(8):
@@ -85,7 +87,7 @@ def main():
         ml += [(mb, f"L{l} LN1 seen")]
         for h in range(4):
             th = mb + 1 + h * 6
-            ml += [(th, f"L{l} h{h} QKV issued"), (th + 1, f"L{l} h{h} qk_ready seen"), (th + 2, f"L{l} h{h} p_ready seen"),
+            ml += [(th, f"L{l} h{h} Q op / K tile seen"), (th + 1, f"L{l} h{h} S (+V) issued"), (th + 2, f"L{l} h{h} P and V seen"),
                    (th + 3, f"L{l} h{h} o_ready seen")]
         ml += [(mb + 25, f"L{l} attention issued"), (mb + 26, f"L{l} LN2 seen")]
         for j in range(8):
