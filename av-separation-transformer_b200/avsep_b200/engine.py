@@ -190,8 +190,10 @@ class Engine:
         B, T, N, Hh, Ww = self._check_inputs("forward", mixed=mixed, frames=frames, out=out)
         F, S = self.cfg.freq_bins, self.cfg.num_speakers
         if out is None:
-            sep = torch.empty((B, S, F, T), device=mixed.device, dtype=torch.float32)
-            masks = torch.empty_like(sep)
+            # one allocation for both outputs: the caching allocator then recycles a handful of blocks, so the
+            # (inputs, outputs) pointer sets the library's CUDA-graph cache is keyed on repeat after a few calls
+            both = torch.empty((2, B, S, F, T), device=mixed.device, dtype=torch.float32)
+            sep, masks = both[0], both[1]
         else:
             sep, masks = out
             for t in out:

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -125,7 +126,10 @@ struct avsep_handle {
   const float *pe_a = nullptr, *pe_v = nullptr, *fng = nullptr, *fnb = nullptr;
   CnnWeights cnn{};
   const uint8_t *cnn_w2_slabs = nullptr, *cnn_w3_rows = nullptr;   // tcgen05 CNN operands
+  const uint8_t* cnn_w3_img = nullptr;                             // conv3 weights as shared-memory images (cnn_ig)
   bool cnn_tc = true;     // tensor-core (tcgen05) CNN for 32x32 frames on the bf16 path
+  bool cnn_ig = false;    // ... as shifted-view implicit GEMMs (visual_cnn_ig_sm100.cu; parity-tested, 157 us L2-warm but
+                          // 192 us inside the step against 185 us for the TMEM-im2col kernel: off by default)
   std::vector<EncLayerW> enc_a, enc_v;
   std::vector<FusLayerW> fus;
   // prepacked weight streams / vector blocks of the fused transformer-stack kernel (null when the config cannot use it)
@@ -301,8 +305,12 @@ int snapshot(avsep_handle* h, cudaStream_t s, const char* name, const void* ptr,
 // ---- stage helpers -----------------------------------------------------------------------------
 const char* run_visual_cnn(avsep_handle* h, cudaStream_t s, const float* frames, int M, int Hh, int Ww, void* pooled,
                            unsigned long long* trace = nullptr) {
-  if (h->cnn_tc && Hh == 32 && Ww == 32 && h->cfg.precision == AVSEP_PREC_BF16)
+  if (h->cnn_tc && Hh == 32 && Ww == 32 && h->cfg.precision == AVSEP_PREC_BF16) {
+    if (h->cnn_ig)       // (its trace is clock64 stamps: [grid][64] long long, see tools/cnn_trace.py --ig)
+      return launch_visual_cnn_ig(s, frames, M, h->cnn, h->cnn_w2_slabs, h->cnn_w3_img, pooled, h->num_sms,
+                                  reinterpret_cast<long long*>(trace));
     return launch_visual_cnn_tc(s, frames, M, h->cnn, h->cnn_w2_slabs, h->cnn_w3_rows, pooled, h->num_sms, trace);
+  }
   return launch_visual_cnn(s, h->cfg.precision, frames, M, Hh, Ww, h->cnn, pooled, h->num_sms);
 }
 
@@ -613,7 +621,7 @@ int forward_cached(avsep_handle* h, cudaStream_t s, Workspace& w, const void* ws
   for (auto& g : h->graphs)
     if (g.key == key) { ent = &g; break; }
   if (ent == nullptr) {
-    if (h->graphs.size() >= 16) {          // evict the least recently used entry
+    if (h->graphs.size() >= 64) {          // evict the least recently used entry
       size_t victim = 0;
       for (size_t i = 1; i < h->graphs.size(); ++i)
         if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
@@ -727,6 +735,7 @@ int avsep_create(const avsep_config* cfg, avsep_handle** out) {
   h->cfg = *cfg;
   h->Fp = (cfg->freq_bins + 7) / 8 * 8;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("AVSEP_CNN_IG")) h->cnn_ig = atoi(e) != 0;      // A/B switch for measurements
   *out = h;
   return 0;
 }
@@ -883,6 +892,9 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     visual_cnn_tc_pack(folded[1].data(), folded[2].data(), tc2.data(), tc3.data());
     off["tcw2"] = ar.add(tc2.data(), tc2.size());
     off["tcw3"] = ar.add(tc3.data(), tc3.size());
+    std::vector<uint8_t> ig3(visual_cnn_ig_w3_bytes());
+    visual_cnn_ig_pack(folded[2].data(), ig3.data());
+    off["igw3"] = ar.add(ig3.data(), ig3.size());
     off["cw1"] = ar.add(p1.data(), p1.size() * 4);
     off["cw2"] = ar.add(p2.data(), p2.size() * 4);
     off["cw3"] = ar.add(p3.data(), p3.size() * 4);
@@ -1025,6 +1037,7 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->cnn.w3l = reinterpret_cast<const uint32_t*>(P("cw3l"));
   h->cnn_w2_slabs = static_cast<const uint8_t*>(P("tcw2"));
   h->cnn_w3_rows = static_cast<const uint8_t*>(P("tcw3"));
+  h->cnn_w3_img = static_cast<const uint8_t*>(P("igw3"));
   h->xs_a = h->xs_v = h->xs_f = nullptr;
   if (pack_stacks) {
     h->xs_a = static_cast<const uint8_t*>(P("xs_a")); h->xs_v = static_cast<const uint8_t*>(P("xs_v"));
@@ -1579,6 +1592,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "ffn_cg2") == 0) { h->ffn_cg2 = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "pdl") == 0) { h->pdl = value != 0; pdl_set(h->pdl && !h->profile); drop_graphs(h); return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "cnn_ig") == 0) { h->cnn_ig = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_stack") == 0) { h->fuse_stack = value != 0; drop_graphs(h); return 0; }

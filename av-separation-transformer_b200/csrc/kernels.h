@@ -165,6 +165,11 @@ void visual_cnn_tc_pack(const float* w2, const float* w3, uint8_t* w2_slabs, uin
 const char* launch_visual_cnn_tc(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
                                  const uint8_t* w3_rows, void* pooled, int num_sms,
                                  unsigned long long* trace = nullptr);
+// shifted-view implicit GEMM variant (visual_cnn_ig_sm100.cu): no im2col gather; conv3 weights as pre-swizzled images
+size_t visual_cnn_ig_w3_bytes();
+void visual_cnn_ig_pack(const float* w3, uint8_t* w3_img);
+const char* launch_visual_cnn_ig(cudaStream_t s, const float* frames, int M, const CnnWeights& w, const uint8_t* w2_slabs,
+                                 const uint8_t* w3_img, void* pooled, int num_sms, long long* trace = nullptr);
 size_t visual_cnn_pack_sizes(int which);   // elements of packed w1/w2/w3 (uint32)
 void visual_cnn_pack(const float* w1, const float* w2, const float* w3, uint32_t* p1, uint32_t* p2, uint32_t* p3,
                      bool lo_part = false);
