@@ -134,6 +134,8 @@ struct avsep_handle {
   std::vector<FusLayerW> fus;
   // prepacked weight streams / vector blocks of the fused transformer-stack kernel (null when the config cannot use it)
   const uint8_t *xs_a = nullptr, *xs_v = nullptr, *xs_f = nullptr;
+  bool xs_f_decoder = false;   // the fusion stream continues with the SeparationDecoder block
+  bool fuse_decoder = true;    // run the decoder inside the fusion stack kernel (option "fuse_decoder")
   bool fuse_stack = true;   // whole encoder / fusion stacks in one persistent kernel (d_model = 256, 4 heads, bf16, len <= 128)
   // cached library-owned workspace
   void* own_ws = nullptr;
@@ -375,9 +377,11 @@ bool stack_fusable(const avsep_handle* h, int len) {
 
 // A whole stack in one kernel (xformer_stack_sm100.cu).  which: 0 audio encoder, 1 visual encoder, 2 fusion.
 int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, float* out_x, void* out_op,
-              const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L, long long* trace = nullptr) {
+              const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L, long long* trace = nullptr,
+              const float* mixed = nullptr, float* separated = nullptr, float* masks = nullptr) {
   StackProblem sp{};
   sp.trace = trace;
+  sp.mixed = mixed; sp.separated = separated; sp.masks = masks; sp.F = h->cfg.freq_bins; sp.S = h->cfg.num_speakers;
   sp.x_in = x_in; sp.out_x = out_x; sp.out_op = out_op; sp.fin_gamma = fin_g; sp.fin_beta = fin_b;
   sp.wstream = which == 0 ? h->xs_a : which == 1 ? h->xs_v : h->xs_f;
   sp.n_layers = which == 2 ? h->cfg.num_fusion_layers : h->cfg.num_encoder_layers;
@@ -385,7 +389,8 @@ int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, flo
   sp.kv = kv; sp.kv_ld = kv_ld;
   sp.B = B; sp.L = L;
   sp.act = which == 2 ? ACT_GELU : ACT_RELU;
-  CKL(which == 0 ? "layer.audio_enc" : which == 1 ? "layer.visual_enc" : "layer.fusion", launch_xformer_stack(s, sp, h->num_sms));
+  CKL(which == 0 ? "layer.audio_enc" : which == 1 ? "layer.visual_enc" : masks ? "layer.fusion_decoder" : "layer.fusion",
+      launch_xformer_stack(s, sp, h->num_sms));
   return 0;
 }
 
@@ -485,12 +490,17 @@ int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* 
 // reference does it (model.py:114-116, before the K/V projection), the K|V rows of every fusion layer come from one GEMM
 // on those T rows (bf16), and the whole fusion stack runs in one kernel.  In: x_a (fp32 residual), x_v (fp32 visual
 // encoder output, L_src rows per utterance).  Out: a_op = fusion.norm(x) in bf16.
-int fusion_stack_fused(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
+// with_decoder (out: *decoded = true): SeparationDecoder runs inside the same kernel and writes separated / masks.
+int fusion_stack_fused(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src, const float* mixed, float* separated,
+                       float* masks, bool* decoded) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, T = w.T;
   const int Ma = B * T, Lf = h->cfg.num_fusion_layers;
   CKL("lerp_kv", launch_lerp_rows(s, w.x_v, d, B, L_src, T, d, w.attn_a, d));
   if (linear(h, s, "gemm.cross_kv", w.attn_a, Ma, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, nullptr, w.kvb)) return 1;
+  *decoded = h->fuse_decoder && h->xs_f_decoder && !h->debug && masks != nullptr;
+  if (*decoded)
+    return run_stack(h, s, 2, w.x_a, nullptr, nullptr, h->fng, h->fnb, w.kvb, Lf * 2 * d, B, T, nullptr, mixed, separated, masks);
   if (run_stack(h, s, 2, w.x_a, h->debug ? w.x_a : nullptr, w.a_op, h->fng, h->fnb, w.kvb, Lf * 2 * d, B, T)) return 1;
   return snapshot(h, s, "fused", w.a_op, static_cast<size_t>(Ma) * d, true);
 }
@@ -604,7 +614,9 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   }
   // --- fusion + decoder ---
   if (ff) {
-    if (fusion_stack_fused(h, s, w, w.N)) return 1;
+    bool decoded = false;
+    if (fusion_stack_fused(h, s, w, w.N, mixed, separated, masks, &decoded)) return 1;
+    if (decoded) return 0;
   } else if (fusion_stack(h, s, w, w.N)) {
     return 1;
   }
@@ -735,8 +747,21 @@ int avsep_create(const avsep_config* cfg, avsep_handle** out) {
   h->cfg = *cfg;
   h->Fp = (cfg->freq_bins + 7) / 8 * 8;
   h->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("AVSEP_CNN_IG")) h->cnn_ig = atoi(e) != 0;      // A/B switch for measurements
   *out = h;
+  // A/B switches for measurement runs: AVSEP_OPTS="name=value,name=value" goes through avsep_set_option
+  if (const char* e = getenv("AVSEP_OPTS")) {
+    std::string opts(e);
+    size_t pos = 0;
+    while (pos < opts.size()) {
+      size_t end = opts.find(',', pos);
+      if (end == std::string::npos) end = opts.size();
+      const std::string kv = opts.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos && avsep_set_option(h, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)) != 0)
+        fprintf(stderr, "avsep: AVSEP_OPTS: option '%s' not accepted\n", kv.c_str());
+      pos = end + 1;
+    }
+  }
   return 0;
 }
 
@@ -990,7 +1015,9 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       }
       off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
     }
-    std::vector<uint8_t> stream(static_cast<size_t>(Lf) * xformer_stream_bytes(true));
+    const bool fuse_dec = 512 + (S * F + 127) / 128 * 128 <= xformer_vec_floats();
+    std::vector<uint8_t> stream(static_cast<size_t>(Lf) * xformer_stream_bytes(true) +
+                                (fuse_dec ? xformer_decoder_bytes(static_cast<int>(S * F)) : 0));
     std::vector<float> vecs(vf);
     for (int l = 0; l < Lf; ++l) {
       const std::string p = "fusion.layers." + std::to_string(l);
@@ -1011,6 +1038,15 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       xformer_pack_cross(win->data.data(), wo->data.data(), w1->data.data(), w2->data.data(), vecs.data(),
                          stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(true));
     }
+    if (fuse_dec) {
+      GETW(w0, "decoder.decoder.0.weight", 2 * d, d);
+      GETW(b0, "decoder.decoder.0.bias", 2 * d);
+      GETW(w3, "decoder.decoder.3.weight", S * F, 2 * d);
+      GETW(b3, "decoder.decoder.3.bias", S * F);
+      xformer_pack_decoder(w0->data.data(), b0->data.data(), w3->data.data(), b3->data.data(), static_cast<int>(S * F),
+                           stream.data() + static_cast<size_t>(Lf) * xformer_stream_bytes(true));
+    }
+    h->xs_f_decoder = fuse_dec;
     off["xs_f"] = ar.add(stream.data(), stream.size());
   }
 #undef GETW
@@ -1596,6 +1632,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "use_graph") == 0) { h->use_graph = value != 0; return 0; }
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_stack") == 0) { h->fuse_stack = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "fuse_decoder") == 0) { h->fuse_decoder = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "attn_small") == 0) { attention_set_small(value != 0); drop_graphs(h); return 0; }

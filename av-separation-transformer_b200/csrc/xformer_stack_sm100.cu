@@ -72,6 +72,11 @@ struct StackDev {
   int out_x, out_op;
   int kv_ld_layer;              // cross: column offset between layers in the K|V matrix (2 * D)
   float qscale;
+  // SeparationDecoder fused behind the last layer (model.py:201-220): Linear(256 -> 512) + GELU, Linear(512 -> S*F),
+  // sigmoid, x mixed_spec, (B,S,F,T) stores.  decoder != 0: the stream holds 1 + 8 + 4 * nc3 more items per tile.
+  int decoder, nc3, SF, F;
+  const float* mixed;
+  float *masks, *separated;
   long long* trace;             // optional [grid][256] clock64 stamps of the CTA's first tile (debug), else null:
                                 //   row thread (warp 2 lane 0) in [0,128), MMA thread in [128,256); see tools/stack_trace.py
 };
@@ -231,6 +236,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             src += 8 * ITEM;
           }
           for (int i = 0; i < 32; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
+        }
+        if (p.decoder) {
+          const uint8_t* src = p.wstream + static_cast<size_t>(p.n_layers) * p.items_per_layer * ITEM;
+          const int n = 1 + 8 + 4 * p.nc3;
+          for (int i = 0; i < n; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
         }
       }
     }
@@ -403,6 +413,57 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           }
           umma_commit(ffn_done);
         }
+        if (p.decoder) {
+          auto wait_h = [&]() {                    // hidden / output chunk c2n has left its accumulator stage
+            const uint32_t st2 = c2n & 1;
+            mbar_wait(&h_full[st2], (c2n >> 1) & 1);
+            tc_fence_after();
+            ++c2n;
+          };
+          ++wn;                                     // decoder vector block (row warps)
+          mbar_wait(a_ready, n_a & 1); ++n_a;       // a = fusion.norm(x) in shared memory
+          tc_fence_after();
+          // Linear(256 -> 512): four 128-wide chunks, A = a (smem); GELU'd H goes to tensor memory over X (dead now)
+          for (int j = 0; j < 4; ++j, ++c1n) {
+            const uint32_t st = c1n & 1;
+            if (j >= 2) wait_h();
+            for (int it = 0; it < 2; ++it) {
+              const uint32_t base = next_item();
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int ks = 2 * it + half;
+                const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmW + st * 128, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[cur_slot]);
+            }
+            umma_commit(&acc1_full[st]);
+          }
+          wait_h();
+          wait_h();
+          // Linear(512 -> S*F): chunks of 128 output columns, A = H from tensor memory (K = 512), B streamed
+          for (int c = 0; c < p.nc3; ++c, ++c1n) {
+            const uint32_t st = c1n & 1;
+            if (c >= 2) wait_h();
+            for (int it = 0; it < 4; ++it) {
+              const uint32_t base = next_item();
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16_ts(tmW + st * 128, tmX + ((2 * it + half) * 4 + kk) * 8, bdesc + 2 * kk, ID128,
+                              (it | half | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[cur_slot]);
+            }
+            umma_commit(&acc1_full[st]);
+          }
+          for (int c = p.nc3 < 2 ? 0 : p.nc3 - 2; c < p.nc3; ++c) wait_h();
+        }
       }
     }
   } else {
@@ -418,7 +479,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     // this row's valid score columns within the part: [lo_i, hi_i)
     const int lo_i = klo - part * 32, hi_i = klo + p.L - part * 32;
     uint32_t nx = 0;                                         // exchanges through `red` so far (double buffered)
-    uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0, n_layer = 0;
+    uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0;
     const int trace_base = (threadIdx.x == 64) ? 0 : 1024;   // only the first row thread stamps
 
     auto exchange = [&](float2 mine, float2 (&all)[4]) {
@@ -530,10 +591,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(x_taken);
       }
-      for (int l = 0; l < p.n_layers; ++l, ++n_layer) {
+      for (int l = 0; l < p.n_layers; ++l) {
         // ---- per-layer vectors: first item of the layer in the weight stream (it was prefetched under the previous
         // layer's FFN); the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
-        const uint32_t vn = n_layer * static_cast<uint32_t>(p.items_per_layer);
+        const uint32_t per_tile = static_cast<uint32_t>(p.n_layers * p.items_per_layer + (p.decoder ? 1 + 8 + 4 * p.nc3 : 0));
+        const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(l * p.items_per_layer);
         const uint32_t vslot = vn % NSLOT;
         named_bar_sync(5, 512);                              // every row warp is done with the previous vectors
         if (l > 0 && etid < D) pend[etid] = vec[VEC_B2 + etid];
@@ -768,6 +830,86 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         tc_fence_after();
         XTRACE(tb + 44);                                     // FFN complete
       }
+      if (p.decoder) {
+        // ---- SeparationDecoder on the tile (model.py:201-220): a = fusion.norm(x) -> H = GELU(a W0^T + b0) kept in tensor
+        // memory over X -> masks = sigmoid(H W3^T + b3), separated = masks * mixed_spec, stored along T ----
+        ln_to_a(vec + VEC_B2, fin_g, fin_b);
+        // decoder vector block (b0 [512] | b3 [nc3 * 128]): next item of the weight stream
+        {
+          const uint32_t per_tile = static_cast<uint32_t>(p.n_layers * p.items_per_layer + 1 + 8 + 4 * p.nc3);
+          const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(p.n_layers * p.items_per_layer);
+          const uint32_t vslot = vn % NSLOT;
+          named_bar_sync(5, 512);                            // every row warp has read the last layer's vectors
+          mbar_wait(&w_full[vslot], (vn / NSLOT) & 1);
+          const float4* src = reinterpret_cast<const float4*>(smem + OFF_RING + vslot * ITEM);
+          float4* dst = reinterpret_cast<float4*>(vec);
+          for (int i = etid; i < (512 + p.nc3 * 128) / 4; i += 512) dst[i] = src[i];
+          named_bar_sync(5, 512);
+          if (etid == 0) mbar_arrive(&w_empty[vslot]);
+        }
+        // hidden chunks: bias + GELU -> bf16 pairs into X[64 j + 16 part, +16)
+        for (int j = 0; j < 4; ++j, ++c1n) {
+          const uint32_t st = c1n & 1;
+          mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
+          tc_fence_after();
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
+          tmem_ld_wait();
+          uint32_t hp[16];
+          const float* bj = vec + j * 128 + part * 32;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            hp[i] = pack_bf16x2(gelu_bf16_grade(__uint_as_float(v[2 * i]) + bj[2 * i]),
+                                gelu_bf16_grade(__uint_as_float(v[2 * i + 1]) + bj[2 * i + 1]));
+          tmem_st_32x32b_x16(tmX + lane_sel + j * 64 + part * 16, hp);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_full[st]);
+        }
+        // output chunks: 128 columns (s, f) each; this thread: row = (utterance, t), 32 columns
+        const int utt = utt0 + r / p.stride, t = r - klo;
+        const bool out_ok = row_valid && utt < p.B;
+        const size_t obase = static_cast<size_t>(utt) * p.SF * p.L + t;
+        const float* mrow = p.mixed + static_cast<size_t>(utt) * p.F * p.L + t;
+        for (int c = 0; c < p.nc3; ++c, ++c1n) {
+          const uint32_t st = c1n & 1;
+          const int col0 = c * 128 + part * 32;
+          // the mixture values of this thread's columns first (their latency hides behind the accumulator wait)
+          float mx[32];
+          {
+            int f = col0 % p.F;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mx[i] = (out_ok && col0 + i < p.SF) ? __ldg(mrow + static_cast<size_t>(f) * p.L) : 0.f;
+              if (++f == p.F) f = 0;
+            }
+          }
+          mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
+          tc_fence_after();
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_full[st]);           // the accumulator stage is drained (values in registers)
+          if (out_ok) {
+            const float* b3 = vec + 512 + col0;
+            float* mo = p.masks + obase + static_cast<size_t>(col0) * p.L;
+            float* so = p.separated + obase + static_cast<size_t>(col0) * p.L;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (col0 + i < p.SF) {
+                const float mk = sigmoid_fast(__uint_as_float(v[i]) + b3[i]);
+                __stcs(mo + static_cast<size_t>(i) * p.L, mk);
+                __stcs(so + static_cast<size_t>(i) * p.L, mk * mx[i]);
+              }
+            }
+          }
+        }
+        named_bar_sync(5, 512);
+        if (elected) mbar_arrive(stage_free);
+      } else
       // ---- stack output: x + last linear2 bias -> fp32 residual rows and / or (final LayerNorm | cast) bf16 rows ----
       {
         uint32_t vu[64];
@@ -945,13 +1087,39 @@ void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const flo
   memcpy(dst + VEC_N2B, n2b, sizeof(float) * D);
 }
 
+// SeparationDecoder block of the fusion stream (after the last layer): vector block (b0 [512] | b3 padded to nc3 * 128),
+// Linear(256 -> 512) as 8 items (chunk j, k-slab pair), Linear(512 -> S*F) as 4 items per 128-column chunk
+size_t xformer_decoder_bytes(int SF) { return static_cast<size_t>(1 + 8 + 4 * ((SF + 127) / 128)) * ITEM; }
+void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int SF, uint8_t* dst) {
+  const int nc3 = (SF + 127) / 128;
+  memset(dst, 0, xformer_decoder_bytes(SF));
+  float* v = reinterpret_cast<float*>(dst);
+  memcpy(v, b0, sizeof(float) * 512);
+  memcpy(v + 512, b3, sizeof(float) * SF);
+  dst += ITEM;
+  for (int j = 0; j < 4; ++j)
+    for (int it = 0; it < 2; ++it, dst += ITEM)
+      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, w0, D, j * 128, 128, (2 * it + half) * 64);
+  for (int c = 0; c < nc3; ++c) {
+    const int nrows = SF - c * 128 < 128 ? SF - c * 128 : 128;
+    for (int it = 0; it < 4; ++it, dst += ITEM)
+      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, w3, 2 * D, c * 128, nrows, (2 * it + half) * 64);
+  }
+}
+
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len) {
   return prec == PREC_BF16 && d_model == D && nhead == NH && len >= 1 && len <= 128;
 }
 
 const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num_sms) {
   if (sp.B <= 0 || sp.L <= 0 || sp.L > 128 || sp.n_layers <= 0) return "xformer_stack: bad problem";
-  if (!sp.out_x && !sp.out_op) return "xformer_stack: no output requested";
+  const bool decoder = sp.masks != nullptr;
+  if (!sp.out_x && !sp.out_op && !decoder) return "xformer_stack: no output requested";
+  if (decoder) {
+    if (!sp.cross || sp.out_x || sp.out_op || !sp.mixed || !sp.separated || sp.F < 1 || sp.S < 1)
+      return "xformer_stack: the fused decoder follows the fusion stack and replaces its outputs";
+    if (512 + (sp.S * sp.F + 127) / 128 * 128 > VEC_FLOATS) return "xformer_stack: S * freq_bins too large for the fused decoder";
+  }
   if (g_enc == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -986,6 +1154,9 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   d.kv_ld_layer = 2 * D;
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
   d.trace = sp.trace;
+  d.decoder = decoder ? 1 : 0;
+  d.SF = sp.S * sp.F; d.F = sp.F; d.nc3 = (d.SF + 127) / 128;
+  d.mixed = sp.mixed; d.masks = sp.masks; d.separated = sp.separated;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   if (launch_pdl(xformer_stack_kernel, dim3(grid), dim3(STACK_THREADS), STACK_SMEM, s, tin, tout, top, tkv, d) !=
       cudaSuccess) {
