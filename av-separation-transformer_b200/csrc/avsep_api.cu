@@ -1015,9 +1015,9 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       }
       off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
     }
-    const bool fuse_dec = 512 + (S * F + 127) / 128 * 128 <= xformer_vec_floats();
+    const bool fuse_dec = xformer_decoder_usable(static_cast<int>(S), static_cast<int>(F));
     std::vector<uint8_t> stream(static_cast<size_t>(Lf) * xformer_stream_bytes(true) +
-                                (fuse_dec ? xformer_decoder_bytes(static_cast<int>(S * F)) : 0));
+                                (fuse_dec ? xformer_decoder_bytes(static_cast<int>(S), static_cast<int>(F)) : 0));
     std::vector<float> vecs(vf);
     for (int l = 0; l < Lf; ++l) {
       const std::string p = "fusion.layers." + std::to_string(l);
@@ -1043,7 +1043,7 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       GETW(b0, "decoder.decoder.0.bias", 2 * d);
       GETW(w3, "decoder.decoder.3.weight", S * F, 2 * d);
       GETW(b3, "decoder.decoder.3.bias", S * F);
-      xformer_pack_decoder(w0->data.data(), b0->data.data(), w3->data.data(), b3->data.data(), static_cast<int>(S * F),
+      xformer_pack_decoder(w0->data.data(), b0->data.data(), w3->data.data(), b3->data.data(), static_cast<int>(S), static_cast<int>(F),
                            stream.data() + static_cast<size_t>(Lf) * xformer_stream_bytes(true));
     }
     h->xs_f_decoder = fuse_dec;
@@ -1618,6 +1618,18 @@ int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const float* x_in, 
   h->prof_stream = static_cast<cudaStream_t>(cuda_stream);
   return run_stack(h, static_cast<cudaStream_t>(cuda_stream), which, x_in, out_x, out_op, g, b, kv,
                    h->cfg.num_fusion_layers * 2 * h->cfg.d_model, B, L, trace_dev);
+}
+
+int avsep_test_fusion_decoder(avsep_handle* h, const float* x_in, const void* kv, int32_t B, int32_t L, const float* mixed,
+                              float* separated, float* masks, long long* trace_dev, void* cuda_stream) {
+  if (!h) return 1;
+  if (!h->finalized) return fail(h, "weights not finalized");
+  if (h->xs_f == nullptr || !h->xs_f_decoder || !xformer_stack_usable(h->cfg.precision, h->cfg.d_model, h->cfg.nhead, L))
+    return fail(h, "test_fusion_decoder: the fused stack kernel does not support this configuration");
+  if (!mixed || !separated || !masks) return fail(h, "test_fusion_decoder: null buffer");
+  h->prof_stream = static_cast<cudaStream_t>(cuda_stream);
+  return run_stack(h, static_cast<cudaStream_t>(cuda_stream), 2, x_in, nullptr, nullptr, h->fng, h->fnb, kv,
+                   h->cfg.num_fusion_layers * 2 * h->cfg.d_model, B, L, trace_dev, mixed, separated, masks);
 }
 
 int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {

@@ -75,6 +75,12 @@ __device__ __forceinline__ float gelu_bf16_grade(float x) {
   return fmaf(hx, xc * p, hx);
 }
 
+// Warpgroup-level register reallocation (all four warps of an aligned warpgroup execute the same instruction).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // fp32 -> TF32 with round-to-nearest (the tensor core would otherwise truncate the low 13 mantissa bits, which

@@ -110,13 +110,15 @@ struct StackProblem {
   int act;
   long long* trace = nullptr;   // optional [grid][256] clock64 stamps (debug)
   // SeparationDecoder fused behind the fusion stack (cross only; replaces out_x / out_op): the stream then continues with
-  // xformer_decoder_bytes(S * F) of decoder items (xformer_pack_decoder)
+  // xformer_decoder_bytes(S, F) of decoder items (xformer_pack_decoder)
   const float* mixed = nullptr;          // (B, F, L) fp32
   float *masks = nullptr, *separated = nullptr;   // (B, S, F, L) fp32
   int F = 0, S = 0;
 };
-size_t xformer_decoder_bytes(int SF);
-void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int SF, uint8_t* dst);
+bool xformer_decoder_usable(int S, int F);
+int xformer_decoder_chunks(int S, int F);
+size_t xformer_decoder_bytes(int S, int F);
+void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int S, int F, uint8_t* dst);
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
 size_t xformer_stream_bytes(bool cross);
 int xformer_vec_floats();

@@ -15,6 +15,9 @@
 //
 // Roles (18 warps): warp 0 lane 0 streams weights (3-slot ring) and the x / K / V tiles; warp 1 lane 0 issues every
 // tcgen05.mma; warps 2..17 are "row" warps: thread = (tile row r = TMEM lane, column part p of 4).
+// 18 warps cap every thread at 96 registers, and with the shared-memory carve-out this kernel needs L1 has no room
+// for spilled registers (every spill is an L2 round trip): hot loops are written to stay inside the cap.  (setmaxnreg
+// with a 20-warp layout was tried: ptxas then spills several times more in the row-warp code.)
 //
 // Tensor memory map (columns): X [0,256) residual | W [256,512) work area:
 //   attention, per head h:  W[0,128)  Q_h|K_h accumulator -> S = Q K^T -> P (bf16 pairs, first 64 columns)
@@ -32,8 +35,10 @@
 #include "kernels.h"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 namespace avsep {
@@ -74,7 +79,7 @@ struct StackDev {
   float qscale;
   // SeparationDecoder fused behind the last layer (model.py:201-220): Linear(256 -> 512) + GELU, Linear(512 -> S*F),
   // sigmoid, x mixed_spec, (B,S,F,T) stores.  decoder != 0: the stream holds 1 + 8 + 4 * nc3 more items per tile.
-  int decoder, nc3, SF, F;
+  int decoder, nc3, SF, F, S;
   const float* mixed;
   float *masks, *separated;
   long long* trace;             // optional [grid][256] clock64 stamps of the CTA's first tile (debug), else null:
@@ -85,10 +90,19 @@ struct StackDev {
 
 __device__ __forceinline__ uint32_t soff(int row, int c) { return static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4)); }
 
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+// Weight items are read by every CTA of every launch: keep them in L2 (evict_last) against the step's streaming traffic
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_line(const void* g) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(g)));
 }
 
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
@@ -189,11 +203,12 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       uint32_t wn = 0;          // stream items issued
       uint32_t hn = 0;          // heads whose K/V tiles were issued (cross)
       const uint32_t box_bytes = static_cast<uint32_t>(p.L) * 128u;
+      const uint64_t pol = l2_policy_evict_last();
       auto load_item = [&](const uint8_t* src) {
         const uint32_t slot = wn % NSLOT, use = wn / NSLOT;
         mbar_wait(&w_empty[slot], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&w_full[slot], ITEM);
-        bulk_load_1d(smem + OFF_RING + slot * ITEM, src, ITEM, &w_full[slot]);
+        bulk_load_1d(smem + OFF_RING + slot * ITEM, src, ITEM, &w_full[slot], pol);
         ++wn;
       };
       int lt = 0;
@@ -423,6 +438,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           ++wn;                                     // decoder vector block (row warps)
           mbar_wait(a_ready, n_a & 1); ++n_a;       // a = fusion.norm(x) in shared memory
           tc_fence_after();
+          XTRACE(112);                              // decoder: a seen
           // Linear(256 -> 512): four 128-wide chunks, A = a (smem); GELU'd H goes to tensor memory over X (dead now)
           for (int j = 0; j < 4; ++j, ++c1n) {
             const uint32_t st = c1n & 1;
@@ -442,8 +458,10 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             }
             umma_commit(&acc1_full[st]);
           }
+          XTRACE(113);                              // decoder: hidden GEMMs issued
           wait_h();
           wait_h();
+          XTRACE(114);                              // decoder: H complete in tensor memory
           // Linear(512 -> S*F): chunks of 128 output columns, A = H from tensor memory (K = 512), B streamed
           for (int c = 0; c < p.nc3; ++c, ++c1n) {
             const uint32_t st = c1n & 1;
@@ -461,6 +479,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               umma_commit(&w_empty[cur_slot]);
             }
             umma_commit(&acc1_full[st]);
+            XTRACE(115 + c);                        // decoder: output chunk c issued
           }
           for (int c = p.nc3 < 2 ? 0 : p.nc3 - 2; c < p.nc3; ++c) wait_h();
         }
@@ -590,6 +609,13 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(x_taken);
+      }
+      if (p.decoder) {
+        // the tile's mixture planes (contiguous: utterances utt0 .. utt0 + U - 1) are wanted in L2 by the decoder phase
+        const int n_utt = p.B - utt0 < p.U ? p.B - utt0 : p.U;
+        const size_t bytes = static_cast<size_t>(n_utt) * p.F * p.L * sizeof(float);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(p.mixed + static_cast<size_t>(utt0) * p.F * p.L);
+        for (size_t off = static_cast<size_t>(etid) * 128; off < bytes; off += 512 * 128) prefetch_l2_line(base + off);
       }
       for (int l = 0; l < p.n_layers; ++l) {
         // ---- per-layer vectors: first item of the layer in the weight stream (it was prefetched under the previous
@@ -834,6 +860,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         // ---- SeparationDecoder on the tile (model.py:201-220): a = fusion.norm(x) -> H = GELU(a W0^T + b0) kept in tensor
         // memory over X -> masks = sigmoid(H W3^T + b3), separated = masks * mixed_spec, stored along T ----
         ln_to_a(vec + VEC_B2, fin_g, fin_b);
+        XTRACE(107);                                         // decoder: final LayerNorm done
         // decoder vector block (b0 [512] | b3 [nc3 * 128]): next item of the weight stream
         {
           const uint32_t per_tile = static_cast<uint32_t>(p.n_layers * p.items_per_layer + 1 + 8 + 4 * p.nc3);
@@ -847,6 +874,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           named_bar_sync(5, 512);
           if (etid == 0) mbar_arrive(&w_empty[vslot]);
         }
+        XTRACE(108);                                         // decoder: vectors loaded
         // hidden chunks: bias + GELU -> bf16 pairs into X[64 j + 16 part, +16)
         for (int j = 0; j < 4; ++j, ++c1n) {
           const uint32_t st = c1n & 1;
@@ -866,48 +894,88 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&h_full[st]);
+          XTRACE(109 + j);                                   // decoder: H_j written
         }
-        // output chunks: 128 columns (s, f) each; this thread: row = (utterance, t), 32 columns
+        // output chunks of 128 columns; the packer orders the columns of a chunk as (frequency bin, speaker) pairs -
+        // column i of chunk c is bin c * 128/S + i / S of speaker i % S - so that one mixture value serves the S masks
+        // computed next to it.  This thread: row = (utterance, t), 32 columns as two halves of 16 (16 / S bins each).
+        // An (s, f) column of (B, S, F, T) is a plane of L floats: a warp (32 consecutive t) writes 128 contiguous
+        // bytes per column.  The mixture values of the next half are in flight while the current one is stored; the
+        // live set (two mixture buffers, 16 accumulator values, S + S running pointers) stays inside the 96 registers.
         const int utt = utt0 + r / p.stride, t = r - klo;
         const bool out_ok = row_valid && utt < p.B;
-        const size_t obase = static_cast<size_t>(utt) * p.SF * p.L + t;
-        const float* mrow = p.mixed + static_cast<size_t>(utt) * p.F * p.L + t;
-        for (int c = 0; c < p.nc3; ++c, ++c1n) {
-          const uint32_t st = c1n & 1;
-          const int col0 = c * 128 + part * 32;
-          // the mixture values of this thread's columns first (their latency hides behind the accumulator wait)
-          float mx[32];
-          {
-            int f = col0 % p.F;
+        const int Lp = p.L;
+        const size_t obase = static_cast<size_t>(out_ok ? utt : 0) * p.SF * Lp + t;
+        float* const mo_u = p.masks + obase;
+        float* const so_u = p.separated + obase;
+        const float* const mx_u = p.mixed + static_cast<size_t>(out_ok ? utt : 0) * p.F * Lp + t;
+        auto dec_out = [&](auto S_) {
+          constexpr int S = decltype(S_)::value;
+          constexpr int G = 16 / S;                            // frequency bins per half
+          constexpr int FPC = 128 / S;                         // frequency bins per chunk
+          const size_t FL = static_cast<size_t>(p.F) * Lp;     // floats between the planes of consecutive speakers
+          auto load_mx = [&](float (&mx)[G], int f0) {         // mixture values of bins [f0, f0 + G)
+            const float* q = mx_u + f0 * Lp;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mx[i] = (out_ok && col0 + i < p.SF) ? __ldg(mrow + static_cast<size_t>(f) * p.L) : 0.f;
-              if (++f == p.F) f = 0;
-            }
-          }
-          mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
-          tc_fence_after();
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&h_full[st]);           // the accumulator stage is drained (values in registers)
-          if (out_ok) {
-            const float* b3 = vec + 512 + col0;
-            float* mo = p.masks + obase + static_cast<size_t>(col0) * p.L;
-            float* so = p.separated + obase + static_cast<size_t>(col0) * p.L;
+            for (int j = 0; j < G; ++j, q += Lp) mx[j] = (out_ok && f0 + j < p.F) ? __ldg(q) : 0.f;
+          };
+          auto store_half = [&](const uint32_t (&v)[16], const float (&mx)[G], int f0, int col) {
+            if (!out_ok || f0 >= p.F) return;
+            const float* b3 = vec + 512 + col;                 // biases in the packed column order
+            float* mo = mo_u + static_cast<size_t>(f0) * Lp;
+            float* so = so_u + static_cast<size_t>(f0) * Lp;
+            if (f0 + G <= p.F) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (col0 + i < p.SF) {
-                const float mk = sigmoid_fast(__uint_as_float(v[i]) + b3[i]);
-                __stcs(mo + static_cast<size_t>(i) * p.L, mk);
-                __stcs(so + static_cast<size_t>(i) * p.L, mk * mx[i]);
+              for (int j = 0; j < G; ++j, mo += Lp, so += Lp) {
+#pragma unroll
+                for (int sp = 0; sp < S; ++sp) {
+                  const float mk = sigmoid_fast(__uint_as_float(v[j * S + sp]) + b3[j * S + sp]);
+                  __stcs(mo + sp * FL, mk);
+                  __stcs(so + sp * FL, mk * mx[j]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < G; ++j, mo += Lp, so += Lp) {
+                if (f0 + j < p.F) {
+#pragma unroll
+                  for (int sp = 0; sp < S; ++sp) {
+                    const float mk = sigmoid_fast(__uint_as_float(v[j * S + sp]) + b3[j * S + sp]);
+                    __stcs(mo + sp * FL, mk);
+                    __stcs(so + sp * FL, mk * mx[j]);
+                  }
+                }
               }
             }
+          };
+          float mxa[G], mxb[G];
+          load_mx(mxa, part * (32 / S));
+          for (int c = 0; c < p.nc3; ++c, ++c1n) {
+            const uint32_t st = c1n & 1;
+            const int f0 = c * FPC + part * (32 / S);
+            load_mx(mxb, f0 + G);
+            XTRACE(113 + 2 * c);                               // decoder: mixture loads of chunk c issued
+            mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
+            tc_fence_after();
+            XTRACE(114 + 2 * c);                               // decoder: output chunk c complete
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmW + lane_sel + st * 128 + part * 32, v);
+            tmem_ld_wait();
+            store_half(v, mxa, f0, c * 128 + part * 32);
+            tmem_ld_32x32b_x16(tmW + lane_sel + st * 128 + part * 32 + 16, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_full[st]);           // the accumulator stage is drained (values in registers)
+            if (c + 1 < p.nc3) load_mx(mxa, f0 + FPC);
+            store_half(v, mxb, f0 + G, c * 128 + part * 32 + 16);
           }
-        }
+        };
+        if (p.S == 2) dec_out(std::integral_constant<int, 2>());
+        else if (p.S == 1) dec_out(std::integral_constant<int, 1>());
+        else dec_out(std::integral_constant<int, 4>());
         named_bar_sync(5, 512);
+        XTRACE(127);                                         // tile done
         if (elected) mbar_arrive(stage_free);
       } else
       // ---- stack output: x + last linear2 bias -> fp32 residual rows and / or (final LayerNorm | cast) bf16 rows ----
@@ -1087,24 +1155,34 @@ void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const flo
   memcpy(dst + VEC_N2B, n2b, sizeof(float) * D);
 }
 
-// SeparationDecoder block of the fusion stream (after the last layer): vector block (b0 [512] | b3 padded to nc3 * 128),
-// Linear(256 -> 512) as 8 items (chunk j, k-slab pair), Linear(512 -> S*F) as 4 items per 128-column chunk
-size_t xformer_decoder_bytes(int SF) { return static_cast<size_t>(1 + 8 + 4 * ((SF + 127) / 128)) * ITEM; }
-void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int SF, uint8_t* dst) {
-  const int nc3 = (SF + 127) / 128;
-  memset(dst, 0, xformer_decoder_bytes(SF));
+// SeparationDecoder block of the fusion stream (after the last layer): vector block (b0 [512] | b3 in packed column
+// order), Linear(256 -> 512) as 8 items (chunk j, k-slab pair), Linear(512 -> S*F) as 4 items per 128-column chunk.
+// Packed column order: column i of chunk c is frequency bin c * 128/S + i / S of speaker i % S (zero rows past F).
+int xformer_decoder_chunks(int S, int F) { return (F + 128 / S - 1) / (128 / S); }
+bool xformer_decoder_usable(int S, int F) {
+  return (S == 1 || S == 2 || S == 4) && F >= 1 && 512 + xformer_decoder_chunks(S, F) * 128 <= VEC_FLOATS;
+}
+size_t xformer_decoder_bytes(int S, int F) { return static_cast<size_t>(1 + 8 + 4 * xformer_decoder_chunks(S, F)) * ITEM; }
+void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int S, int F, uint8_t* dst) {
+  const int nc3 = xformer_decoder_chunks(S, F), fpc = 128 / S;
+  memset(dst, 0, xformer_decoder_bytes(S, F));
+  std::vector<float> wp(static_cast<size_t>(nc3) * 128 * 2 * D, 0.f);
   float* v = reinterpret_cast<float*>(dst);
   memcpy(v, b0, sizeof(float) * 512);
-  memcpy(v + 512, b3, sizeof(float) * SF);
+  for (int c = 0; c < nc3; ++c)
+    for (int i = 0; i < 128; ++i) {
+      const int f = c * fpc + i / S, sp = i % S;
+      if (f >= F) continue;
+      v[512 + c * 128 + i] = b3[sp * F + f];
+      memcpy(&wp[static_cast<size_t>(c * 128 + i) * 2 * D], w3 + static_cast<size_t>(sp * F + f) * 2 * D, sizeof(float) * 2 * D);
+    }
   dst += ITEM;
   for (int j = 0; j < 4; ++j)
     for (int it = 0; it < 2; ++it, dst += ITEM)
       for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, w0, D, j * 128, 128, (2 * it + half) * 64);
-  for (int c = 0; c < nc3; ++c) {
-    const int nrows = SF - c * 128 < 128 ? SF - c * 128 : 128;
+  for (int c = 0; c < nc3; ++c)
     for (int it = 0; it < 4; ++it, dst += ITEM)
-      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, w3, 2 * D, c * 128, nrows, (2 * it + half) * 64);
-  }
+      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, wp.data(), 2 * D, c * 128, 128, (2 * it + half) * 64);
 }
 
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len) {
@@ -1118,7 +1196,7 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   if (decoder) {
     if (!sp.cross || sp.out_x || sp.out_op || !sp.mixed || !sp.separated || sp.F < 1 || sp.S < 1)
       return "xformer_stack: the fused decoder follows the fusion stack and replaces its outputs";
-    if (512 + (sp.S * sp.F + 127) / 128 * 128 > VEC_FLOATS) return "xformer_stack: S * freq_bins too large for the fused decoder";
+    if (!xformer_decoder_usable(sp.S, sp.F)) return "xformer_stack: speaker count / freq_bins not supported by the fused decoder";
   }
   if (g_enc == nullptr) {
     void* fn = nullptr;
@@ -1155,7 +1233,7 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
   d.trace = sp.trace;
   d.decoder = decoder ? 1 : 0;
-  d.SF = sp.S * sp.F; d.F = sp.F; d.nc3 = (d.SF + 127) / 128;
+  d.SF = sp.S * sp.F; d.F = sp.F; d.S = sp.S; d.nc3 = decoder ? xformer_decoder_chunks(sp.S, sp.F) : 0;
   d.mixed = sp.mixed; d.masks = sp.masks; d.separated = sp.separated;
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
   if (launch_pdl(xformer_stack_kernel, dim3(grid), dim3(STACK_THREADS), STACK_SMEM, s, tin, tout, top, tkv, d) !=

@@ -232,6 +232,12 @@ AVSEP_API int avsep_test_xformer_stack(avsep_handle* h, int32_t which, const flo
                                        int32_t L, float* out_x, void* out_op, int32_t final_ln, long long* trace_dev,
                                        void* cuda_stream);   /* trace_dev: NULL or [grid][256] clock stamps (tools/stack_trace.py) */
 
+/* Test hook: CrossModalFusion.layers + .norm followed by SeparationDecoder (model.py:166-173,201-220) in the one fused
+ * kernel the forward uses: x_in fp32 [B*L, d], kv as above, mixed (B, F, L) fp32 -> separated / masks (B, S, F, L) fp32. */
+AVSEP_API int avsep_test_fusion_decoder(avsep_handle* h, const float* x_in, const void* kv, int32_t B, int32_t L,
+                                        const float* mixed, float* separated, float* masks, long long* trace_dev,
+                                        void* cuda_stream);
+
 /* ---- batch sharding over the GPUs of one box (BASELINE.json north_star: "inputs scattered and
  * separated/masks gathered over NVLink") -------------------------------------------------------------------------
  * The path shards by utterance with no collective inside the model (model.py has no op that mixes batch elements in

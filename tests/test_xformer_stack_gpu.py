@@ -111,3 +111,52 @@ def test_outputs_are_selectable_and_rows_outside_the_batch_untouched(setup):
     _, op_only = _run(eng, 0, x, None, B, L, False, True, True)
     both_x, both_op = _run(eng, 0, x, None, B, L, True, True, True)
     assert np.array_equal(x_only, both_x) and np.array_equal(op_only, both_op)
+
+
+@pytest.mark.parametrize("B,T,N", [(1, 63, 50), (5, 63, 50), (3, 32, 10), (9, 20, 7), (300, 63, 50)])
+def test_fusion_stack_with_fused_decoder_matches_oracle(setup, B, T, N):
+    """CrossModalFusion + SeparationDecoder in the one kernel the forward launches (avsep_test_fusion_decoder): masks and
+    separated against the oracle's fusion loop + decoder (model.py:166-173,201-220) on the same K|V rows; odd batches
+    leave half a tile empty, B=300 gives every CTA more than one tile, short clips pack 4 utterances per tile."""
+    cfg, P, eng = setup
+    d, Lf, S, Fq = cfg.d_model, cfg.num_fusion_layers, cfg.num_speakers, cfg.freq_bins
+    rng = np.random.default_rng(7 * B + T)
+    a = rng.standard_normal((B, T, d)).astype(np.float32)
+    v = rng.standard_normal((B, N, d)).astype(np.float32)
+    mixed = rng.random((B, Fq, T)).astype(np.float32) * 3.0
+    with torch.no_grad():
+        vi = F.interpolate(torch.from_numpy(v).permute(0, 2, 1), size=T, mode="linear", align_corners=False).permute(0, 2, 1)
+        f = torch.from_numpy(a)
+        kv_cols = []
+        for l in range(Lf):
+            p = f"fusion.layers.{l}"
+            h = F.layer_norm(f, (d,), P[f"{p}.norm1.weight"], P[f"{p}.norm1.bias"], 1e-5)
+            f = f + otorch._mha(h, vi, P, f"{p}.cross_attn", cfg.nhead, need_weights=True)
+            h = F.layer_norm(f, (d,), P[f"{p}.norm2.weight"], P[f"{p}.norm2.bias"], 1e-5)
+            h = F.gelu(F.linear(h, P[f"{p}.ff.0.weight"], P[f"{p}.ff.0.bias"]))
+            f = f + F.linear(h, P[f"{p}.ff.3.weight"], P[f"{p}.ff.3.bias"])
+            W, bias = P[f"{p}.cross_attn.in_proj_weight"], P[f"{p}.cross_attn.in_proj_bias"]
+            kv_cols.append(F.linear(vi, W[d:], bias[d:]))
+        f = F.layer_norm(f, (d,), P["fusion.norm.weight"], P["fusion.norm.bias"], 1e-5)
+        h = F.gelu(F.linear(f, P["decoder.decoder.0.weight"], P["decoder.decoder.0.bias"]))
+        logits = F.linear(h, P["decoder.decoder.3.weight"], P["decoder.decoder.3.bias"])
+        masks_ref = torch.sigmoid(logits.view(B, T, S, Fq).permute(0, 2, 3, 1)).numpy()
+        kv = torch.cat(kv_cols, dim=-1).reshape(B * T, Lf * 2 * d).to(torch.bfloat16)
+    dev = torch.device("cuda", eng.device)
+    xd = torch.from_numpy(a.reshape(B * T, d)).to(dev).contiguous()
+    kvd = kv.to(dev).contiguous()
+    md = torch.from_numpy(mixed).to(dev).contiguous()
+    # one guard utterance behind the outputs: the kernel must not write past the batch
+    sep = torch.full((B + 1, S, Fq, T), float("nan"), device=dev)
+    msk = torch.full((B + 1, S, Fq, T), float("nan"), device=dev)
+    rc = eng.lib.avsep_test_fusion_decoder(eng.h, xd.data_ptr(), kvd.data_ptr(), B, T, md.data_ptr(), sep.data_ptr(),
+                                           msk.data_ptr(), None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, eng.lib.avsep_last_error(eng.h).decode()
+    torch.cuda.synchronize()
+    assert torch.isnan(sep[B]).all() and torch.isnan(msk[B]).all()
+    got_m, got_s = msk[:B].cpu().numpy(), sep[:B].cpu().numpy()
+    assert np.isfinite(got_m).all() and np.isfinite(got_s).all()
+    err = float(np.abs(got_m - masks_ref).max())
+    print(f"fusion+decoder B={B} T={T} N={N}: max|d masks| = {err:.3e}")
+    assert err < 1e-2, err                                            # BASELINE.json north_star: masks within 1e-2 (bf16)
+    assert np.array_equal(got_s, got_m * mixed[:, None])             # separated is exactly masks * mixed_spec (fp32)

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--which", type=int, default=0)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--len", type=int, default=63)
+    ap.add_argument("--decoder", action="store_true", help="which=2 with the SeparationDecoder fused behind the stack")
     args = ap.parse_args()
     from avsep_b200 import AVSeparationTransformer
     torch.manual_seed(0)
@@ -39,16 +40,27 @@ def main():
     grid = min(148, (B + U - 1) // U)
     trace = torch.zeros(grid * 256, device="cuda", dtype=torch.int64)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if args.decoder:
+        assert args.which == 2
+        mixed = torch.rand(B, 257, L, device="cuda")
+        sep = torch.empty(B, 2, 257, L, device="cuda")
+        masks = torch.empty_like(sep)
+
+    def launch(tr):
+        if args.decoder:
+            return eng.lib.avsep_test_fusion_decoder(eng.h, x.data_ptr(), kv.data_ptr(), B, L, mixed.data_ptr(), sep.data_ptr(),
+                                                     masks.data_ptr(), tr, st)
+        return eng.lib.avsep_test_xformer_stack(eng.h, args.which, x.data_ptr(), kv.data_ptr() if kv is not None else None, B, L,
+                                                None, out.data_ptr(), 1 if args.which != 1 else 0, tr, st)
+
     for it in range(3):
-        rc = eng.lib.avsep_test_xformer_stack(eng.h, args.which, x.data_ptr(), kv.data_ptr() if kv is not None else None, B, L,
-                                              None, out.data_ptr(), 1 if args.which != 1 else 0, trace.data_ptr(), st)
+        rc = launch(trace.data_ptr())
         assert rc == 0, eng.lib.avsep_last_error(eng.h).decode()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for it in range(10):
-        eng.lib.avsep_test_xformer_stack(eng.h, args.which, x.data_ptr(), kv.data_ptr() if kv is not None else None, B, L,
-                                         None, out.data_ptr(), 1 if args.which != 1 else 0, None, st)
+        launch(None)
     e1.record()
     torch.cuda.synchronize()
     print(f"which={args.which} B={B} L={L} grid={grid}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch (no trace)")
@@ -92,7 +104,11 @@ def main():
         ml += [(mb + 25, f"L{l} attention issued"), (mb + 26, f"L{l} LN2 seen")]
         for j in range(8):
             ml += [(mb + 27 + 3 * j, f"L{l} G1_{j} issued"), (mb + 28 + 3 * j, f"L{l} H_{j} seen"), (mb + 29 + 3 * j, f"L{l} G2_{j} issued")]
+    rl += [(107, "dec final LN done"), (108, "dec vectors loaded")] + [(109 + j, f"dec H_{j} written") for j in range(4)]
+    for c in range(5):
+        rl += [(113 + 2 * c, f"dec out {c} mixture loads issued"), (114 + 2 * c, f"dec out {c} acc complete")]
     rl += [(127, "tile done")]
+    ml += [(112, "dec a seen"), (113, "dec hidden GEMMs issued"), (114, "dec H complete")] + [(115 + c, f"dec out {c} issued") for c in range(5)]
     show("row", row, rl)
     print()
     show("mma", mma, ml)
