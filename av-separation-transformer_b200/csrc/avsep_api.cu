@@ -135,6 +135,8 @@ struct avsep_handle {
   // prepacked weight streams / vector blocks of the fused transformer-stack kernel (null when the config cannot use it)
   const uint8_t *xs_a = nullptr, *xs_v = nullptr, *xs_f = nullptr;
   bool xs_f_decoder = false;   // the fusion stream continues with the SeparationDecoder block
+  const uint8_t *xs_a_np = nullptr, *xs_v_np = nullptr;   // encoder streams past their input-projection items
+  bool fuse_proj = true;       // Conv1d #2 / frame_proj inside the encoder stack kernels (option "fuse_proj")
   bool fuse_decoder = true;    // run the decoder inside the fusion stack kernel (option "fuse_decoder")
   bool fuse_stack = true;   // whole encoder / fusion stacks in one persistent kernel (d_model = 256, 4 heads, bf16, len <= 128)
   // cached library-owned workspace
@@ -378,12 +380,18 @@ bool stack_fusable(const avsep_handle* h, int len) {
 // A whole stack in one kernel (xformer_stack_sm100.cu).  which: 0 audio encoder, 1 visual encoder, 2 fusion.
 int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, float* out_x, void* out_op,
               const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L, long long* trace = nullptr,
-              const float* mixed = nullptr, float* separated = nullptr, float* masks = nullptr) {
+              const float* mixed = nullptr, float* separated = nullptr, float* masks = nullptr, const void* pro_a = nullptr) {
   StackProblem sp{};
   sp.trace = trace;
+  if (pro_a != nullptr) {        // x_in is produced inside the kernel (which 0: Conv1d #2 + ReLU + PE; 1: frame_proj + PE)
+    sp.pro_a = pro_a; sp.pro_relu = which == 0;
+    sp.pro_taps = which == 0 ? 3 : 1; sp.pro_k = which == 0 ? h->cfg.d_model : 128;
+    sp.pro_pitch = which == 0 ? L + 2 : L; sp.pro_rows = B * sp.pro_pitch;
+    sp.pe = which == 0 ? h->pe_a : h->pe_v;
+  }
   sp.mixed = mixed; sp.separated = separated; sp.masks = masks; sp.F = h->cfg.freq_bins; sp.S = h->cfg.num_speakers;
   sp.x_in = x_in; sp.out_x = out_x; sp.out_op = out_op; sp.fin_gamma = fin_g; sp.fin_beta = fin_b;
-  sp.wstream = which == 0 ? h->xs_a : which == 1 ? h->xs_v : h->xs_f;
+  sp.wstream = which == 0 ? (pro_a ? h->xs_a : h->xs_a_np) : which == 1 ? (pro_a ? h->xs_v : h->xs_v_np) : h->xs_f;
   sp.n_layers = which == 2 ? h->cfg.num_fusion_layers : h->cfg.num_encoder_layers;
   sp.cross = which == 2;
   sp.kv = kv; sp.kv_ld = kv_ld;
@@ -430,7 +438,7 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
 // layer's LayerNorm: x_a (fp32) and a_op = LN_{g,b}(x_a).
 // x_only: the fused stack kernel computes the first LayerNorm itself, so only the fp32 residual rows are written.
 int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* mixed, const float* g, const float* b,
-                   bool x_only = false) {
+                   bool x_only = false, bool conv1_only = false) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, F = h->cfg.freq_bins, B = w.B, T = w.T, prec = h->cfg.precision;
   const int Map = B * (T + 2);
@@ -444,6 +452,7 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
     e.out_op = w.h1; e.ld_op = d;
     CKL("gemm.conv1d_0", launch_gemm(s, prec, p, e));
   }
+  if (conv1_only) return 0;      // Conv1d #2 + ReLU + PE run inside the encoder stack kernel, on h1
   {
     GemmProblem p{};
     p.A = w.h1; p.lda = d; p.rowsA = Map; p.M = Map; p.W = h->wc2; p.ldw = 3 * d; p.N = d; p.K = d;
@@ -464,12 +473,13 @@ int audio_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
 // VisualEncoder up to (not including) the transformer: CNN, pool, frame_proj, +PE (model.py:106-110), then the
 // first layer's LayerNorm: x_v (fp32) and v_op = LN_{g,b}(x_v).
 int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* frames, const float* g, const float* b,
-                    bool x_only = false) {
+                    bool x_only = false, bool cnn_only = false) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, N = w.N;
   const int Mv = B * N;
   CKL("visual_cnn", run_visual_cnn(h, s, frames, Mv, w.Hh, w.Ww, w.pooled));
   if (snapshot(h, s, "visual_pool", w.pooled, static_cast<size_t>(Mv) * 128, true)) return 1;
+  if (cnn_only) return 0;        // frame_proj + PE run inside the encoder stack kernel, on the pooled features
   GemmProblem p{};
   p.A = w.pooled; p.lda = 128; p.rowsA = Mv; p.M = Mv; p.W = h->wproj; p.ldw = 128; p.N = d; p.K = 128;
   p.taps = 1;
@@ -591,18 +601,23 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   const bool fa = stack_fusable(h, w.T), fv = stack_fusable(h, w.N);
   const bool ff = fa && fv;            // the fused fusion stack reads the fp32 residual rows of both encoders
   // --- visual branch (enqueued first: its CNN is the longest kernel) ---
-  if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b, fv)) return 1;
+  const bool fp = h->fuse_proj && !h->debug;     // input projections inside the stack kernels (no stage snapshots then)
+  if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b, fv, fv && fp)) return 1;
   if (fv) {
     // out: x_v (fp32) for the interpolation in front of the K/V projection; v_op (bf16 cast) only for the unfused fusion
-    if (run_stack(h, sv, 1, w.x_v, w.x_v, ff ? nullptr : w.v_op, nullptr, nullptr, nullptr, 0, w.B, w.N)) return 1;
+    if (run_stack(h, sv, 1, w.x_v, w.x_v, ff ? nullptr : w.v_op, nullptr, nullptr, nullptr, 0, w.B, w.N, nullptr, nullptr,
+                  nullptr, nullptr, fp ? w.pooled : nullptr))
+      return 1;
   } else if (encoder_stack(h, sv, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) {
     return 1;
   }
   if (snapshot(h, sv, "visual_enc", w.x_v, static_cast<size_t>(Mv) * d, false)) return 1;
   // --- audio branch ---
-  if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b, fa)) return 1;
+  if (audio_frontend(h, s, w, mixed, h->enc_a[0].n1g, h->enc_a[0].n1b, fa, fa && fp)) return 1;
   if (fa) {
-    if (run_stack(h, s, 0, w.x_a, w.x_a, ff ? nullptr : w.a_op, h->fus[0].n1g, h->fus[0].n1b, nullptr, 0, w.B, w.T)) return 1;
+    if (run_stack(h, s, 0, w.x_a, w.x_a, ff ? nullptr : w.a_op, h->fus[0].n1g, h->fus[0].n1b, nullptr, 0, w.B, w.T, nullptr,
+                  nullptr, nullptr, nullptr, fp ? w.h1 : nullptr))
+      return 1;
   } else if (encoder_stack(h, s, h->enc_a, w.B, w.T, w.x_a, w.y_a, w.a_op, w.qkv_a, w.attn_a, w.ffn_a, h->fus[0].n1g,
                            h->fus[0].n1b)) {
     return 1;
@@ -992,7 +1007,22 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
     const size_t vf = static_cast<size_t>(xformer_vec_floats());
     for (int stack = 0; stack < 2; ++stack) {
       const std::string pre = stack == 0 ? "audio_encoder" : "visual_encoder";
-      std::vector<uint8_t> stream(static_cast<size_t>(Le) * xformer_stream_bytes(false));
+      // the stream starts with the input projection (Conv1d #2 as 3 taps x 256 / frame_proj as 1 x 128), whose bias
+      // rides in layer 0's vector block
+      const size_t pro_bytes = stack == 0 ? xformer_pro_bytes(3, static_cast<int>(d)) : xformer_pro_bytes(1, 128);
+      std::vector<uint8_t> stream(pro_bytes + static_cast<size_t>(Le) * xformer_stream_bytes(false));
+      const HostTensor* b0t = nullptr;
+      if (stack == 0) {
+        GETW(wc, "audio_encoder.input_proj.2.weight", d, d, 3);
+        GETW(bc, "audio_encoder.input_proj.2.bias", d);
+        xformer_pack_pro(wc->data.data(), static_cast<int>(3 * d), 3, 3, static_cast<int>(d), stream.data());
+        b0t = bc;
+      } else {
+        GETW(wc, "visual_encoder.frame_proj.weight", d, 128);
+        GETW(bc, "visual_encoder.frame_proj.bias", d);
+        xformer_pack_pro(wc->data.data(), 128, 1, 1, 128, stream.data());
+        b0t = bc;
+      }
       std::vector<float> vecs(vf);
       for (int l = 0; l < Le; ++l) {
         const std::string p = pre + ".transformer.layers." + std::to_string(l);
@@ -1009,9 +1039,10 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
         GETW(n2g, p + ".norm2.weight", d);
         GETW(n2b, p + ".norm2.bias", d);
         xformer_pack_vecs(bqkv->data.data(), static_cast<int>(3 * d), bo->data.data(), b1->data.data(), b2->data.data(),
-                          n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data());
+                          n1g->data.data(), n1b->data.data(), n2g->data.data(), n2b->data.data(), vecs.data(),
+                          l == 0 ? b0t->data.data() : nullptr);
         xformer_pack_self(wqkv->data.data(), wo->data.data(), w1->data.data(), w2->data.data(), vecs.data(),
-                          stream.data() + static_cast<size_t>(l) * xformer_stream_bytes(false));
+                          stream.data() + pro_bytes + static_cast<size_t>(l) * xformer_stream_bytes(false));
       }
       off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
     }
@@ -1077,6 +1108,7 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
   h->xs_a = h->xs_v = h->xs_f = nullptr;
   if (pack_stacks) {
     h->xs_a = static_cast<const uint8_t*>(P("xs_a")); h->xs_v = static_cast<const uint8_t*>(P("xs_v"));
+    h->xs_a_np = h->xs_a + xformer_pro_bytes(3, h->cfg.d_model); h->xs_v_np = h->xs_v + xformer_pro_bytes(1, 128);
     h->xs_f = static_cast<const uint8_t*>(P("xs_f"));
   }
   h->enc_a.clear(); h->enc_v.clear(); h->fus.clear();
@@ -1645,6 +1677,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ffn") == 0) { h->fuse_ffn = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_stack") == 0) { h->fuse_stack = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_decoder") == 0) { h->fuse_decoder = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "fuse_proj") == 0) { h->fuse_proj = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "attn_small") == 0) { attention_set_small(value != 0); drop_graphs(h); return 0; }

@@ -111,6 +111,11 @@ struct StackProblem {
   long long* trace = nullptr;   // optional [grid][256] clock64 stamps (debug)
   // SeparationDecoder fused behind the fusion stack (cross only; replaces out_x / out_op): the stream then continues with
   // xformer_decoder_bytes(S, F) of decoder items (xformer_pack_decoder)
+  // Input projection fused in front of layer 0 (self stacks; replaces x_in): x = act(sum_tap A[utt * pro_pitch + t + tap]
+  // W_tap^T + b0) + pe[t].  The stream then starts with xformer_pro_bytes(pro_taps, pro_k) of projection items.
+  const void* pro_a = nullptr;           // bf16 [pro_rows, pro_k]
+  int pro_rows = 0, pro_pitch = 0, pro_taps = 0, pro_k = 0, pro_relu = 0;
+  const float* pe = nullptr;             // fp32 [>= L, 256]
   const float* mixed = nullptr;          // (B, F, L) fp32
   float *masks = nullptr, *separated = nullptr;   // (B, S, F, L) fp32
   int F = 0, S = 0;
@@ -119,6 +124,9 @@ bool xformer_decoder_usable(int S, int F);
 int xformer_decoder_chunks(int S, int F);
 size_t xformer_decoder_bytes(int S, int F);
 void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, const float* b3, int S, int F, uint8_t* dst);
+size_t xformer_pro_bytes(int taps, int K);
+// W element (n, tap, k) at W[n * ld + k * col_stride + tap]: Conv1d weight (out, in, 3): ld = 3 in, col_stride = 3
+void xformer_pack_pro(const float* W, int ld, int col_stride, int taps, int K, uint8_t* dst);
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
 size_t xformer_stream_bytes(bool cross);
 int xformer_vec_floats();
@@ -127,7 +135,7 @@ void xformer_pack_self(const float* wqkv, const float* wo, const float* w1, cons
 void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const float* w2, const float* vecs,
                         uint8_t* dst);
 void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const float* b1, const float* b2, const float* n1g,
-                       const float* n1b, const float* n2g, const float* n2b, float* dst);
+                       const float* n1b, const float* n2g, const float* n2b, float* dst, const float* b0 = nullptr);
 const char* launch_xformer_stack(cudaStream_t s, const StackProblem& p, int num_sms);
 
 // x_out = x + y (y may be null); out = LayerNorm(x_out) * gamma + beta (skipped when gamma == null, then out = x_out).

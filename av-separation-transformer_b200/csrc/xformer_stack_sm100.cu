@@ -56,7 +56,7 @@ constexpr int OFF_VT = OFF_KT + SLAB;             // V_h tile [keys x 64] (MN-ma
 constexpr int OFF_RED = OFF_VT + SLAB;            // 2 x [128 rows][4 parts] float2
 // per-layer vector block = first item of every layer in the weight stream
 constexpr int VEC_BQKV = 0, VEC_BO = 768, VEC_B1 = 1024, VEC_B2 = 2048, VEC_N1G = 2304, VEC_N1B = 2560,
-              VEC_N2G = 2816, VEC_N2B = 3072, VEC_FLOATS = 3328;
+              VEC_N2G = 2816, VEC_N2B = 3072, VEC_B0 = 3328, VEC_FLOATS = 3584;   // VEC_B0: bias of the input projection (layer 0)
 constexpr int OFF_VEC = OFF_RED + 2 * 4096;
 constexpr int OFF_PEND = OFF_VEC + VEC_FLOATS * 4;   // [256] bias carried into the next LayerNorm | final gamma | beta
 constexpr int OFF_BAR = OFF_PEND + 3 * 1024;
@@ -82,6 +82,13 @@ struct StackDev {
   int decoder, nc3, SF, F, S;
   const float* mixed;
   float *masks, *separated;
+  // Input projection fused in front of layer 0 (self stacks): x = act(sum_tap A[row + tap] W_tap^T + b0) + PE[t], with
+  // A = bf16 rows [*, pro_ks * 64] (pro_pitch rows per utterance; tap = row shift), W as pro_taps * pro_ks stream items
+  // ahead of layer 0, PE = fp32 [*, 256].  pro_taps == 0: x comes from x_in instead.
+  //   audio  (model.py:56-58): Conv1d(256 -> 256, k = 3, pad 1) + ReLU on the zero-haloed Conv1d #1 output, + PE
+  //   visual (model.py:108-110): frame_proj Linear(128 -> 256) on the pooled CNN features, + PE
+  int pro_taps, pro_ks, pro_pitch, pro_relu;
+  const float* pe;
   long long* trace;             // optional [grid][256] clock64 stamps of the CTA's first tile (debug), else null:
                                 //   row thread (warp 2 lane 0) in [0,128), MMA thread in [128,256); see tools/stack_trace.py
 };
@@ -145,7 +152,10 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   uint64_t* ffn_done = bars + 23;
   uint64_t* v_full = bars + 24;            // self: V_h accumulator complete
   uint64_t* v_ready = bars + 25;           // (16) self: V tile in shared memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* pa_full = bars + 26;           // [4] input projection: A slab landed
+  uint64_t* pa_free = bars + 30;           // [4] input projection: the MMAs have read the A slab
+  uint64_t* x_ready = bars + 34;           // input projection complete (X holds the pre-activation rows)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
   float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
   float* pend = reinterpret_cast<float*>(smem + OFF_PEND);
@@ -158,7 +168,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     tma_prefetch_desc(&tmXin);
     if (p.out_x) tma_prefetch_desc(&tmXout);
     if (p.out_op) tma_prefetch_desc(&tmOp);
-    if (p.cross) tma_prefetch_desc(&tmKV);
+    if (p.cross || p.pro_taps) tma_prefetch_desc(&tmKV);
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(x_full, 1);
     mbar_init(x_taken, 16);
@@ -177,6 +187,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     mbar_init(ffn_done, 1);
     mbar_init(v_full, 1);
     mbar_init(v_ready, 16);
+    for (int i = 0; i < 4; ++i) { mbar_init(&pa_full[i], 1); mbar_init(&pa_free[i], 1); }
+    mbar_init(x_ready, 1);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < D; i += STACK_THREADS) {
@@ -194,6 +206,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmX = tmem_base + TM_X, tmW = tmem_base + TM_W;
+  const int n_pro = p.pro_taps * p.pro_ks;      // stream items of the input projection (ahead of layer 0)
   griddep_launch_dependents();
   griddep_wait();
 
@@ -201,6 +214,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     if (lane == 0) {
       // ---------------- producer: x tile, weight stream (incl. the per-layer vector block), (cross) K / V tiles ------
       uint32_t wn = 0;          // stream items issued
+      uint32_t an = 0;          // input-projection A slabs issued
       uint32_t hn = 0;          // heads whose K/V tiles were issued (cross)
       const uint32_t box_bytes = static_cast<uint32_t>(p.L) * 128u;
       const uint64_t pol = l2_policy_evict_last();
@@ -224,13 +238,30 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           ++hn;
         };
         if (lt > 0) mbar_wait(stage_free, (lt - 1) & 1);
-        mbar_arrive_expect_tx(x_full, 8u * p.U * box_bytes);
-        for (int s = 0; s < 8; ++s)
-          for (int u = 0; u < p.U; ++u)
-            tma_load_2d(smem + OFF_A + s * SLAB + u * p.stride * 128, &tmXin, x_full, s * 32, (utt0 + u) * p.L);
-        mbar_wait(x_taken, lt & 1);            // staging (a_op + first two ring slots) is free again
+        if (p.pro_taps) {
+          // input projection: A slabs (tensor map tmKV: boxes of a whole utterance slot, so that every tile row holds
+          // finite data) through a 4-slot ring in the operand area, one weight item per slab
+          const uint8_t* src = p.wstream;
+          int st = 0;
+          for (int tap = 0; tap < p.pro_taps; ++tap)
+            for (int ks = 0; ks < p.pro_ks; ++ks, ++st, ++an) {
+              const uint32_t sa = an & 3;
+              mbar_wait(&pa_free[sa], ((an >> 2) & 1) ^ 1);
+              mbar_arrive_expect_tx(&pa_full[sa], static_cast<uint32_t>(p.U * p.stride) * 128u);
+              for (int u = 0; u < p.U; ++u)
+                tma_load_2d(smem + OFF_A + sa * SLAB + u * p.stride * 128, &tmKV, &pa_full[sa], ks * 64,
+                            (utt0 + u) * p.pro_pitch + tap);
+              load_item(src + static_cast<size_t>(st) * ITEM);
+            }
+        } else {
+          mbar_arrive_expect_tx(x_full, 8u * p.U * box_bytes);
+          for (int s = 0; s < 8; ++s)
+            for (int u = 0; u < p.U; ++u)
+              tma_load_2d(smem + OFF_A + s * SLAB + u * p.stride * 128, &tmXin, x_full, s * 32, (utt0 + u) * p.L);
+          mbar_wait(x_taken, lt & 1);            // staging (a_op + first two ring slots) is free again
+        }
         for (int l = 0; l < p.n_layers; ++l) {
-          const uint8_t* src = p.wstream + static_cast<size_t>(l) * p.items_per_layer * ITEM;
+          const uint8_t* src = p.wstream + static_cast<size_t>(n_pro + l * p.items_per_layer) * ITEM;
           load_item(src);                      // vector block
           src += ITEM;
           if (!p.cross) {
@@ -253,7 +284,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           for (int i = 0; i < 32; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
         }
         if (p.decoder) {
-          const uint8_t* src = p.wstream + static_cast<size_t>(p.n_layers) * p.items_per_layer * ITEM;
+          const uint8_t* src = p.wstream + static_cast<size_t>(n_pro + p.n_layers * p.items_per_layer) * ITEM;
           const int n = 1 + 8 + 4 * p.nc3;
           for (int i = 0; i < n; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
         }
@@ -322,7 +353,27 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       constexpr int trace_base = 128;
       int lt = 0;
       XTRACE(0);
+      uint32_t am = 0;                             // input-projection A slabs consumed
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++lt) {
+        if (p.pro_taps) {
+          // X = sum over (tap, k-slab) of A_slab W_item^T : two 128-column halves per item
+          for (int st = 0; st < n_pro; ++st, ++am) {
+            const uint32_t sa = am & 3;
+            mbar_wait(&pa_full[sa], (am >> 2) & 1);
+            const uint32_t base = next_item();
+            const uint64_t adesc = umma_desc_kmajor_sw128(a_base + sa * SLAB, 1024);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint64_t bdesc = umma_desc_kmajor_sw128(base + hf * SLAB, 1024);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16(tmX + hf * 128, adesc + 2 * kk, bdesc + 2 * kk, ID128, (st | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&w_empty[cur_slot]);
+            umma_commit(&pa_free[sa]);
+          }
+          umma_commit(x_ready);
+        }
         for (int l = 0; l < p.n_layers; ++l) {
           const int tb = 1 + l * 60;               // MMA-thread stamps of layer l: tb + 0 LN1 seen; per head 6; FFN per chunk 3
           ++wn;                                    // the layer's vector block is consumed by the row warps
@@ -586,6 +637,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       const int utt0 = tile * p.U;
       // ---- residual tile: staging slabs (fp32, 32 columns each) -> tensor memory ----
       XTRACE(0);
+      if (!p.pro_taps) {
       mbar_wait(x_full, lt & 1);
       XTRACE(1);                                             // x staged
       {
@@ -610,6 +662,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(x_taken);
       }
+      }
       if (p.decoder) {
         // the tile's mixture planes (contiguous: utterances utt0 .. utt0 + U - 1) are wanted in L2 by the decoder phase
         const int n_utt = p.B - utt0 < p.U ? p.B - utt0 : p.U;
@@ -620,9 +673,16 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       for (int l = 0; l < p.n_layers; ++l) {
         // ---- per-layer vectors: first item of the layer in the weight stream (it was prefetched under the previous
         // layer's FFN); the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
-        const uint32_t per_tile = static_cast<uint32_t>(p.n_layers * p.items_per_layer + (p.decoder ? 1 + 8 + 4 * p.nc3 : 0));
-        const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(l * p.items_per_layer);
+        const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + (p.decoder ? 1 + 8 + 4 * p.nc3 : 0));
+        const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + l * p.items_per_layer);
         const uint32_t vslot = vn % NSLOT;
+        if (l == 0 && p.pro_taps) {
+          // the projection items went through the same ring slots: only once they are all consumed does a wait on the
+          // slot's parity mean "the vector block has landed" (a waiter may be at most one phase behind)
+          mbar_wait(x_ready, lt & 1);
+          tc_fence_after();
+          XTRACE(1);                                         // projection complete
+        }
         named_bar_sync(5, 512);                              // every row warp is done with the previous vectors
         if (l > 0 && etid < D) pend[etid] = vec[VEC_B2 + etid];
         mbar_wait(&w_full[vslot], (vn / NSLOT) & 1);
@@ -637,6 +697,31 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         tc_fence_after();
         const int tb = 2 + l * 60;     // row-thread stamps of layer l: +0 LN1 start, +1 LN1 done; per head 6; +26.. FFN
         XTRACE(tb);
+        if (l == 0 && p.pro_taps) {
+          // input projection epilogue, in place: X = act(X + b0) + PE[t] (32 columns at a time)
+          const float* per = p.pe + static_cast<size_t>(row_valid ? r - klo : 0) * D + part * 64;
+          const float* b0 = vec + VEC_B0 + part * 64;
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            float4 pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pv[i] = __ldg(reinterpret_cast<const float4*>(per + hc * 32) + i);
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmX + lane_sel + part * 64 + hc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(b0 + hc * 32 + 4 * i);
+              float x0 = __uint_as_float(v[4 * i]) + b4.x, x1 = __uint_as_float(v[4 * i + 1]) + b4.y;
+              float x2 = __uint_as_float(v[4 * i + 2]) + b4.z, x3 = __uint_as_float(v[4 * i + 3]) + b4.w;
+              if (p.pro_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+              v[4 * i] = __float_as_uint(x0 + pv[i].x); v[4 * i + 1] = __float_as_uint(x1 + pv[i].y);
+              v[4 * i + 2] = __float_as_uint(x2 + pv[i].z); v[4 * i + 3] = __float_as_uint(x3 + pv[i].w);
+            }
+            tmem_st_32x32b_x32(tmX + lane_sel + part * 64 + hc * 32, v);
+          }
+          tmem_st_wait();
+        }
         ln_to_a(l > 0 ? pend : nullptr, vec + VEC_N1G, vec + VEC_N1B);
         XTRACE(tb + 1);
 
@@ -863,8 +948,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         XTRACE(107);                                         // decoder: final LayerNorm done
         // decoder vector block (b0 [512] | b3 [nc3 * 128]): next item of the weight stream
         {
-          const uint32_t per_tile = static_cast<uint32_t>(p.n_layers * p.items_per_layer + 1 + 8 + 4 * p.nc3);
-          const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(p.n_layers * p.items_per_layer);
+          const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + 1 + 8 + 4 * p.nc3);
+          const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer);
           const uint32_t vslot = vn % NSLOT;
           named_bar_sync(5, 512);                            // every row warp has read the last layer's vectors
           mbar_wait(&w_full[vslot], (vn / NSLOT) & 1);
@@ -1143,7 +1228,7 @@ void xformer_pack_cross(const float* wq, const float* wo, const float* w1, const
 }
 
 void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const float* b1, const float* b2, const float* n1g,
-                       const float* n1b, const float* n2g, const float* n2b, float* dst) {
+                       const float* n1b, const float* n2g, const float* n2b, float* dst, const float* b0) {
   memset(dst, 0, sizeof(float) * VEC_FLOATS);
   memcpy(dst + VEC_BQKV, bqkv, sizeof(float) * n_bqkv);
   memcpy(dst + VEC_BO, bo, sizeof(float) * D);
@@ -1153,6 +1238,19 @@ void xformer_pack_vecs(const float* bqkv, int n_bqkv, const float* bo, const flo
   memcpy(dst + VEC_N1B, n1b, sizeof(float) * D);
   memcpy(dst + VEC_N2G, n2g, sizeof(float) * D);
   memcpy(dst + VEC_N2B, n2b, sizeof(float) * D);
+  if (b0 != nullptr) memcpy(dst + VEC_B0, b0, sizeof(float) * D);
+}
+
+// Input projection items (ahead of layer 0): item (tap, k-slab) = W_tap[:, 64 ks .. +64) as two 128-row slabs
+size_t xformer_pro_bytes(int taps, int K) { return static_cast<size_t>(taps) * (K / 64) * ITEM; }
+void xformer_pack_pro(const float* W, int ld, int col_stride, int taps, int K, uint8_t* dst) {
+  std::vector<float> tile(static_cast<size_t>(D) * 64);
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ks = 0; ks < K / 64; ++ks, dst += ITEM) {
+      for (int n = 0; n < D; ++n)
+        for (int k = 0; k < 64; ++k) tile[n * 64 + k] = W[static_cast<size_t>(n) * ld + static_cast<size_t>(ks * 64 + k) * col_stride + tap];
+      for (int hf = 0; hf < 2; ++hf) put_tile(dst + hf * SLAB, tile.data(), 64, hf * 128, 128, 0);
+    }
 }
 
 // SeparationDecoder block of the fusion stream (after the last layer): vector block (b0 [512] | b3 in packed column
@@ -1192,7 +1290,12 @@ bool xformer_stack_usable(int prec, int d_model, int nhead, int len) {
 const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num_sms) {
   if (sp.B <= 0 || sp.L <= 0 || sp.L > 128 || sp.n_layers <= 0) return "xformer_stack: bad problem";
   const bool decoder = sp.masks != nullptr;
+  const bool pro = sp.pro_a != nullptr;
   if (!sp.out_x && !sp.out_op && !decoder) return "xformer_stack: no output requested";
+  if (pro && (sp.cross || (sp.pro_taps != 1 && sp.pro_taps != 3) || sp.pro_k < 64 || sp.pro_k % 64 != 0 || sp.pe == nullptr ||
+              sp.pro_pitch < sp.L + sp.pro_taps - 1 || sp.pro_rows < 1))
+    return "xformer_stack: bad input projection";
+  if (!pro && sp.x_in == nullptr) return "xformer_stack: no input";
   if (decoder) {
     if (!sp.cross || sp.out_x || sp.out_op || !sp.mixed || !sp.separated || sp.F < 1 || sp.S < 1)
       return "xformer_stack: the fused decoder follows the fusion stack and replaces its outputs";
@@ -1214,8 +1317,14 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   const int M = sp.B * sp.L;
   const int n_tiles = (sp.B + U - 1) / U;
   CUtensorMap tin, tout, top, tkv;
-  if (const char* e = enc2d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.x_in, D, M, D, 32, sp.L)) return e;
-  tout = tin; top = tin; tkv = tin;
+  if (pro) {
+    if (const char* e = enc2d(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, sp.pro_a, sp.pro_k, sp.pro_rows, sp.pro_k, 64, stride)) return e;
+    tin = tkv;
+  } else {
+    if (const char* e = enc2d(&tin, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.x_in, D, M, D, 32, sp.L)) return e;
+    tkv = tin;
+  }
+  tout = tin; top = tin;
   if (sp.out_x)
     if (const char* e = enc2d(&tout, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, sp.out_x, D, M, D, 32, sp.L)) return e;
   if (sp.out_op)
@@ -1232,6 +1341,7 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   d.kv_ld_layer = 2 * D;
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
   d.trace = sp.trace;
+  d.pro_taps = pro ? sp.pro_taps : 0; d.pro_ks = sp.pro_k / 64; d.pro_pitch = sp.pro_pitch; d.pro_relu = sp.pro_relu; d.pe = sp.pe;
   d.decoder = decoder ? 1 : 0;
   d.SF = sp.S * sp.F; d.F = sp.F; d.S = sp.S; d.nc3 = decoder ? xformer_decoder_chunks(sp.S, sp.F) : 0;
   d.mixed = sp.mixed; d.masks = sp.masks; d.separated = sp.separated;
