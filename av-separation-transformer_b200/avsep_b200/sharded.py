@@ -99,7 +99,7 @@ class ShardedForward:
     """
 
     def __init__(self, backend, forward_fn, per_rank_batch: int, shapes: dict, rank: int, world: int,
-                 n_input_sets: int = 1, group=None):
+                 n_input_sets: int = 1, group=None, copy_lanes: int = 1):
         self.mem, self.fwd = backend, forward_fn
         self.B, self.rank, self.world, self.group = int(per_rank_batch), int(rank), int(world), group
         self.n_sets = int(n_input_sets)
@@ -140,6 +140,13 @@ class ShardedForward:
             self.loc_out = [(self.mem.empty((B,) + self.shapes["out"]), self.mem.empty((B,) + self.shapes["out"]))
                             for _ in range(2)]
             self.s_in, self.s_out = self.mem.stream(), self.mem.stream()
+            # copy_lanes > 1: every transfer is cut into that many pieces on extra streams (more copy engines and more
+            # requests in flight per rank; tools/nvlink_probe.py: the root's links carry more when both directions run)
+            self.lanes = max(1, int(copy_lanes))
+            self.x_in = [self.mem.stream() for _ in range(self.lanes - 1)]
+            self.x_out = [self.mem.stream() for _ in range(self.lanes - 1)]
+            self.ev_lane = [self.mem.event() for _ in range(2 * (self.lanes - 1))]
+            self.ev_go = [self.mem.event() for _ in range(2)]
             self.ev_in_ready = [self.mem.event() for _ in range(2)]
             self.ev_fwd_done = [self.mem.event() for _ in range(2)]
             self.ev_out_free = [self.mem.event() for _ in range(2)]
@@ -162,8 +169,9 @@ class ShardedForward:
         if self.used[b]:
             self.s_in.wait_event(self.ev_fwd_done[b])
         off = self.lo
-        self.mem.copy(m.data_ptr(), self.ptr[f"in{s_set}.mixed"] + 4 * off * self.per["mixed"], self.B * self.per["mixed"], self.s_in)
-        self.mem.copy(f.data_ptr(), self.ptr[f"in{s_set}.frames"] + 4 * off * self.per["frames"], self.B * self.per["frames"], self.s_in)
+        self._copy(self.s_in, self.x_in, 0, [
+            (m.data_ptr(), self.ptr[f"in{s_set}.mixed"] + 4 * off * self.per["mixed"], self.B * self.per["mixed"]),
+            (f.data_ptr(), self.ptr[f"in{s_set}.frames"] + 4 * off * self.per["frames"], self.B * self.per["frames"])])
         self.ev_in_ready[b].record(self.s_in)
         # forward on the shard, once its inputs have landed and the push that last read these outputs is done
         comp.wait_event(self.ev_in_ready[b])
@@ -173,10 +181,32 @@ class ShardedForward:
         self.ev_fwd_done[b].record(comp)
         # gather: push the shard's outputs into the root's global buffers
         self.s_out.wait_event(self.ev_fwd_done[b])
-        self.mem.copy(self.ptr[f"out{b}.sep"] + 4 * off * self.per["out"], sep.data_ptr(), self.B * self.per["out"], self.s_out)
-        self.mem.copy(self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"], self.s_out)
+        self._copy(self.s_out, self.x_out, 1, [
+            (self.ptr[f"out{b}.sep"] + 4 * off * self.per["out"], sep.data_ptr(), self.B * self.per["out"]),
+            (self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"])])
         self.ev_out_free[b].record(self.s_out)
         self.used[b] = True
+
+    def _copy(self, lead, extra, which, jobs):
+        """jobs: [(dst_ptr, src_ptr, nfloats)] on the lead stream, or cut into len(extra) + 1 pieces each, one piece per
+        stream; the lead stream ends up ordered after every piece."""
+        if not extra:
+            for dst, src, n in jobs:
+                self.mem.copy(dst, src, n, lead)
+            return
+        k = len(extra) + 1
+        self.ev_go[which].record(lead)
+        for lane, st in enumerate([lead] + extra):
+            if lane:
+                st.wait_event(self.ev_go[which])
+            for dst, src, n in jobs:
+                lo, hi = (n * lane // k) & ~3, n if lane == k - 1 else (n * (lane + 1) // k) & ~3     # 16-byte pieces
+                if hi > lo:
+                    self.mem.copy(dst + 4 * lo, src + 4 * lo, hi - lo, st)
+            if lane:
+                ev = self.ev_lane[which * (k - 1) + lane - 1]
+                ev.record(st)
+                lead.wait_event(ev)
 
     def finish(self):
         """All enqueued scatters, forwards and gathers of every rank are complete when this returns."""

@@ -137,6 +137,8 @@ struct avsep_handle {
   bool xs_f_decoder = false;   // the fusion stream continues with the SeparationDecoder block
   const uint8_t *xs_a_np = nullptr, *xs_v_np = nullptr;   // encoder streams past their input-projection items
   bool fuse_proj = true;       // Conv1d #2 / frame_proj inside the encoder stack kernels (option "fuse_proj")
+  bool xs_v_kvp = false;       // the visual stream ends with the fusion layers' K | V projection block
+  bool fuse_kvp = true;        // interpolation + K | V projection inside the visual stack kernel (option "fuse_kvp")
   bool fuse_decoder = true;    // run the decoder inside the fusion stack kernel (option "fuse_decoder")
   bool fuse_stack = true;   // whole encoder / fusion stacks in one persistent kernel (d_model = 256, 4 heads, bf16, len <= 128)
   // cached library-owned workspace
@@ -380,9 +382,13 @@ bool stack_fusable(const avsep_handle* h, int len) {
 // A whole stack in one kernel (xformer_stack_sm100.cu).  which: 0 audio encoder, 1 visual encoder, 2 fusion.
 int run_stack(avsep_handle* h, cudaStream_t s, int which, const float* x_in, float* out_x, void* out_op,
               const float* fin_g, const float* fin_b, const void* kv, int kv_ld, int B, int L, long long* trace = nullptr,
-              const float* mixed = nullptr, float* separated = nullptr, float* masks = nullptr, const void* pro_a = nullptr) {
+              const float* mixed = nullptr, float* separated = nullptr, float* masks = nullptr, const void* pro_a = nullptr,
+              void* kvp_out = nullptr, int kvp_L = 0) {
   StackProblem sp{};
   sp.trace = trace;
+  if (kvp_out != nullptr) {      // which 1: the fusion layers' K | V rows are produced inside the kernel
+    sp.kvp_out = kvp_out; sp.kvp_L = kvp_L; sp.kvp_n = h->cfg.num_fusion_layers * 2 * h->cfg.d_model; sp.kvp_ld = sp.kvp_n;
+  }
   if (pro_a != nullptr) {        // x_in is produced inside the kernel (which 0: Conv1d #2 + ReLU + PE; 1: frame_proj + PE)
     sp.pro_a = pro_a; sp.pro_relu = which == 0;
     sp.pro_taps = which == 0 ? 3 : 1; sp.pro_k = which == 0 ? h->cfg.d_model : 128;
@@ -502,12 +508,14 @@ int visual_frontend(avsep_handle* h, cudaStream_t s, Workspace& w, const float* 
 // encoder output, L_src rows per utterance).  Out: a_op = fusion.norm(x) in bf16.
 // with_decoder (out: *decoded = true): SeparationDecoder runs inside the same kernel and writes separated / masks.
 int fusion_stack_fused(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src, const float* mixed, float* separated,
-                       float* masks, bool* decoded) {
+                       float* masks, bool* decoded, bool have_kv = false) {
   h->prof_stream = s;
   const int d = h->cfg.d_model, B = w.B, T = w.T;
   const int Ma = B * T, Lf = h->cfg.num_fusion_layers;
-  CKL("lerp_kv", launch_lerp_rows(s, w.x_v, d, B, L_src, T, d, w.attn_a, d));
-  if (linear(h, s, "gemm.cross_kv", w.attn_a, Ma, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, nullptr, w.kvb)) return 1;
+  if (!have_kv) {                // else the visual stack kernel has already written w.kvb
+    CKL("lerp_kv", launch_lerp_rows(s, w.x_v, d, B, L_src, T, d, w.attn_a, d));
+    if (linear(h, s, "gemm.cross_kv", w.attn_a, Ma, d, h->wkv_all, h->bkv_all, Lf * 2 * d, ACT_NONE, nullptr, w.kvb)) return 1;
+  }
   *decoded = h->fuse_decoder && h->xs_f_decoder && !h->debug && masks != nullptr;
   if (*decoded)
     return run_stack(h, s, 2, w.x_a, nullptr, nullptr, h->fng, h->fnb, w.kvb, Lf * 2 * d, B, T, nullptr, mixed, separated, masks);
@@ -602,11 +610,15 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   const bool ff = fa && fv;            // the fused fusion stack reads the fp32 residual rows of both encoders
   // --- visual branch (enqueued first: its CNN is the longest kernel) ---
   const bool fp = h->fuse_proj && !h->debug;     // input projections inside the stack kernels (no stage snapshots then)
+  bool kvp = false;
   if (visual_frontend(h, sv, w, frames, h->enc_v[0].n1g, h->enc_v[0].n1b, fv, fv && fp)) return 1;
   if (fv) {
     // out: x_v (fp32) for the interpolation in front of the K/V projection; v_op (bf16 cast) only for the unfused fusion
-    if (run_stack(h, sv, 1, w.x_v, w.x_v, ff ? nullptr : w.v_op, nullptr, nullptr, nullptr, 0, w.B, w.N, nullptr, nullptr,
-                  nullptr, nullptr, fp ? w.pooled : nullptr))
+    // fused K | V projection: needs the fused fusion stack behind it and the audio frames inside a visual tile slot
+    kvp = ff && h->fuse_kvp && h->xs_v_kvp && !h->debug &&
+          xformer_kvp_usable(h->cfg.num_fusion_layers * 2 * d, w.N, w.T);
+    if (run_stack(h, sv, 1, w.x_v, kvp ? nullptr : w.x_v, (ff || kvp) ? nullptr : w.v_op, nullptr, nullptr, nullptr, 0, w.B,
+                  w.N, nullptr, nullptr, nullptr, nullptr, fp ? w.pooled : nullptr, kvp ? w.kvb : nullptr, w.T))
       return 1;
   } else if (encoder_stack(h, sv, h->enc_v, w.B, w.N, w.x_v, w.y_v, w.v_op, w.qkv_v, w.attn_v, w.ffn_v, nullptr, nullptr)) {
     return 1;
@@ -630,7 +642,7 @@ int forward_device(avsep_handle* h, cudaStream_t s, Workspace& w, const float* m
   // --- fusion + decoder ---
   if (ff) {
     bool decoded = false;
-    if (fusion_stack_fused(h, s, w, w.N, mixed, separated, masks, &decoded)) return 1;
+    if (fusion_stack_fused(h, s, w, w.N, mixed, separated, masks, &decoded, kvp)) return 1;
     if (decoded) return 0;
   } else if (fusion_stack(h, s, w, w.N)) {
     return 1;
@@ -1010,7 +1022,10 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
       // the stream starts with the input projection (Conv1d #2 as 3 taps x 256 / frame_proj as 1 x 128), whose bias
       // rides in layer 0's vector block
       const size_t pro_bytes = stack == 0 ? xformer_pro_bytes(3, static_cast<int>(d)) : xformer_pro_bytes(1, 128);
-      std::vector<uint8_t> stream(pro_bytes + static_cast<size_t>(Le) * xformer_stream_bytes(false));
+      const int n_kv = static_cast<int>(Lf * 2 * d);
+      const bool with_kvp = stack == 1 && xformer_kvp_usable(n_kv, 1, 1);
+      std::vector<uint8_t> stream(pro_bytes + static_cast<size_t>(Le) * xformer_stream_bytes(false) +
+                                  (with_kvp ? xformer_kvp_bytes(n_kv) : 0));
       const HostTensor* b0t = nullptr;
       if (stack == 0) {
         GETW(wc, "audio_encoder.input_proj.2.weight", d, d, 3);
@@ -1043,6 +1058,18 @@ int avsep_finalize_weights(avsep_handle* h, void* cuda_stream) {
                           l == 0 ? b0t->data.data() : nullptr);
         xformer_pack_self(wqkv->data.data(), wo->data.data(), w1->data.data(), w2->data.data(), vecs.data(),
                           stream.data() + pro_bytes + static_cast<size_t>(l) * xformer_stream_bytes(false));
+      }
+      if (with_kvp) {
+        std::vector<float> wkv(static_cast<size_t>(n_kv) * d), bkv(n_kv);
+        for (int l = 0; l < Lf; ++l) {
+          const std::string p = "fusion.layers." + std::to_string(l);
+          GETW(win, p + ".cross_attn.in_proj_weight", 3 * d, d);
+          GETW(bin, p + ".cross_attn.in_proj_bias", 3 * d);
+          memcpy(wkv.data() + static_cast<size_t>(l) * 2 * d * d, win->data.data() + d * d, sizeof(float) * 2 * d * d);
+          memcpy(bkv.data() + static_cast<size_t>(l) * 2 * d, bin->data.data() + d, sizeof(float) * 2 * d);
+        }
+        xformer_pack_kvp(wkv.data(), bkv.data(), n_kv, stream.data() + pro_bytes + static_cast<size_t>(Le) * xformer_stream_bytes(false));
+        h->xs_v_kvp = true;
       }
       off[stack == 0 ? "xs_a" : "xs_v"] = ar.add(stream.data(), stream.size());
     }
@@ -1678,6 +1705,7 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_stack") == 0) { h->fuse_stack = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_decoder") == 0) { h->fuse_decoder = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "fuse_proj") == 0) { h->fuse_proj = value != 0; drop_graphs(h); return 0; }
+  if (strcmp(name, "fuse_kvp") == 0) { h->fuse_kvp = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "ffn_fused_min_rows") == 0) { h->ffn_fused_min_rows = value; drop_graphs(h); return 0; }
   if (strcmp(name, "two_stream") == 0) { h->two_stream = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "attn_small") == 0) { attention_set_small(value != 0); drop_graphs(h); return 0; }

@@ -116,6 +116,11 @@ struct StackProblem {
   const void* pro_a = nullptr;           // bf16 [pro_rows, pro_k]
   int pro_rows = 0, pro_pitch = 0, pro_taps = 0, pro_k = 0, pro_relu = 0;
   const float* pe = nullptr;             // fp32 [>= L, 256]
+  // K | V projection of the fusion layers fused behind the last layer (self stacks; replaces out_x / out_op): the
+  // output rows, interpolated to kvp_L rows per utterance, times the kvp_n stacked K | V weight rows -> bf16
+  // [B * kvp_L, kvp_ld]; the stream then ends with xformer_kvp_bytes(kvp_n) of items (xformer_pack_kvp)
+  void* kvp_out = nullptr;
+  int kvp_L = 0, kvp_n = 0, kvp_ld = 0;
   const float* mixed = nullptr;          // (B, F, L) fp32
   float *masks = nullptr, *separated = nullptr;   // (B, S, F, L) fp32
   int F = 0, S = 0;
@@ -127,6 +132,9 @@ void xformer_pack_decoder(const float* w0, const float* b0, const float* w3, con
 size_t xformer_pro_bytes(int taps, int K);
 // W element (n, tap, k) at W[n * ld + k * col_stride + tap]: Conv1d weight (out, in, 3): ld = 3 in, col_stride = 3
 void xformer_pack_pro(const float* W, int ld, int col_stride, int taps, int K, uint8_t* dst);
+bool xformer_kvp_usable(int n, int L_src, int L_out);
+size_t xformer_kvp_bytes(int n);
+void xformer_pack_kvp(const float* wkv, const float* bkv, int n, uint8_t* dst);   // wkv [n, 256] row-major, bkv [n]
 bool xformer_stack_usable(int prec, int d_model, int nhead, int len);
 size_t xformer_stream_bytes(bool cross);
 int xformer_vec_floats();

@@ -89,6 +89,13 @@ struct StackDev {
   //   visual (model.py:108-110): frame_proj Linear(128 -> 256) on the pooled CNN features, + PE
   int pro_taps, pro_ks, pro_pitch, pro_relu;
   const float* pe;
+  // K | V projection of the fusion layers fused behind the last layer (visual stack; replaces out_x / out_op): the
+  // stack output rows are interpolated to kvp_L rows per utterance (F.interpolate linear, align_corners=False;
+  // model.py:114-116) and multiplied by the kvp_chunks * 128 stacked K | V weight rows of every fusion layer
+  // (model.py:155,169; functional.py:5847-5865): out = bf16 [B * kvp_L, kvp_ld].  kvp_chunks == 0: off.
+  int kvp_chunks, kvp_L, kvp_ld;
+  float kvp_scale;              // L / kvp_L
+  __nv_bfloat16* kvp_out;
   long long* trace;             // optional [grid][256] clock64 stamps of the CTA's first tile (debug), else null:
                                 //   row thread (warp 2 lane 0) in [0,128), MMA thread in [128,256); see tools/stack_trace.py
 };
@@ -155,7 +162,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   uint64_t* pa_full = bars + 26;           // [4] input projection: A slab landed
   uint64_t* pa_free = bars + 30;           // [4] input projection: the MMAs have read the A slab
   uint64_t* x_ready = bars + 34;           // input projection complete (X holds the pre-activation rows)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 35);
+  uint64_t* kv_stage_free = bars + 35;     // (16) K|V projection: the fp32 staging in the ring has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
   float2* red = reinterpret_cast<float2*>(smem + OFF_RED);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
   float* pend = reinterpret_cast<float*>(smem + OFF_PEND);
@@ -189,6 +197,7 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     mbar_init(v_ready, 16);
     for (int i = 0; i < 4; ++i) { mbar_init(&pa_full[i], 1); mbar_init(&pa_free[i], 1); }
     mbar_init(x_ready, 1);
+    mbar_init(kv_stage_free, 16);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < D; i += STACK_THREADS) {
@@ -287,6 +296,11 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           const uint8_t* src = p.wstream + static_cast<size_t>(n_pro + p.n_layers * p.items_per_layer) * ITEM;
           const int n = 1 + 8 + 4 * p.nc3;
           for (int i = 0; i < n; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
+        }
+        if (p.kvp_chunks) {
+          const uint8_t* src = p.wstream + static_cast<size_t>(n_pro + p.n_layers * p.items_per_layer) * ITEM;
+          mbar_wait(kv_stage_free, lt & 1);       // the ring doubled as the fp32 staging of the interpolation
+          for (int i = 0; i < 1 + 2 * p.kvp_chunks; ++i) load_item(src + static_cast<size_t>(i) * ITEM);
         }
       }
     }
@@ -533,6 +547,36 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             XTRACE(115 + c);                        // decoder: output chunk c issued
           }
           for (int c = p.nc3 < 2 ? 0 : p.nc3 - 2; c < p.nc3; ++c) wait_h();
+        }
+        if (p.kvp_chunks) {
+          auto wait_h = [&]() {
+            const uint32_t st2 = c2n & 1;
+            mbar_wait(&h_full[st2], (c2n >> 1) & 1);
+            tc_fence_after();
+            ++c2n;
+          };
+          ++wn;                                     // K | V bias block (row warps)
+          mbar_wait(a_ready, n_a & 1); ++n_a;       // interpolated rows in shared memory
+          tc_fence_after();
+          for (int c = 0; c < p.kvp_chunks; ++c, ++c1n) {
+            const uint32_t st = c1n & 1;
+            if (c >= 2) wait_h();
+            for (int it = 0; it < 2; ++it) {
+              const uint32_t base = next_item();
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int ks = 2 * it + half;
+                const uint64_t adesc = umma_desc_kmajor_sw128(a_base + ks * SLAB, 1024);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(base + half * SLAB, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_f16(tmW + st * 128, adesc + 2 * kk, bdesc + 2 * kk, ID128, (ks | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit(&w_empty[cur_slot]);
+            }
+            umma_commit(&acc1_full[st]);
+          }
+          for (int c = p.kvp_chunks < 2 ? 0 : p.kvp_chunks - 2; c < p.kvp_chunks; ++c) wait_h();
         }
       }
     }
@@ -1062,6 +1106,99 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         named_bar_sync(5, 512);
         XTRACE(127);                                         // tile done
         if (elected) mbar_arrive(stage_free);
+      } else if (p.kvp_chunks) {
+        // ---- K | V rows of the fusion layers from this tile's output (model.py:114-116 then 155,169) ----
+        // 1. x = X + last linear2 bias -> fp32 staging rows in the (idle) weight ring + K/V tile area: 1 KB per row,
+        //    16-byte chunks XOR-swizzled by the row so that thread-per-row accesses are conflict-free
+        uint8_t* const stg = smem + OFF_RING;
+        {
+          uint32_t vu[64];
+          float sum, sq;
+          read_x(vu, vec + VEC_B2, false, sum, sq);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            *reinterpret_cast<uint4*>(stg + r * 1024 + (((part * 16 + i) ^ (r & 7)) << 4)) =
+                make_uint4(vu[4 * i], vu[4 * i + 1], vu[4 * i + 2], vu[4 * i + 3]);
+        }
+        named_bar_sync(5, 512);
+        // 2. linear interpolation along time (ATen upsample_linear1d, align_corners = False) -> bf16 A operand
+        {
+          const int t = r - klo;
+          const bool live = t < p.kvp_L;
+          const float sp = fmaxf(p.kvp_scale * (static_cast<float>(t) + 0.5f) - 0.5f, 0.0f);
+          int i0 = static_cast<int>(sp);
+          if (i0 > p.L - 1) i0 = p.L - 1;
+          const int i1 = min(i0 + 1, p.L - 1);
+          const float w1 = sp - static_cast<float>(i0), w0 = 1.0f - w1;
+          const int r0 = klo + i0, r1 = klo + i1;
+          uint8_t* slab = smem + OFF_A + part * SLAB;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (live) {
+              const float4 a0 = *reinterpret_cast<const float4*>(stg + r0 * 1024 + (((part * 16 + 2 * c) ^ (r0 & 7)) << 4));
+              const float4 a1 = *reinterpret_cast<const float4*>(stg + r0 * 1024 + (((part * 16 + 2 * c + 1) ^ (r0 & 7)) << 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(stg + r1 * 1024 + (((part * 16 + 2 * c) ^ (r1 & 7)) << 4));
+              const float4 b1 = *reinterpret_cast<const float4*>(stg + r1 * 1024 + (((part * 16 + 2 * c + 1) ^ (r1 & 7)) << 4));
+              w.x = pack_bf16x2(w0 * a0.x + w1 * b0.x, w0 * a0.y + w1 * b0.y);
+              w.y = pack_bf16x2(w0 * a0.z + w1 * b0.z, w0 * a0.w + w1 * b0.w);
+              w.z = pack_bf16x2(w0 * a1.x + w1 * b1.x, w0 * a1.y + w1 * b1.y);
+              w.w = pack_bf16x2(w0 * a1.z + w1 * b1.z, w0 * a1.w + w1 * b1.w);
+            }
+            *reinterpret_cast<uint4*>(slab + soff(r, c)) = w;
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(kv_stage_free); mbar_arrive(a_ready); }
+        }
+        // 3. bias block: next item of the weight stream
+        {
+          const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + 1 + 2 * p.kvp_chunks);
+          const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer);
+          const uint32_t vslot = vn % NSLOT;
+          named_bar_sync(5, 512);                            // every row warp has read the last layer's vectors
+          mbar_wait(&w_full[vslot], (vn / NSLOT) & 1);
+          const float4* src = reinterpret_cast<const float4*>(smem + OFF_RING + vslot * ITEM);
+          float4* dst = reinterpret_cast<float4*>(vec);
+          for (int i = etid; i < p.kvp_chunks * 128 / 4; i += 512) dst[i] = src[i];
+          named_bar_sync(5, 512);
+          if (etid == 0) mbar_arrive(&w_empty[vslot]);
+        }
+        // 4. per 128-column chunk: accumulator + bias -> bf16 -> 64 contiguous bytes of the row in global memory
+        {
+          const int utt = utt0 + r / p.stride, t = r - klo;
+          const bool out_ok = t < p.kvp_L && utt < p.B;
+          __nv_bfloat16* orow = p.kvp_out + (static_cast<size_t>(out_ok ? utt : 0) * p.kvp_L + (out_ok ? t : 0)) * p.kvp_ld + part * 32;
+          for (int c = 0; c < p.kvp_chunks; ++c, ++c1n) {
+            const uint32_t st = c1n & 1;
+            mbar_wait(&acc1_full[st], (c1n >> 1) & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmW + lane_sel + st * 128 + part * 32, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_full[st]);
+            if (out_ok) {
+              const float* bj = vec + c * 128 + part * 32;
+              uint4* o = reinterpret_cast<uint4*>(orow + c * 128);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 ba = *reinterpret_cast<const float4*>(bj + 8 * i), bb = *reinterpret_cast<const float4*>(bj + 8 * i + 4);
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(v[8 * i]) + ba.x, __uint_as_float(v[8 * i + 1]) + ba.y);
+                w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + ba.z, __uint_as_float(v[8 * i + 3]) + ba.w);
+                w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + bb.x, __uint_as_float(v[8 * i + 5]) + bb.y);
+                w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + bb.z, __uint_as_float(v[8 * i + 7]) + bb.w);
+                o[i] = w;
+              }
+            }
+          }
+        }
+        named_bar_sync(5, 512);
+        XTRACE(127);                                         // tile done
+        if (elected) mbar_arrive(stage_free);
       } else
       // ---- stack output: x + last linear2 bias -> fp32 residual rows and / or (final LayerNorm | cast) bf16 rows ----
       {
@@ -1253,6 +1390,24 @@ void xformer_pack_pro(const float* W, int ld, int col_stride, int taps, int K, u
     }
 }
 
+// K | V projection block behind the last layer of a self stack: bias block | per 128-row chunk of wkv two items
+// (k-slab pairs), as linear1 chunks are packed
+size_t xformer_kvp_bytes(int n) { return static_cast<size_t>(1 + 2 * (n / 128)) * ITEM; }
+bool xformer_kvp_usable(int n, int L_src, int L_out) {
+  if (n < 128 || n % 128 != 0 || n > VEC_FLOATS || L_src < 1 || L_src > 128 || L_out < 1) return false;
+  int U = 1;
+  while (U < 16 && 2 * U * L_src <= 128) U *= 2;
+  return L_out <= 128 / U;                       // the interpolated rows of an utterance stay inside its tile slot
+}
+void xformer_pack_kvp(const float* wkv, const float* bkv, int n, uint8_t* dst) {
+  memset(dst, 0, xformer_kvp_bytes(n));
+  memcpy(dst, bkv, sizeof(float) * n);
+  dst += ITEM;
+  for (int c = 0; c < n / 128; ++c)
+    for (int it = 0; it < 2; ++it, dst += ITEM)
+      for (int half = 0; half < 2; ++half) put_tile(dst + half * SLAB, wkv, D, c * 128, 128, (2 * it + half) * 64);
+}
+
 // SeparationDecoder block of the fusion stream (after the last layer): vector block (b0 [512] | b3 in packed column
 // order), Linear(256 -> 512) as 8 items (chunk j, k-slab pair), Linear(512 -> S*F) as 4 items per 128-column chunk.
 // Packed column order: column i of chunk c is frequency bin c * 128/S + i / S of speaker i % S (zero rows past F).
@@ -1291,7 +1446,11 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   if (sp.B <= 0 || sp.L <= 0 || sp.L > 128 || sp.n_layers <= 0) return "xformer_stack: bad problem";
   const bool decoder = sp.masks != nullptr;
   const bool pro = sp.pro_a != nullptr;
-  if (!sp.out_x && !sp.out_op && !decoder) return "xformer_stack: no output requested";
+  const bool kvp = sp.kvp_out != nullptr;
+  if (!sp.out_x && !sp.out_op && !decoder && !kvp) return "xformer_stack: no output requested";
+  if (kvp && (sp.cross || sp.out_x || sp.out_op || !xformer_kvp_usable(sp.kvp_n, sp.L, sp.kvp_L) || sp.kvp_ld < sp.kvp_n ||
+              sp.kvp_ld % 8 != 0 || (reinterpret_cast<uintptr_t>(sp.kvp_out) & 15) != 0))
+    return "xformer_stack: bad K|V projection";
   if (pro && (sp.cross || (sp.pro_taps != 1 && sp.pro_taps != 3) || sp.pro_k < 64 || sp.pro_k % 64 != 0 || sp.pe == nullptr ||
               sp.pro_pitch < sp.L + sp.pro_taps - 1 || sp.pro_rows < 1))
     return "xformer_stack: bad input projection";
@@ -1342,6 +1501,9 @@ const char* launch_xformer_stack(cudaStream_t s, const StackProblem& sp, int num
   d.qscale = 1.4426950408889634f / 8.0f;       // log2(e) / sqrt(head dim 64)
   d.trace = sp.trace;
   d.pro_taps = pro ? sp.pro_taps : 0; d.pro_ks = sp.pro_k / 64; d.pro_pitch = sp.pro_pitch; d.pro_relu = sp.pro_relu; d.pe = sp.pe;
+  d.kvp_chunks = kvp ? sp.kvp_n / 128 : 0; d.kvp_L = sp.kvp_L; d.kvp_ld = sp.kvp_ld;
+  d.kvp_scale = kvp ? static_cast<float>(sp.L) / static_cast<float>(sp.kvp_L) : 0.f;
+  d.kvp_out = static_cast<__nv_bfloat16*>(sp.kvp_out);
   d.decoder = decoder ? 1 : 0;
   d.SF = sp.S * sp.F; d.F = sp.F; d.S = sp.S; d.nc3 = decoder ? xformer_decoder_chunks(sp.S, sp.F) : 0;
   d.mixed = sp.mixed; d.masks = sp.masks; d.separated = sp.separated;

@@ -409,7 +409,8 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         from avsep_b200.sharded import PeerMemoryCuda, ShardedForward
         shapes = dict(mixed=(F, T), frames=(N, HW, HW), out=(S, F, T))
-        sg = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets)
+        sg = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets,
+                            copy_lanes=int(os.environ.get("AVSEP_COPY_LANES", "1")))
         if rank == 0:
             for s_i, (gm, gf) in enumerate(sg.root_in):
                 for r in range(world):

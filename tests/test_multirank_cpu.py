@@ -121,7 +121,7 @@ def _fake_forward(mixed, frames, sep, masks):
         sep[:, s] = masks[:, s] * mixed
 
 
-def _sharded_worker(rank, world, port, out):
+def _sharded_worker(rank, world, port, out, lanes=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from avsep_b200.sharded import ShardedForward, shard_slices
@@ -129,7 +129,7 @@ def _sharded_worker(rank, world, port, out):
     try:
         B, shapes = 3, dict(mixed=(5, 7), frames=(4, 2, 2), out=(2, 5, 7))
         assert shard_slices(world, B) == [(0, 3), (3, 6)]
-        sf = ShardedForward(be, _fake_forward, B, shapes, rank, world, n_input_sets=3)
+        sf = ShardedForward(be, _fake_forward, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes)
         if rank == 0:
             g = torch.Generator().manual_seed(0)
             for m, f in sf.root_in:
@@ -166,3 +166,12 @@ def test_sharded_forward_scatter_gather_world_two_gloo():
         mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
         assert out["ok"] is True, dict(out)
         assert out["bytes"] == (4 * 3 * (35 + 16), 4 * 3 * 2 * 70)
+
+
+def test_sharded_forward_with_three_copy_lanes_world_two_gloo():
+    """Every transfer cut into three pieces on three streams (the 8-GPU configuration): the pieces tile each shard."""
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_sharded_worker, args=(world, port, out, 3), nprocs=world, join=True)
+        assert out["ok"] is True, dict(out)
