@@ -592,6 +592,9 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     const bool row_valid = (r - klo) < p.L;                  // tile rows past the utterance's length are padding
     // this row's valid score columns within the part: [lo_i, hi_i)
     const int lo_i = klo - part * 32, hi_i = klo + p.L - part * 32;
+    // stream items per tile: input projection | layers | decoder block or K|V projection block
+    const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + (p.decoder ? 1 + 8 + 4 * p.nc3 : 0) +
+                                                    (p.kvp_chunks ? 1 + 2 * p.kvp_chunks : 0));
     uint32_t nx = 0;                                         // exchanges through `red` so far (double buffered)
     uint32_t n_h = 0, n_attn = 0, n_ffn = 0, c1n = 0;
     const int trace_base = (threadIdx.x == 64) ? 0 : 1024;   // only the first row thread stamps
@@ -717,7 +720,6 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       for (int l = 0; l < p.n_layers; ++l) {
         // ---- per-layer vectors: first item of the layer in the weight stream (it was prefetched under the previous
         // layer's FFN); the previous layer's linear2 bias is carried into this layer's first LayerNorm ----
-        const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + (p.decoder ? 1 + 8 + 4 * p.nc3 : 0));
         const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + l * p.items_per_layer);
         const uint32_t vslot = vn % NSLOT;
         if (l == 0 && p.pro_taps) {
@@ -992,7 +994,6 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         XTRACE(107);                                         // decoder: final LayerNorm done
         // decoder vector block (b0 [512] | b3 [nc3 * 128]): next item of the weight stream
         {
-          const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + 1 + 8 + 4 * p.nc3);
           const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer);
           const uint32_t vslot = vn % NSLOT;
           named_bar_sync(5, 512);                            // every row warp has read the last layer's vectors
@@ -1154,7 +1155,6 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         }
         // 3. bias block: next item of the weight stream
         {
-          const uint32_t per_tile = static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer + 1 + 2 * p.kvp_chunks);
           const uint32_t vn = static_cast<uint32_t>(lt) * per_tile + static_cast<uint32_t>(n_pro + p.n_layers * p.items_per_layer);
           const uint32_t vslot = vn % NSLOT;
           named_bar_sync(5, 512);                            // every row warp has read the last layer's vectors
