@@ -159,7 +159,6 @@ struct avsep_handle {
   size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
   int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
-  bool ffn_cg2 = false;  // experimental: fused FFN on CTA pairs (tcgen05 cta_group::2), see ffn_fused_cg2_sm100.cu
   bool pdl = true;       // programmatic dependent launch between consecutive kernels of a stream
   int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
   void* host_ws = nullptr;
@@ -430,7 +429,7 @@ int encoder_stack(avsep_handle* h, cudaStream_t s, const std::vector<EncLayerW>&
     const float* g = last ? final_g : layers[l + 1].n1g;
     const float* b = last ? final_b : layers[l + 1].n1b;
     if (h->fuse_ffn && ffn_fusable(prec, d) && M >= h->ffn_fused_min_rows) {
-      CKL("ffn.fused", (h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x,
+      CKL("ffn.fused", launch_ffn_fused(s, a_op, w.w1, w.b1, w.w2, w.b2, ACT_RELU, x, x,
                                                                              g, b, a_op, M, h->num_sms, nullptr));
     } else {
       if (linear(h, s, "gemm.ffn1", a_op, M, d, w.w1, w.b1, 4 * d, ACT_RELU, nullptr, ffn)) return 1;
@@ -558,7 +557,7 @@ int fusion_stack(avsep_handle* h, cudaStream_t s, Workspace& w, int L_src) {
     const float* g = last ? h->fng : h->fus[l + 1].n1g;
     const float* b = last ? h->fnb : h->fus[l + 1].n1b;
     if (h->fuse_ffn && ffn_fusable(prec, d) && Ma >= h->ffn_fused_min_rows) {
-      CKL("ffn.fused", (h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU,
+      CKL("ffn.fused", launch_ffn_fused(s, w.a_op, fw.w1, fw.b1, fw.w2, fw.b2, ACT_GELU,
                                                                              w.x_a, w.x_a, g, b, w.a_op, Ma, h->num_sms,
                                                                              nullptr));
     } else {
@@ -1644,7 +1643,7 @@ int avsep_test_ffn_fused(avsep_handle* h, const void* a, const void* w1, const f
                          const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
                          void* out_op, int32_t M, void* cuda_stream) {
   if (!h) return 1;
-  CK((h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
+  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
                                                              x_inout, x_inout, gamma, beta, out_op, M, h->num_sms, nullptr));
   return 0;
 }
@@ -1655,7 +1654,7 @@ int avsep_test_ffn_fused_trace(avsep_handle* h, const void* a, const void* w1, c
                                const float* b2, int32_t act, float* x_inout, const float* gamma, const float* beta,
                                void* out_op, int32_t M, unsigned long long* trace_dev, void* cuda_stream) {
   if (!h) return 1;
-  CK((h->ffn_cg2 ? launch_ffn_fused_cg2 : launch_ffn_fused)(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
+  CK(launch_ffn_fused(static_cast<cudaStream_t>(cuda_stream), a, w1, b1, w2, b2, act,
                                                              x_inout, x_inout, gamma, beta, out_op, M, h->num_sms, trace_dev));
   return 0;
 }
@@ -1696,7 +1695,6 @@ int avsep_set_option(avsep_handle* h, const char* name, int32_t value) {
   if (strcmp(name, "fuse_ln") == 0) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "host_chunk") == 0) { h->host_chunk = value; return 0; }
   if (strcmp(name, "host_lanes") == 0) { h->host_lanes = value; return 0; }
-  if (strcmp(name, "ffn_cg2") == 0) { h->ffn_cg2 = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "pdl") == 0) { h->pdl = value != 0; pdl_set(h->pdl && !h->profile); drop_graphs(h); return 0; }
   if (strcmp(name, "cnn_tc") == 0) { h->cnn_tc = value != 0; drop_graphs(h); return 0; }
   if (strcmp(name, "cnn_ig") == 0) { h->cnn_ig = value != 0; drop_graphs(h); return 0; }

@@ -137,15 +137,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // The watchdog's slow path is a real function call: inlined, its printf argument set-up added ~25 instructions to every
 // wait, and the persistent multi-role kernels are instruction-cache bound (32 KB L1.5 per SM, three roles running
 // different code at once).
-static __device__ __noinline__ void mbar_timeout() {
-  printf("avsep: mbarrier watchdog fired (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  // the barrier's shared-memory offset identifies the wait site (barriers sit in one block per kernel)
+  printf("avsep: mbarrier watchdog fired (block %d,%d thread %d, barrier at smem +%u, parity %u)\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, static_cast<unsigned>(__cvta_generic_to_shared(bar)), parity);
   __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout();
+    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout(bar, parity);
   }
 }
 
@@ -167,7 +169,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 1000u)) {
-    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout();
+    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout(bar, parity);
   }
 }
 
@@ -349,7 +351,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout();
+    if (clock64() - t0 > AVSEP_WATCHDOG_CYCLES) mbar_timeout(bar, parity);
   }
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -88,12 +88,6 @@ const char* launch_ffn_fused(cudaStream_t s, const void* a, const void* w1, cons
                              const float* b2, int act, const float* resid, float* x_out, const float* gamma,
                              const float* beta, void* out_op, int M, int num_sms,
                              unsigned long long* trace = nullptr);
-// cta_group::2 variant (CTA pairs, half of every weight slab per CTA); experimental, see ffn_fused_cg2_sm100.cu
-const char* launch_ffn_fused_cg2(cudaStream_t s, const void* a, const void* w1, const float* b1, const void* w2,
-                             const float* b2, int act, const float* resid, float* x_out, const float* gamma,
-                             const float* beta, void* out_op, int M, int num_sms,
-                             unsigned long long* trace = nullptr);
-
 // A whole transformer stack in one persistent kernel (xformer_stack_sm100.cu): d_model = 256, 4 heads, bf16, sequences of
 // at most 128 rows.  The residual tile stays in tensor memory through every layer; weights stream as prepacked images.
 struct StackProblem {

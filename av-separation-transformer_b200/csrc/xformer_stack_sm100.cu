@@ -500,7 +500,8 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             tc_fence_after();
             ++c2n;
           };
-          ++wn;                                     // decoder vector block (row warps)
+          mbar_wait(&w_full[wn % NSLOT], (wn / NSLOT) & 1);   // decoder vector block (row warps): see it land (as below)
+          ++wn;
           mbar_wait(a_ready, n_a & 1); ++n_a;       // a = fusion.norm(x) in shared memory
           tc_fence_after();
           XTRACE(112);                              // decoder: a seen
@@ -555,7 +556,12 @@ xformer_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             tc_fence_after();
             ++c2n;
           };
-          ++wn;                                     // K | V bias block (row warps)
+          // K | V bias block: consumed by the row warps, but this thread must see it land before it moves on -- three
+          // items later it waits on the same ring slot, and a parity wait is only unambiguous one phase behind (the
+          // producer issues the block when the staging is released, i.e. at the same moment this thread starts; the
+          // next two items can overtake it)
+          mbar_wait(&w_full[wn % NSLOT], (wn / NSLOT) & 1);
+          ++wn;
           mbar_wait(a_ready, n_a & 1); ++n_a;       // interpolated rows in shared memory
           tc_fence_after();
           for (int c = 0; c < p.kvp_chunks; ++c, ++c1n) {

@@ -398,9 +398,15 @@ def run_ours(args, rank, local_rank, world):
             sampler.stop()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
 
+    def phase(msg):       # AVSEP_BENCH_VERBOSE=1: progress markers on stderr (locating a failure in a multi-rank run)
+        if os.environ.get("AVSEP_BENCH_VERBOSE"):
+            torch.cuda.synchronize()
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(args.warmup):
         step(i)
+    phase("warm-up done")
     launches_per_step = eng.launch_count()
     ms_sharded = timed(step, args.steps, 0, sampler)
 
@@ -437,7 +443,9 @@ def run_ours(args, rank, local_rank, world):
             wall = time.perf_counter() - t0
             return max_over_ranks(e0.elapsed_time(e1)) / steps, max_over_ranks(wall * 1e3) / steps
 
+        phase("sharded (no traffic) timed; scatter/gather buffers ready")
         ms_sg, ms_sg_wall = sg_timed(args.steps, max(args.warmup, 4))
+        phase("scatter/gather timed")
         # verify the gathered result on the root: shard r of the last step == the root's own forward of those inputs
         verified = None
         if rank == 0:
@@ -476,6 +484,7 @@ def run_ours(args, rank, local_rank, world):
         clocks = None
     barrier()
 
+    phase("headline done")
     # ---- python_api: the drop-in module call `model(mixed, frames)` (what a user of the reference writes) -------------
     def python_api_ms(bsz, steps):
         ms_in = [(m[:bsz].contiguous(), f[:bsz].contiguous()) for m, f in sets]
@@ -596,8 +605,10 @@ def run_ours(args, rank, local_rank, world):
             dist.gather(sep2, ga_s, dst=0)
             dist.gather(masks2, ga_m, dst=0)
 
+        phase("e2e / copy rounds done")
         n_g = max(6, min(args.steps, 30))
         ms_nccl = timed(nccl_step, n_g, 3)
+        phase("nccl scatter/gather done")
         extras_multi["nccl_scatter_gather_fp32"] = {
             "ms_per_step": round(ms_nccl, 4), "value": throughput(world, B, ms_nccl),
             "what": "same data path with dist.scatter / dist.gather (NCCL send/recv kernels, in stream order, no overlap)"}
@@ -611,6 +622,7 @@ def run_ours(args, rank, local_rank, world):
                 "global_batch": B, "per_gpu_batch": bs, "ms_per_step": round(ms_strong, 4),
                 "value": throughput(world, bs, ms_strong),
                 "what": "BASELINE.md reading of configs[1]: the fixed global batch split over the GPUs, outputs stay sharded"}
+        phase("strong scaling done")
         sweep = {}
         for bs in (8, 64, 1024):                       # configs[4]: per-GPU batch sweep (no traffic), this N
             ins = [synthetic_batch(bs, F, T, N, HW, HW, seed=7 + lo, device=dev)]
@@ -620,6 +632,7 @@ def run_ours(args, rank, local_rank, world):
             del ins, o_s, o_m
         extras_multi["per_gpu_batch_sweep"] = sweep
 
+    phase("multi-GPU extras done")
     # ---- per-kernel pass (same steps again, every launch bracketed by CUDA events on the launching stream) ----
     eng.set_profile(True)
     eng.profile_report(reset=True)

@@ -117,7 +117,6 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
  *   "epilogue_tma" (1)       TMA-slab GEMM epilogues (0: cooperative stores)
  *   "fuse_ffn" (1)           one kernel per feed-forward sub-layer when d_model = 256, bf16, rows >= ffn_fused_min_rows
  *   "ffn_fused_min_rows" (2048)
- *   "ffn_cg2" (0)            experimental cta_group::2 variant of the fused feed-forward kernel
  *   "cnn_tc" (1)             tcgen05 CNN for 32x32 frames (0: generic mma.sync kernel)
  *   "attn_tc" (1)            1: tcgen05 attention when min(Lq, Lk) >= attn_tc_min_len; 0: never; 2: whenever usable
  *   "attn_tc_min_len" (96)

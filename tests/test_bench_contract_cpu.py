@@ -45,4 +45,11 @@ def test_multi_gpu_line_is_whole_job_throughput():
     d = json.load(open(_latest("r[0-9]_v*_bench_n8.json")))
     assert BASE <= set(d) and d["n_gpus"] == 8 and d["config"]["global_batch"] == 8 * 256
     assert abs(d["value"] - 8 * 256 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
-    assert "outputs_gathered_to_rank0" in d
+    # round 2: the headline IS the north-star data path (inputs scattered from rank 0, separated + masks gathered to it,
+    # inside the timed region); the no-traffic variant and the transfer accounting ride beside it
+    assert "scattered" in d["config"]["parallelism"] and "gathered" in d["config"]["parallelism"]
+    assert {"ms_per_step", "value"} <= set(d["sharded_no_traffic"])
+    sg = d["scatter_gather"]
+    assert sg["gathered_equals_local_forward"] is True
+    assert sg["bytes_out_of_rank0_per_step"] == 7 * d["e2e"]["h2d_bytes_per_step"]
+    assert sg["bytes_into_rank0_per_step"] == 7 * d["e2e"]["d2h_bytes_per_step"]

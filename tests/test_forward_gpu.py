@@ -127,6 +127,28 @@ def test_more_tiles_than_sms_gives_the_same_rows():
         assert np.array_equal(masks_s, masks[sub]) and np.array_equal(sep_s, sep[sub]), sub
 
 
+def test_repeated_many_tile_forwards_are_stable():
+    """Stress for ordering bugs between the kernel's roles that only show with several tiles per CTA and back-to-back
+    graph replays (a ring-slot parity wait two phases behind hung 1 run in 3 here before the MMA role was made to
+    observe the K|V bias block landing): 150 forwards of 1024 utterances, every result bit-identical to the first."""
+    cfg = CONFIGS["default"]
+    P = make_state_dict(cfg, seed=44, gain=2.0)
+    B, T, N = 1024, 63, 50
+    mixed, frames = make_inputs(cfg, 64, T, N, 32, 32, seed=44, kind="dataset")
+    model = build_model(cfg, P, "bf16")
+    dev = torch.device("cuda", model.engine.device)
+    m = torch.from_numpy(mixed).to(dev).repeat(B // 64, 1, 1).contiguous()
+    f = torch.from_numpy(frames).to(dev).repeat(B // 64, 1, 1, 1).contiguous()
+    sep0, masks0 = model(m, f)
+    sep0, masks0 = sep0.clone(), masks0.clone()
+    assert torch.equal(masks0[:64], masks0[64:128])                  # the same utterances in other tiles of other CTAs
+    for it in range(150):
+        sep, masks = model(m, f)
+        if it % 25 == 24:
+            assert torch.equal(masks, masks0) and torch.equal(sep, sep0), it
+    torch.cuda.synchronize()
+
+
 def test_host_buffer_entry_point_matches_device_entry_point():
     cfg = CONFIGS["tiny2"]
     P = make_state_dict(cfg, seed=51, gain=2.0)

@@ -56,9 +56,8 @@ def test_gemm_tcgen05(eng, M, N, K, act, bn):
     assert err < 2e-3, err
 
 
-@pytest.mark.parametrize("cg2", [0, 1])
 @pytest.mark.parametrize("M,act", [(128, 1), (1000, 1), (16128, 1), (12800, 2), (77, 2), (148 * 128 + 300, 1)])
-def test_ffn_fused(eng, M, act, cg2):
+def test_ffn_fused(eng, M, act):
     """linear1 -> ReLU / GELU -> linear2 -> +residual -> LayerNorm in one kernel (hidden stays on chip)."""
     g = torch.Generator(device="cuda").manual_seed(M + act)
     d, hid = 256, 1024
@@ -75,14 +74,10 @@ def test_ffn_fused(eng, M, act, cg2):
     x_ref = x + hdn.bfloat16().float() @ w2.float().t() + b2        # the hidden is rounded to bf16 between the GEMMs
     ln_ref = torch.nn.functional.layer_norm(x_ref, (d,), gamma, beta, 1e-5)
     out = torch.zeros(M, d, device="cuda", dtype=torch.bfloat16)
-    eng.set_option("ffn_cg2", cg2)          # 1 = the experimental cta_group::2 kernel (CTA pairs)
-    try:
-        _check(eng, eng.lib.avsep_test_ffn_fused(eng.h, a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                                 b2.data_ptr(), act, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                 out.data_ptr(), M, _s()))
-        torch.cuda.synchronize()
-    finally:
-        eng.set_option("ffn_cg2", 0)
+    _check(eng, eng.lib.avsep_test_ffn_fused(eng.h, a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                             b2.data_ptr(), act, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                             out.data_ptr(), M, _s()))
+    torch.cuda.synchronize()
     assert (x - x_ref).abs().max().item() < 2e-2          # bf16 rounding of the hidden at a different point of the tie
     assert (x - x_ref).abs().mean().item() < 2e-4
     assert (out.float() - ln_ref).abs().max().item() < 6e-2

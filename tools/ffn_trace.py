@@ -5,7 +5,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "av-separation-transformer_b200"))
 from avsep_b200.engine import Engine, EngineConfig
 eng = Engine(EngineConfig(65, 64, 4, 1, 1, 2, "bf16"), 0)
-eng.set_option("ffn_cg2", int(os.environ.get("FFN_CG2", "0")))
 for M, act in ((16128, 1), (16128, 2)):
     d, hid = 256, 1024
     a = torch.randn(M, d, device="cuda").bfloat16()
