@@ -136,7 +136,7 @@ def test_repeated_many_tile_forwards_are_stable():
     B, T, N = 1024, 63, 50
     mixed, frames = make_inputs(cfg, 64, T, N, 32, 32, seed=44, kind="dataset")
     model = build_model(cfg, P, "bf16")
-    dev = torch.device("cuda", model.engine.device)
+    dev = torch.device("cuda")
     m = torch.from_numpy(mixed).to(dev).repeat(B // 64, 1, 1).contiguous()
     f = torch.from_numpy(frames).to(dev).repeat(B // 64, 1, 1, 1).contiguous()
     sep0, masks0 = model(m, f)
