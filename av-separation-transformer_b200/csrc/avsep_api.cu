@@ -263,6 +263,7 @@ int check_shape(avsep_handle* h, int B, int T, int N, int Hh, int Ww) {
   if (!h->finalized) return fail(h, "weights not finalized: call avsep_finalize_weights first");
   if (B < 1 || T < 1 || N < 1 || Hh < 1 || Ww < 1) return fail(h, "empty input: B, T, N, H, W must be >= 1");
   if (T > 5000 || N > 5000) return fail(h, "sequence longer than the positional table (max_len=5000, model.py:286)");
+  if (B > 65535) return fail(h, "batch above 65535 utterances per call (grid dimension of the per-utterance kernels): split it");
   return 0;
 }
 

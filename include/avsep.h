@@ -115,6 +115,12 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
 /* Execution options (A/B switches; every position is parity-tested).  name -> meaning (default):
  *   "fuse_ln" (1)            residual + LayerNorm inside the GEMM epilogue (0: separate add+LayerNorm kernel)
  *   "epilogue_tma" (1)       TMA-slab GEMM epilogues (0: cooperative stores)
+ *   "fuse_stack" (1)         every layer of an encoder / fusion stack in one persistent kernel when d_model = 256, 4 heads,
+ *                            bf16 and the clip has at most 128 frames (xformer_stack_sm100.cu); the switches below refine it
+ *   "fuse_proj" (1)          ... with Conv1d #2 + ReLU + PE / frame_proj + PE fused in front of the encoder stacks
+ *   "fuse_kvp" (1)           ... with the interpolation + K|V projection of the fusion layers fused behind the visual stack
+ *   "fuse_decoder" (1)       ... with the final LayerNorm + SeparationDecoder fused behind the fusion stack
+ *   "cnn_ig" (0)             shifted-view implicit-GEMM CNN (visual_cnn_ig_sm100.cu) instead of the TMEM-im2col one
  *   "fuse_ffn" (1)           one kernel per feed-forward sub-layer when d_model = 256, bf16, rows >= ffn_fused_min_rows
  *   "ffn_fused_min_rows" (2048)
  *   "cnn_tc" (1)             tcgen05 CNN for 32x32 frames (0: generic mma.sync kernel)
@@ -126,6 +132,7 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
  *   "pdl" (1)                programmatic dependent launch between consecutive kernels
  *   "host_chunk" (64), "host_lanes" (2)   avsep_forward_host pipeline: utterances per chunk, concurrent compute lanes
  *   "profile_spin_us"        length of the GPU spin kernel that precedes a profiled forward
+ * The environment variable AVSEP_OPTS="name=value,name=value" applies options at avsep_create (measurement runs).
  * Kernel-selection switches ("epilogue_tma", "attn_tc", "attn_tc_min_len", "attn_small", "pdl") are process-wide:
  * they apply to every handle of the process, not only to `h`. */
 AVSEP_API int avsep_set_option(avsep_handle* h, const char* name, int32_t value);
