@@ -158,9 +158,9 @@ struct avsep_handle {
   float* synth_waves = nullptr;   // scratch of avsep_synth_batch
   size_t synth_cap = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
-  int host_chunk = 64;   // utterances per pipeline chunk of avsep_forward_host
+  int host_chunk = 0;    // utterances per pipeline chunk of the host path; 0 = auto (see host_submit)
   bool pdl = true;       // programmatic dependent launch between consecutive kernels of a stream
-  int host_lanes = 2;    // chunks whose kernels may be in flight at once (each lane has its own stream + workspace)
+  int host_lanes = 0;    // chunks whose kernels may be in flight at once (own stream + workspace each); 0 = auto
   void* host_ws = nullptr;
   size_t host_ws_bytes = 0;
   cudaStream_t host_comp[3] = {nullptr, nullptr, nullptr};
@@ -1182,7 +1182,7 @@ int avsep_forward(avsep_handle* h, const float* mixed_spec, const float* lip_fra
 
 namespace {
 int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int B, int T, int N, int Hh, int Ww,
-                float* separated, float* masks, int slot_id, cudaStream_t s) {
+                float* separated, float* masks, int slot_id, cudaStream_t s, bool streaming) {
   // Software pipeline over chunks of the batch: H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1 run
   // concurrently on separate streams (PCIe is full duplex), so a call costs ~max(copy-in, compute, copy-out); the
   // two slots extend the same pipeline across consecutive calls.
@@ -1213,7 +1213,14 @@ int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frame
     return 0;
   };
   if (make_event(sl.ev_start) || make_event(sl.ev_end)) return 1;
-  const int Bc = h->host_chunk > 0 && h->host_chunk < B ? h->host_chunk : B;
+  // Chunk size: a stack kernel takes as long for 64 utterances as for 256 (one tile per CTA either way), so chunks are
+  // a trade between pipelining inside one call and kernel time.  Measured at B = 256 (tools/e2e_probe.py): the one-call
+  // form is fastest with ~56-utterance chunks on two compute lanes (copy-in of chunk i+1 under the kernels of chunk i),
+  // the streaming form - where consecutive calls overlap anyway - with 128-utterance chunks on one lane (161 k against
+  // 140 k utt-s/s with 64 x 2).
+  const int auto_chunk = streaming ? 128 : 56;
+  const int want_chunk = h->host_chunk > 0 ? h->host_chunk : auto_chunk;
+  const int Bc = want_chunk < B ? want_chunk : B;
   std::vector<int> starts, sizes;
   for (int b0 = 0; b0 < B; b0 += Bc) {
     starts.push_back(b0);
@@ -1227,7 +1234,8 @@ int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frame
   }
   // one workspace + compute stream per lane: with small chunks a single forward cannot fill the GPU, so the kernels
   // of consecutive chunks are allowed to overlap
-  const int lanes = h->host_lanes < 1 ? 1 : (h->host_lanes > 3 ? 3 : h->host_lanes);
+  const int want_lanes = h->host_lanes > 0 ? h->host_lanes : (streaming ? 1 : 2);
+  const int lanes = want_lanes > 3 ? 3 : want_lanes;
   Workspace wl[3];
   const size_t per_lane = carve_workspace(h, wl[0], nullptr, Bc, T, N, Hh, Ww);
   if (h->host_ws_bytes < per_lane * lanes) {
@@ -1293,7 +1301,7 @@ int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frame
 int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B, int32_t T,
                        int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream) {
   if (!h) return 1;
-  if (host_submit(h, mixed_spec, lip_frames, B, T, N, Hh, Ww, separated, masks, 0, static_cast<cudaStream_t>(cuda_stream)))
+  if (host_submit(h, mixed_spec, lip_frames, B, T, N, Hh, Ww, separated, masks, 0, static_cast<cudaStream_t>(cuda_stream), false))
     return 1;
   CUDA_OK(cudaEventSynchronize(h->slot[0].ev_end));
   return 0;
@@ -1304,7 +1312,7 @@ int avsep_forward_host_async(avsep_handle* h, const float* mixed_spec, const flo
                              void* cuda_stream) {
   if (!h) return 1;
   return host_submit(h, mixed_spec, lip_frames, B, T, N, Hh, Ww, separated, masks, slot,
-                     static_cast<cudaStream_t>(cuda_stream));
+                     static_cast<cudaStream_t>(cuda_stream), true);
 }
 
 int avsep_host_wait(avsep_handle* h, int32_t slot) {

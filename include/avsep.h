@@ -130,7 +130,8 @@ AVSEP_API int avsep_debug_get_stage(avsep_handle* h, const char* name, float* ho
  *   "use_graph" (1)          CUDA-graph replay keyed by (shape, buffers)
  *   "two_stream" (1)         audio and visual branches on two streams
  *   "pdl" (1)                programmatic dependent launch between consecutive kernels
- *   "host_chunk" (64), "host_lanes" (2)   avsep_forward_host pipeline: utterances per chunk, concurrent compute lanes
+ *   "host_chunk" (0), "host_lanes" (0)    host-buffer pipeline: utterances per chunk, concurrent compute lanes; 0 = auto
+ *                            (56 x 2 lanes for avsep_forward_host, 128 x 1 lane for avsep_forward_host_async)
  *   "profile_spin_us"        length of the GPU spin kernel that precedes a profiled forward
  * The environment variable AVSEP_OPTS="name=value,name=value" applies options at avsep_create (measurement runs).
  * Kernel-selection switches ("epilogue_tma", "attn_tc", "attn_tc_min_len", "attn_small", "pdl") are process-wide:

@@ -36,7 +36,7 @@ def stream_run(n):
         if i >= 2: eng.host_wait(sl)
         eng.forward_host_async(mixed, frames, outs[sl][0], outs[sl][1], sl)
     eng.host_wait(0); eng.host_wait(1)
-for chunk, lanes in [(64, 1), (64, 2), (96, 2), (128, 1), (128, 2), (256, 1), (32, 2), (48, 2)]:
+for chunk, lanes in [tuple(int(v) for v in x.split("x")) for x in os.environ.get("E2E_GRID", "64x1,64x2,96x2,128x1,128x2,256x1,32x2,48x2").split(",")]:
     eng.set_option("host_chunk", chunk); eng.set_option("host_lanes", lanes)
     for _ in range(3): eng.forward_host(mixed, frames, sep, masks)
     ms = timed(lambda: eng.forward_host(mixed, frames, sep, masks), 10)
