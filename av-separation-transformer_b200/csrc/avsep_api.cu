@@ -153,7 +153,7 @@ struct avsep_handle {
     std::vector<cudaEvent_t> ev;                            // 2 per chunk: copy-in done, kernels done
     cudaEvent_t ev_start = nullptr, ev_end = nullptr;       // ev_end: last copy-out done
     cudaEvent_t ev_lane[3] = {nullptr, nullptr, nullptr};   // last kernels of this slot on each compute lane
-  } slot[2];
+  } slot[AVSEP_HOST_SLOTS];
   std::vector<void*> shared_owned, shared_mapped;   // avsep_shared_alloc / avsep_shared_open
   float* synth_waves = nullptr;   // scratch of avsep_synth_batch
   size_t synth_cap = 0;
@@ -1187,7 +1187,7 @@ int host_submit(avsep_handle* h, const float* mixed_spec, const float* lip_frame
   // concurrently on separate streams (PCIe is full duplex), so a call costs ~max(copy-in, compute, copy-out); the
   // two slots extend the same pipeline across consecutive calls.
   if (!mixed_spec || !lip_frames || !separated || !masks) return fail(h, "avsep_forward_host: null buffer");
-  if (slot_id < 0 || slot_id > 1) return fail(h, "avsep_forward_host_async: slot must be 0 or 1");
+  if (slot_id < 0 || slot_id >= AVSEP_HOST_SLOTS) return fail(h, "avsep_forward_host_async: slot must be 0 .. AVSEP_HOST_SLOTS - 1");
   if (check_shape(h, B, T, N, Hh, Ww)) return 1;
   CUDA_OK(cudaSetDevice(h->cfg.device));
   avsep_handle::HostSlot& sl = h->slot[slot_id];
@@ -1317,7 +1317,7 @@ int avsep_forward_host_async(avsep_handle* h, const float* mixed_spec, const flo
 
 int avsep_host_wait(avsep_handle* h, int32_t slot) {
   if (!h) return 1;
-  if (slot < 0 || slot > 1) return fail(h, "avsep_host_wait: slot must be 0 or 1");
+  if (slot < 0 || slot >= AVSEP_HOST_SLOTS) return fail(h, "avsep_host_wait: slot must be 0 .. AVSEP_HOST_SLOTS - 1");
   if (h->slot[slot].ev_end == nullptr) return 0;       // nothing was ever submitted on this slot
   CUDA_OK(cudaSetDevice(h->cfg.device));
   CUDA_OK(cudaEventSynchronize(h->slot[slot].ev_end));

@@ -81,11 +81,13 @@ AVSEP_API int avsep_forward_host(avsep_handle* h, const float* mixed_spec, const
                        int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks, void* cuda_stream);
 
 /* Streaming form of avsep_forward_host for back-to-back batches (the demo.py:45-50 loop over a dataset): enqueues the
- * copy-in / kernels / copy-out pipeline of one batch on I/O slot 0 or 1 and returns; avsep_host_wait(slot) returns
- * when that slot's results are in the host buffers.  Alternating the two slots overlaps the copy-in of batch i+1 with
- * the kernels and copy-out of batch i.  Host buffers must be pinned for the copies to be asynchronous, and must stay
+ * copy-in / kernels / copy-out pipeline of one batch on I/O slot 0 .. AVSEP_HOST_SLOTS - 1 and returns;
+ * avsep_host_wait(slot) returns when that slot's results are in the host buffers.  Cycling through the slots overlaps
+ * the copy-in of batch i+1 with the kernels and copy-out of batch i (two slots are enough for that; a third keeps both
+ * PCIe directions busy across the hand-over).  Host buffers must be pinned for the copies to be asynchronous, and must stay
  * valid (inputs) / untouched (outputs) until the wait.  A slot is reused only after its previous batch has finished
  * with its device buffers (ordered on the device; the caller only has to wait before reading results). */
+#define AVSEP_HOST_SLOTS 4
 AVSEP_API int avsep_forward_host_async(avsep_handle* h, const float* mixed_spec, const float* lip_frames, int32_t B,
                                        int32_t T, int32_t N, int32_t Hh, int32_t Ww, float* separated, float* masks,
                                        int32_t slot, void* cuda_stream);

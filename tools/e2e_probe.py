@@ -28,14 +28,14 @@ def both():
     with torch.cuda.stream(s2): d2h()
 print(json.dumps({"h2d_ms": timed(h2d), "d2h_ms": timed(d2h), "both_ms": timed(both),
                   "h2d_MB": (mixed.numel() + frames.numel()) * 4 / 1e6, "d2h_MB": 2 * sep.numel() * 4 / 1e6}), flush=True)
-sep2 = torch.empty_like(sep).pin_memory(); masks2 = torch.empty_like(masks).pin_memory()
-outs = [(sep, masks), (sep2, masks2)]
+NS = int(os.environ.get("E2E_SLOTS", "2"))
+outs = [(sep, masks)] + [(torch.empty_like(sep).pin_memory(), torch.empty_like(masks).pin_memory()) for _ in range(NS - 1)]
 def stream_run(n):
     for i in range(n):
-        sl = i % 2
-        if i >= 2: eng.host_wait(sl)
+        sl = i % NS
+        if i >= NS: eng.host_wait(sl)
         eng.forward_host_async(mixed, frames, outs[sl][0], outs[sl][1], sl)
-    eng.host_wait(0); eng.host_wait(1)
+    for sl in range(NS): eng.host_wait(sl)
 for chunk, lanes in [tuple(int(v) for v in x.split("x")) for x in os.environ.get("E2E_GRID", "64x1,64x2,96x2,128x1,128x2,256x1,32x2,48x2").split(",")]:
     eng.set_option("host_chunk", chunk); eng.set_option("host_lanes", lanes)
     for _ in range(3): eng.forward_host(mixed, frames, sep, masks)
