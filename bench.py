@@ -436,19 +436,26 @@ def run_ours(args, rank, local_rank, world):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
             e0.record(stream)
             for i in range(steps):
                 sg.step(i)
+                marks[i].record(stream)           # diagnostic only: forward-to-forward intervals of this rank
             if rank != 0:
                 stream.wait_stream(sg.s_in)
                 stream.wait_stream(sg.s_out)      # this rank's last push is inside its timed interval
             e1.record(stream)
             sg.finish()
             wall = time.perf_counter() - t0
-            return max_over_ranks(e0.elapsed_time(e1)) / steps, max_over_ranks(wall * 1e3) / steps
+            per = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+            spread = {"median_step_ms": round(max_over_ranks(per[len(per) // 2]), 4),
+                      "slowest_step_ms": round(max_over_ranks(per[-1]), 4)}
+            return max_over_ranks(e0.elapsed_time(e1)) / steps, max_over_ranks(wall * 1e3) / steps, spread
 
         phase("sharded (no traffic) timed; scatter/gather buffers ready")
-        ms_sg, ms_sg_wall = sg_timed(args.steps, max(args.warmup, 4))
+        # warm-up covers every (input set, output buffer) pair of the root: 3 x 2 CUDA graphs, the first two uses of a
+        # pair run eagerly / capture (forward_cached), so 12 steps keep graph instantiation out of the timed region
+        ms_sg, ms_sg_wall, sg_spread = sg_timed(args.steps, max(args.warmup, 2 * 2 * n_sets))
         phase("scatter/gather timed")
         # verify the gathered result on the root: shard r of the last step == the root's own forward of those inputs
         verified = None
@@ -729,6 +736,8 @@ def run_ours(args, rank, local_rank, world):
         out["sharded_no_traffic"] = sharded_entry
         out["scatter_gather"] = {
             "ms_per_step_device": round(ms_sg, 4), "ms_per_step_wall": round(ms_sg_wall, 4),
+            "step_spread": dict(sg_spread, what="forward-to-forward intervals inside the timed region, max over ranks "
+                                                "(diagnostic: a one-off stall shows as slowest >> median)"),
             "bytes_out_of_rank0_per_step": sg.bytes_in_per_step * (world - 1),
             "bytes_into_rank0_per_step": sg.bytes_out_per_step * (world - 1),
             "rank0_egress_gbs": round(sg.bytes_in_per_step * (world - 1) / (ms_per_step * 1e-3) / 1e9, 1),
