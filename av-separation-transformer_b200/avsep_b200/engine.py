@@ -305,6 +305,17 @@ class Engine:
         self._check(rc, "avsep_decoder")
         return sep, masks
 
+    def separate(self, masks, mixed, out=None):
+        """avsep_separate: SeparationDecoder.separate (reference model.py:210-220), masks (B,S,F,T) x mixed (B,F,T)."""
+        masks = self._dev_f32(masks, "masks")
+        mixed = self._dev_f32(mixed, "mixed_spec")
+        B, T, _, _, _ = self._check_inputs("separate", mixed=mixed, out=(masks,) if out is None else (masks, out))
+        sep = torch.empty_like(masks) if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self.lib.avsep_separate(self.h, masks.data_ptr(), mixed.data_ptr(), B, T, sep.data_ptr(), self._stream())
+        self._check(rc, "avsep_separate")
+        return sep
+
     # ---- rows either side of the path --------------------------------------------------------------
     def synth_batch(self, geom: dict, amps, freqs, phases, noise=None, want_clean: bool = True):
         """avsep_synth_batch: device tensors amps/freqs/phases (B,S) float64, noise (B,S,nf,ph,pw) float32 or None.

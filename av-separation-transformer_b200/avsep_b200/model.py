@@ -274,8 +274,9 @@ class SeparationDecoder(_InferenceOnly):
         return self._run("decoder", fused, ones)[1]
 
     def separate(self, masks: torch.Tensor, mixed_spec: torch.Tensor) -> torch.Tensor:
-        # model.py:210-220; stand-alone use only -- in the full model the multiply is fused into the decoder epilogue
-        return masks * mixed_spec.unsqueeze(1)
+        # model.py:210-220 through avsep_separate; stand-alone use only -- in the full model the multiply is fused
+        # into the decoder epilogue.  One fp32 multiply per element: bit-identical to the reference's product.
+        return self._run("separate", masks, mixed_spec)
 
 
 class AVSeparationTransformer(_InferenceOnly):

@@ -18,6 +18,15 @@ The root computes its own shard in place (zero copy).  Local input / output buff
 with events; the root's output buffers are double buffered as well, so a consumer on the root can read step i-1 while
 step i is being written.
 
+``gather="masks"`` ("gather only masks, the root recomputes separated = masks x mixed, which it already
+holds") halves the bytes into the root: a rank pushes its ``masks`` shard only and then raises a ticket in the root's
+memory (``avsep_flag_signal``, same stream, so it lands after the data); the root's rebuild stream waits for every
+rank's ticket (``avsep_flag_wait``: a one-CTA kernel polling the root's own memory -- no host round trip, no
+collective), runs ``avsep_separate`` over the remote shards -- one fp32 multiply per element, bit-identical to what
+the remote decoder epilogue wrote -- and acknowledges with a ticket in every rank's memory, which is what a rank
+waits for before it overwrites that output slot two steps later.  The root ends up with the same bytes in the same
+buffers as with ``gather="both"``.
+
 The memory backend is injected so that the bookkeeping (shard offsets, buffer rotation, ordering) is covered by
 world_size-2 gloo tests on CPU (tests/test_multirank_cpu.py); on a GPU box the backend is the C ABI above.
 """
@@ -76,6 +85,27 @@ class PeerMemoryCuda:
         self.eng._check(self.eng.lib.avsep_copy_async(self.eng.h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nfloats * 4,
                                                       C.c_void_p(stream.cuda_stream)), "avsep_copy_async")
 
+    def zero(self, ptr: int, nfloats: int):
+        self.view(ptr, (nfloats,)).zero_()
+
+    def _flag_array(self, ptrs):
+        return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+    def signal(self, flag_ptrs, value: int, stream):
+        self.eng._check(self.eng.lib.avsep_flag_signal(self.eng.h, self._flag_array(flag_ptrs), len(flag_ptrs),
+                                                       value & 0xFFFFFFFF, C.c_void_p(stream.cuda_stream)),
+                        "avsep_flag_signal")
+
+    def wait(self, flag_ptrs, value: int, stream, timeout_s: float = 20.0):
+        self.eng._check(self.eng.lib.avsep_flag_wait(self.eng.h, self._flag_array(flag_ptrs), len(flag_ptrs),
+                                                     value & 0xFFFFFFFF, float(timeout_s),
+                                                     C.c_void_p(stream.cuda_stream)), "avsep_flag_wait")
+
+    def separate(self, masks_ptr: int, mixed_ptr: int, n_utt: int, T: int, sep_ptr: int, stream):
+        self.eng._check(self.eng.lib.avsep_separate(self.eng.h, C.c_void_p(masks_ptr), C.c_void_p(mixed_ptr), n_utt, T,
+                                                    C.c_void_p(sep_ptr), C.c_void_p(stream.cuda_stream)),
+                        "avsep_separate")
+
     # stream / event plumbing (torch is used for streams only)
     def stream(self):
         return torch.cuda.Stream(device=self.dev)
@@ -99,7 +129,10 @@ class ShardedForward:
     """
 
     def __init__(self, backend, forward_fn, per_rank_batch: int, shapes: dict, rank: int, world: int,
-                 n_input_sets: int = 1, group=None, copy_lanes: int = 1):
+                 n_input_sets: int = 1, group=None, copy_lanes: int = 1, gather: str = "both"):
+        if gather not in ("both", "masks"):
+            raise ValueError("gather must be 'both' (separated + masks on the wire) or 'masks' (the root rebuilds separated)")
+        self.gather = gather
         self.mem, self.fwd = backend, forward_fn
         self.B, self.rank, self.world, self.group = int(per_rank_batch), int(rank), int(world), group
         self.n_sets = int(n_input_sets)
@@ -152,7 +185,37 @@ class ShardedForward:
             self.ev_out_free = [self.mem.event() for _ in range(2)]
             self.used = [False, False]
         self.bytes_in_per_step = 4 * self.B * (self.per["mixed"] + self.per["frames"])     # per non-root rank
-        self.bytes_out_per_step = 4 * self.B * 2 * self.per["out"]
+        self.bytes_out_per_step = 4 * self.B * (1 if gather == "masks" else 2) * self.per["out"]
+        self.count, self.last_ticket = 0, [0, 0]
+        if gather == "masks" and world > 1:
+            self._init_tickets()
+
+    FLAG_STRIDE = 16       # floats: one 64-byte line per flag
+
+    def _init_tickets(self):
+        """arrived[r] lives in the root's memory (rank r raises it after its masks landed); ack lives in every other
+        rank's memory (the root raises it after it rebuilt `separated` from that step's masks)."""
+        if self.world > 17:
+            raise ValueError("gather='masks' supports up to 17 ranks (16 flags per wait)")
+        st = self.FLAG_STRIDE
+        if self.rank == 0:
+            self.arrived, h = self.mem.alloc(self.world * st)
+            self.mem.zero(self.arrived, self.world * st)
+            mine = ("arrived", h)
+        else:
+            self.ack, h = self.mem.alloc(st)
+            self.mem.zero(self.ack, st)
+            mine = ("ack", h)
+        self.mem.synchronize()
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        if self.rank == 0:
+            self.peer_ack = [self.mem.open(everyone[r][1]) for r in range(1, self.world)]
+            self.s_rb = self.mem.stream()
+            self.ev_rebuilt = [self.mem.event() for _ in range(2)]
+        else:
+            self.arrived = self.mem.open(everyone[0][1])
+        dist.barrier(group=self.group)          # every flag is zeroed and mapped before the first ticket
 
     # ---- one step: scatter -> forward -> gather, all enqueued asynchronously -------------------------------------
     def step(self, i: int):
@@ -161,6 +224,16 @@ class ShardedForward:
             m, f = self.root_in[s_set]
             sep, masks = self.root_out[b]
             self.fwd(m[self.lo:self.hi], f[self.lo:self.hi], sep[self.lo:self.hi], masks[self.lo:self.hi])
+            self.count += 1
+            if self.gather == "masks" and self.world > 1:
+                # rebuild the remote shards' `separated` once their masks have landed, then free the slot for step + 2
+                ticket, st, B = self.count, 4 * self.FLAG_STRIDE, self.B
+                self.mem.wait([self.arrived + r * st for r in range(1, self.world)], ticket, self.s_rb)
+                self.mem.separate(self.ptr[f"out{b}.masks"] + 4 * B * self.per["out"],
+                                  self.ptr[f"in{s_set}.mixed"] + 4 * B * self.per["mixed"], (self.world - 1) * B,
+                                  self.shapes["mixed"][1], self.ptr[f"out{b}.sep"] + 4 * B * self.per["out"], self.s_rb)
+                self.mem.signal(self.peer_ack, ticket, self.s_rb)
+                self.ev_rebuilt[b].record(self.s_rb)
             return
         comp = self.mem.current_stream()
         m, f = self.loc_in[b]
@@ -181,9 +254,18 @@ class ShardedForward:
         self.ev_fwd_done[b].record(comp)
         # gather: push the shard's outputs into the root's global buffers
         self.s_out.wait_event(self.ev_fwd_done[b])
-        self._copy(self.s_out, self.x_out, 1, [
-            (self.ptr[f"out{b}.sep"] + 4 * off * self.per["out"], sep.data_ptr(), self.B * self.per["out"]),
-            (self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"])])
+        self.count += 1
+        if self.gather == "masks":
+            if self.last_ticket[b]:      # the root has rebuilt `separated` from what this output slot held before
+                self.mem.wait([self.ack], self.last_ticket[b], self.s_out)
+            self._copy(self.s_out, self.x_out, 1, [
+                (self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"])])
+            self.mem.signal([self.arrived + 4 * self.FLAG_STRIDE * self.rank], self.count, self.s_out)
+            self.last_ticket[b] = self.count
+        else:
+            self._copy(self.s_out, self.x_out, 1, [
+                (self.ptr[f"out{b}.sep"] + 4 * off * self.per["out"], sep.data_ptr(), self.B * self.per["out"]),
+                (self.ptr[f"out{b}.masks"] + 4 * off * self.per["out"], masks.data_ptr(), self.B * self.per["out"])])
         self.ev_out_free[b].record(self.s_out)
         self.used[b] = True
 

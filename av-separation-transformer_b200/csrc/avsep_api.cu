@@ -1452,6 +1452,49 @@ int avsep_copy_async(avsep_handle* h, void* dst, const void* src, size_t bytes, 
   return 0;
 }
 
+int avsep_separate(avsep_handle* h, const float* masks, const float* mixed_spec, int32_t B, int32_t T, float* separated,
+                   void* cuda_stream) {
+  if (!h) return 1;
+  if (!masks || !mixed_spec || !separated) return fail(h, "avsep_separate: null buffer");
+  if (B < 1 || T < 1) return fail(h, "avsep_separate: B and T must be >= 1");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  const char* e = launch_separate(static_cast<cudaStream_t>(cuda_stream), masks, mixed_spec, separated, B,
+                                  h->cfg.num_speakers, h->cfg.freq_bins, T);
+  return e ? fail(h, e) : 0;
+}
+
+namespace {
+int make_flag_set(avsep_handle* h, uint32_t* const* flags, int32_t n, FlagSet& f, const char* who) {
+  if (!flags || n < 1 || n > FlagSet::MAX) return fail(h, std::string(who) + ": 1 .. 16 flags");
+  f.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!flags[i] || (reinterpret_cast<uintptr_t>(flags[i]) & 3)) return fail(h, std::string(who) + ": bad flag pointer");
+    f.ptr[i] = flags[i];
+  }
+  return 0;
+}
+}  // namespace
+
+int avsep_flag_signal(avsep_handle* h, uint32_t* const* flags, int32_t n, uint32_t value, void* cuda_stream) {
+  if (!h) return 1;
+  FlagSet f;
+  if (make_flag_set(h, flags, n, f, "avsep_flag_signal")) return 1;
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  const char* e = launch_flag_signal(static_cast<cudaStream_t>(cuda_stream), f, value);
+  return e ? fail(h, e) : 0;
+}
+
+int avsep_flag_wait(avsep_handle* h, uint32_t* const* flags, int32_t n, uint32_t value, double timeout_s,
+                    void* cuda_stream) {
+  if (!h) return 1;
+  FlagSet f;
+  if (make_flag_set(h, flags, n, f, "avsep_flag_wait")) return 1;
+  if (!(timeout_s > 0.0) || timeout_s > 3600.0) return fail(h, "avsep_flag_wait: timeout_s must be in (0, 3600]");
+  CUDA_OK(cudaSetDevice(h->cfg.device));
+  const char* e = launch_flag_wait(static_cast<cudaStream_t>(cuda_stream), f, value, timeout_s);
+  return e ? fail(h, e) : 0;
+}
+
 // ---- sub-module forwards ------------------------------------------------------------------------
 int avsep_audio_encoder(avsep_handle* h, const float* mixed_spec, int32_t B, int32_t T, float* out_BTd,
                         void* cuda_stream) {

@@ -148,6 +148,18 @@ const char* launch_add_layernorm(cudaStream_t s, int prec, const float* x, const
 // mixed (B,F,T) fp32 -> Xp (B, T+2, Fp) operand precision, zero halo rows and zero pad columns.
 const char* launch_prep_audio(cudaStream_t s, int prec, const float* mixed, void* xp, int B, int F, int T, int Fp);
 
+// SeparationDecoder.separate (model.py:210-220): out[b,s,f,t] = masks[b,s,f,t] * mixed[b,f,t] (peer_gather.cu).
+const char* launch_separate(cudaStream_t s, const float* masks, const float* mixed, float* out, long long B, int S,
+                            int F, int T);
+// Ticket flags of the masks-only gather: 32-bit words in this GPU's or a peer's memory, raised / awaited in stream order.
+struct FlagSet {
+  static constexpr int MAX = 16;
+  unsigned* ptr[MAX];
+  int n;
+};
+const char* launch_flag_signal(cudaStream_t s, const FlagSet& f, unsigned value);
+const char* launch_flag_wait(cudaStream_t s, const FlagSet& f, unsigned value, double timeout_s);
+
 struct AttnProblem {
   const void* q; int ldq;          // operand-precision rows [B*Lq, ldq], head h at columns h*hd
   const void* k; const void* v;    // self: operand precision rows [B*Lk, ldkv]; cross (lerp): fp32 rows [B*Nsrc, ldkv]

@@ -429,7 +429,7 @@ def run_ours(args, rank, local_rank, world):
                     gf[r * B:(r + 1) * B].copy_(f_r)
         barrier()
 
-        def sg_timed(steps, warmup):
+        def sg_timed(sg, steps, warmup):
             for i in range(warmup):
                 sg.step(i)
             sg.finish()
@@ -444,6 +444,8 @@ def run_ours(args, rank, local_rank, world):
             if rank != 0:
                 stream.wait_stream(sg.s_in)
                 stream.wait_stream(sg.s_out)      # this rank's last push is inside its timed interval
+            elif hasattr(sg, "s_rb"):
+                stream.wait_stream(sg.s_rb)       # masks-only gather: the root's last rebuild is inside it too
             e1.record(stream)
             sg.finish()
             wall = time.perf_counter() - t0
@@ -455,21 +457,50 @@ def run_ours(args, rank, local_rank, world):
         phase("sharded (no traffic) timed; scatter/gather buffers ready")
         # warm-up covers every (input set, output buffer) pair of the root: 3 x 2 CUDA graphs, the first two uses of a
         # pair run eagerly / capture (forward_cached), so 12 steps keep graph instantiation out of the timed region
-        ms_sg, ms_sg_wall, sg_spread = sg_timed(args.steps, max(args.warmup, 2 * 2 * n_sets))
+        ms_sg, ms_sg_wall, sg_spread = sg_timed(sg, args.steps, max(args.warmup, 2 * 2 * n_sets))
         phase("scatter/gather timed")
         # verify the gathered result on the root: shard r of the last step == the root's own forward of those inputs
-        verified = None
-        if rank == 0:
+        def sg_verify(sgx):
+            if rank != 0:
+                return None
             i_last = args.steps - 1
-            gm, gf = sg.root_in[i_last % n_sets]
-            gsep, gmasks = sg.root_out[i_last & 1]
-            verified = True
+            gm, gf = sgx.root_in[i_last % n_sets]
+            gsep, gmasks = sgx.root_out[i_last & 1]
+            ok = True
             for r in sorted({0, 1, world - 1}):
                 fwd_raw(gm[r * B:(r + 1) * B], gf[r * B:(r + 1) * B], sep, masks)
                 torch.cuda.synchronize()
-                verified = verified and bool(torch.equal(gsep[r * B:(r + 1) * B], sep)) and \
+                ok = ok and bool(torch.equal(gsep[r * B:(r + 1) * B], sep)) and \
                     bool(torch.equal(gmasks[r * B:(r + 1) * B], masks))
+            return ok
+
+        verified = sg_verify(sg)
         barrier()
+        # side entry: the same step with masks only on the wire (SURVEY 8e mitigation): every rank pushes its masks and
+        # raises a ticket, the root rebuilds the remote shards' `separated` (avsep_separate) -- same bytes in the same
+        # root buffers, half of the traffic into the root
+        masks_only_entry = None
+        if not os.environ.get("AVSEP_BENCH_NO_MASKS_ONLY"):
+            sg_m = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets, gather="masks")
+            if rank == 0:
+                for (gm, gf), (hm, hf) in zip(sg.root_in, sg_m.root_in):
+                    hm.copy_(gm)
+                    hf.copy_(gf)
+            barrier()
+            ms_m, ms_m_wall, spread_m = sg_timed(sg_m, args.steps, max(args.warmup, 2 * 2 * n_sets))
+            ok_m = sg_verify(sg_m)
+            barrier()
+            ms_mm = max(ms_m, ms_m_wall)
+            masks_only_entry = {
+                "ms_per_step": round(ms_mm, 4), "value": throughput(world, B, ms_mm),
+                "bytes_into_rank0_per_step": sg_m.bytes_out_per_step * (world - 1),
+                "bytes_out_of_rank0_per_step": sg_m.bytes_in_per_step * (world - 1),
+                "root_buffers_equal_local_forward": ok_m, "step_spread": spread_m,
+                "what": "scatter -> forward -> gather with masks only on the wire: ranks push masks + a ticket "
+                        "(avsep_flag_signal), the root waits in stream order (avsep_flag_wait) and rebuilds the remote "
+                        "shards' separated = masks x mixed (avsep_separate, bit-identical); separated + masks (fp32) of "
+                        "the global batch end up in the root's buffers as in the headline"}
+            phase("masks-only gather timed")
         sharded_entry = {"ms_per_step": round(ms_sharded, 4), "value": throughput(world, B, ms_sharded),
                          "what": "every rank's shard stays on its GPU: inputs generated per rank, outputs not gathered"}
         ms_per_step = max(ms_sg, ms_sg_wall)     # device time of the slowest rank; wall clock as the cross-rank check
@@ -734,6 +765,8 @@ def run_ours(args, rank, local_rank, world):
         out["python_api"] = python_api
     if world > 1:
         out["sharded_no_traffic"] = sharded_entry
+        if masks_only_entry is not None:
+            out["scatter_gather_masks_only"] = masks_only_entry
         out["scatter_gather"] = {
             "ms_per_step_device": round(ms_sg, 4), "ms_per_step_wall": round(ms_sg_wall, 4),
             "step_spread": dict(sg_spread, what="forward-to-forward intervals inside the timed region, max over ranks "

@@ -266,6 +266,26 @@ AVSEP_API int avsep_shared_close(avsep_handle* h, void* dev_ptr);
 /* dst / src: any mix of this device's memory, peer memory mapped with avsep_shared_open, or pinned host memory. */
 AVSEP_API int avsep_copy_async(avsep_handle* h, void* dst, const void* src, size_t bytes, void* cuda_stream);
 
+
+/* SeparationDecoder.separate (reference model.py:210-220): separated[b,s,f,t] = masks[b,s,f,t] * mixed_spec[b,f,t],
+ * masks / separated (B, S, F, T) fp32 contiguous, mixed_spec (B, F, T) fp32; S and F are the handle's (16-byte
+ * accesses when masks and separated share their alignment modulo 16, element-wise otherwise).
+ * One fp32 multiply per element: bit-identical to the reference's broadcast product and to the `separated` that
+ * avsep_forward's decoder epilogue writes. */
+AVSEP_API int avsep_separate(avsep_handle* h, const float* masks, const float* mixed_spec, int32_t B, int32_t T,
+                             float* separated, void* cuda_stream);
+
+/* Masks-only gather ("gather only masks: the root recomputes separated = masks x mixed, which it already
+ * holds"): a rank pushes its masks shard with avsep_copy_async and then raises a ticket -- a 32-bit word in memory
+ * from avsep_shared_alloc, its own or a mapped peer's -- with avsep_flag_signal on the same stream; the consumer
+ * orders its stream after the ticket with avsep_flag_wait (a one-CTA kernel polling its own memory; no host
+ * round trip, no collective) and rebuilds the shard's `separated` with avsep_separate.  Tickets only grow; wait
+ * succeeds once every flag >= value.  A flag that does not arrive within timeout_s makes the waiting kernel trap (the
+ * next CUDA call on the handle's device fails) instead of hanging the stream.  n <= 16. */
+AVSEP_API int avsep_flag_signal(avsep_handle* h, uint32_t* const* flags, int32_t n, uint32_t value, void* cuda_stream);
+AVSEP_API int avsep_flag_wait(avsep_handle* h, uint32_t* const* flags, int32_t n, uint32_t value, double timeout_s,
+                              void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,32 @@ class _HostBackend:
         import ctypes
         ctypes.memmove(dst, src, nfloats * 4)
 
+    # tickets of the masks-only gather: 32-bit words in shared memory, polled by the waiting process
+    def zero(self, ptr, nfloats):
+        import ctypes
+        ctypes.memset(ptr, 0, nfloats * 4)
+
+    def signal(self, flag_ptrs, value, stream):
+        import ctypes
+        for p in flag_ptrs:
+            ctypes.c_uint32.from_address(p).value = value
+
+    def wait(self, flag_ptrs, value, stream, timeout_s=30.0):
+        import ctypes
+        import time
+        t0 = time.time()
+        for p in flag_ptrs:
+            while ctypes.c_uint32.from_address(p).value < value:
+                time.sleep(0.0005)
+                assert time.time() - t0 < timeout_s, "ticket did not arrive"
+        self.waits = getattr(self, "waits", 0) + 1
+
+    def separate(self, masks_ptr, mixed_ptr, n_utt, T, sep_ptr, stream):
+        S, F = self.out_shape[0], self.out_shape[1]
+        masks = self.view(masks_ptr, (n_utt, S, F, T))
+        mixed = self.view(mixed_ptr, (n_utt, F, T))
+        self.view(sep_ptr, (n_utt, S, F, T)).copy_(masks * mixed.unsqueeze(1))
+
     def stream(self): return self._Obj()
     def current_stream(self): return self._Obj()
     def event(self): return self._Obj()
@@ -121,7 +147,7 @@ def _fake_forward(mixed, frames, sep, masks):
         sep[:, s] = masks[:, s] * mixed
 
 
-def _sharded_worker(rank, world, port, out, lanes=1):
+def _sharded_worker(rank, world, port, out, lanes=1, gather="both"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from avsep_b200.sharded import ShardedForward, shard_slices
@@ -129,7 +155,8 @@ def _sharded_worker(rank, world, port, out, lanes=1):
     try:
         B, shapes = 3, dict(mixed=(5, 7), frames=(4, 2, 2), out=(2, 5, 7))
         assert shard_slices(world, B) == [(0, 3), (3, 6)]
-        sf = ShardedForward(be, _fake_forward, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes)
+        be.out_shape = shapes["out"]
+        sf = ShardedForward(be, _fake_forward, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes, gather=gather)
         if rank == 0:
             g = torch.Generator().manual_seed(0)
             for m, f in sf.root_in:
@@ -153,6 +180,9 @@ def _sharded_worker(rank, world, port, out, lanes=1):
                 out["err"] = err
             out["ok"] = ok
             out["bytes"] = (sf.bytes_in_per_step, sf.bytes_out_per_step)
+            out["root_waits"] = getattr(be, "waits", 0)
+        else:
+            out["peer_waits"] = getattr(be, "waits", 0)
         dist.barrier()
     finally:
         be.close(unlink=(rank == 0))
@@ -175,3 +205,16 @@ def test_sharded_forward_with_three_copy_lanes_world_two_gloo():
         out = m.dict()
         mp.spawn(_sharded_worker, args=(world, port, out, 3), nprocs=world, join=True)
         assert out["ok"] is True, dict(out)
+
+
+def test_sharded_forward_masks_only_gather_world_two_gloo():
+    """gather='masks': only the masks shard crosses to the root, which rebuilds `separated` after the rank's ticket
+    arrived and acknowledges; the root's buffers end up identical to the two-tensor gather."""
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_sharded_worker, args=(world, port, out, 1, "masks"), nprocs=world, join=True)
+        assert out["ok"] is True, dict(out)
+        assert out["bytes"] == (4 * 3 * (35 + 16), 4 * 3 * 70)          # half of the bytes into the root
+        assert out["root_waits"] == 5          # one ticket wait per step on the root ...
+        assert out["peer_waits"] == 3          # ... and one acknowledge wait per reuse of an output slot (steps 2, 3, 4)

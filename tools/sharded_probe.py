@@ -54,8 +54,8 @@ shapes = dict(mixed=(F, T), frames=(N, HW, HW), out=(S, F, T))
 WARM = int(os.environ.get("PROBE_WARMUP", "6"))
 
 
-def run(label, fwd_fn, skip=(), lanes=1):
-    sg = Probe(PeerMemoryCuda(eng), fwd_fn, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes)
+def run(label, fwd_fn, skip=(), lanes=1, gather="both"):
+    sg = Probe(PeerMemoryCuda(eng), fwd_fn, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes, gather=gather)
     sg.skip = skip
     if rank == 0:
         for gm, gf in sg.root_in:
@@ -75,6 +75,8 @@ def run(label, fwd_fn, skip=(), lanes=1):
     if rank != 0:
         stream.wait_stream(sg.s_in)
         stream.wait_stream(sg.s_out)
+    elif hasattr(sg, "s_rb"):
+        stream.wait_stream(sg.s_rb)
     e1.record(stream)
     sg.finish()
     per = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))      # forward-to-forward intervals
@@ -110,4 +112,6 @@ for _ in range(int(os.environ.get("PROBE_REPEAT", "1"))):
     run("forward only", _raw, skip=(0, 1))
     run("full, 2 copy lanes", _raw, lanes=2)
     run("full (again)", _raw)
+    run("full, masks only on the wire", _raw, gather="masks")
+    run("copies only, masks only on the wire", noop, gather="masks")
 dist.destroy_process_group()
