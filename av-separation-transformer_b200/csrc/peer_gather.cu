@@ -100,11 +100,29 @@ __global__ void flag_wait_kernel(FlagSet f, unsigned value, unsigned long long t
   __threadfence_system();
 }
 
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and loading may have to wait
+// for running kernels -- a waiter spinning for a signal kernel that is not loaded yet would never see it.  Every entry
+// point of this file therefore loads all of the file's kernels first (once per device).
+const char* preload_kernels() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return "peer_gather: bad device";
+  if (done[dev]) return nullptr;
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, flag_signal_kernel) != cudaSuccess || cudaFuncGetAttributes(&a, flag_wait_kernel) != cudaSuccess ||
+      cudaFuncGetAttributes(&a, separate_kernel<true>) != cudaSuccess ||
+      cudaFuncGetAttributes(&a, separate_kernel<false>) != cudaSuccess)
+    return "peer_gather: kernel image not loadable on this device";
+  done[dev] = true;
+  return nullptr;
+}
+
 }  // namespace
 
 const char* launch_separate(cudaStream_t s, const float* masks, const float* mixed, float* out, long long B, int S,
                             int F, int T) {
   if (B <= 0) return nullptr;
+  if (const char* e = preload_kernels()) return e;
   const long long plane = static_cast<long long>(F) * T;
   if (plane > 0x7fffffffLL) return "separate: F*T too large";
   const long long total = B * S * plane;
@@ -125,6 +143,7 @@ const char* launch_separate(cudaStream_t s, const float* masks, const float* mix
 const char* launch_flag_signal(cudaStream_t s, const FlagSet& f, unsigned value) {
   if (f.n <= 0) return nullptr;
   if (f.n > FlagSet::MAX) return "flag_signal: too many flags";
+  if (const char* e = preload_kernels()) return e;
   flag_signal_kernel<<<1, 32, 0, s>>>(f, value);
   return cudaGetLastError() == cudaSuccess ? nullptr : "flag_signal: launch failed";
 }
@@ -132,6 +151,7 @@ const char* launch_flag_signal(cudaStream_t s, const FlagSet& f, unsigned value)
 const char* launch_flag_wait(cudaStream_t s, const FlagSet& f, unsigned value, double timeout_s) {
   if (f.n <= 0) return nullptr;
   if (f.n > FlagSet::MAX) return "flag_wait: too many flags";
+  if (const char* e = preload_kernels()) return e;
   flag_wait_kernel<<<1, 32, 0, s>>>(f, value, static_cast<unsigned long long>(timeout_s * 1e9));
   return cudaGetLastError() == cudaSuccess ? nullptr : "flag_wait: launch failed";
 }

@@ -85,9 +85,14 @@ def test_ticket_flags_order_two_streams():
     ptrs = [flags.data_ptr() + 64 * i for i in range(3)]
     arr = (C.c_void_p * 3)(*ptrs)
     waiter, signaller = torch.cuda.Stream(), torch.cuda.Stream()
-    torch.cuda.synchronize()
     data = torch.zeros(1 << 20, device="cuda")
     seen = torch.zeros(1, device="cuda")
+    # every kernel the test launches while the waiter spins is loaded beforehand: with lazy module loading a first
+    # launch may wait for running kernels (the library preloads its own for the same reason)
+    data.fill_(1.0)
+    seen.copy_(data[-1:])
+    data.zero_()
+    torch.cuda.synchronize()
     rc = eng.lib.avsep_flag_wait(eng.h, arr, 3, 7, C.c_double(20.0), C.c_void_p(waiter.cuda_stream))
     assert rc == 0, eng.lib.avsep_last_error(eng.h)
     with torch.cuda.stream(waiter):
