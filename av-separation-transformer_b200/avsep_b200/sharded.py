@@ -96,7 +96,7 @@ class PeerMemoryCuda:
                                                        value & 0xFFFFFFFF, C.c_void_p(stream.cuda_stream)),
                         "avsep_flag_signal")
 
-    def wait(self, flag_ptrs, value: int, stream, timeout_s: float = 20.0):
+    def wait(self, flag_ptrs, value: int, stream, timeout_s: float = 60.0):
         self.eng._check(self.eng.lib.avsep_flag_wait(self.eng.h, self._flag_array(flag_ptrs), len(flag_ptrs),
                                                      value & 0xFFFFFFFF, float(timeout_s),
                                                      C.c_void_p(stream.cuda_stream)), "avsep_flag_wait")

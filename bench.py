@@ -13,10 +13,13 @@ model d=512, 8 heads, 6+6 layers, 3 speakers, B=256).
 
 N = 1: `value` = forward with the inputs resident in HBM.
 N > 1: `value` = the north-star data path: the root (rank 0) holds the global batch, every rank pulls its
-shard of the inputs over NVLink, runs the forward, and pushes `separated` + `masks` (fp32) back into the root's global
-buffers -- scatter and gather inside the timed region, executed by the copy engines on peer memory
-(avsep_b200/sharded.py).  The no-traffic variant (every rank's shard stays on its GPU) is reported beside it as
-`sharded_no_traffic`.  Weak scaling: the per-GPU batch is fixed.
+shard of the inputs over NVLink and runs the forward, and `separated` + `masks` (fp32) of the global batch end up in
+the root's global buffers -- scatter and gather inside the timed region, executed by the copy engines on peer memory
+(avsep_b200/sharded.py).  On the way back the ranks push `masks` and a ticket; the root rebuilds the remote rows of
+`separated` = masks x mixed from the mixture it holds (one fp32 multiply, bit-identical to what the rank computed --
+checked in the run), which halves the bytes into the root's NVLink ports.  The two-tensor wire format
+(`scatter_gather_two_tensors`; AVSEP_GATHER=both makes it the headline) and the no-traffic variant
+(`sharded_no_traffic`) are reported beside it.  Weak scaling: the per-GPU batch is fixed.
 Prints ONE JSON line (rank 0).  Metric: separated utterance-seconds per second = B_total * clip seconds / time.
 """
 from __future__ import annotations
@@ -419,8 +422,17 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         from avsep_b200.sharded import PeerMemoryCuda, ShardedForward
         shapes = dict(mixed=(F, T), frames=(N, HW, HW), out=(S, F, T))
+        # what crosses NVLink on the way back: "masks" (default; ranks push masks + a ticket, the root rebuilds the remote
+        # rows of `separated` from the mixture it holds -- bit-identical, half of the bytes into the root) or "both"
+        # (separated and masks pushed as two tensors).  Either way separated + masks (fp32) of the global batch end up in
+        # the root's buffers inside the timed region; the other wire format is timed right after as a side entry.
+        wire = os.environ.get("AVSEP_GATHER", "masks")
+        if wire not in ("masks", "both"):
+            raise SystemExit("AVSEP_GATHER must be 'masks' or 'both'")
+        other_wire = "both" if wire == "masks" else "masks"
+        lanes = int(os.environ.get("AVSEP_COPY_LANES", "1"))
         sg = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets,
-                            copy_lanes=int(os.environ.get("AVSEP_COPY_LANES", "1")))
+                            copy_lanes=lanes, gather=wire)
         if rank == 0:
             for s_i, (gm, gf) in enumerate(sg.root_in):
                 for r in range(world):
@@ -476,31 +488,32 @@ def run_ours(args, rank, local_rank, world):
 
         verified = sg_verify(sg)
         barrier()
-        # side entry: the same step with masks only on the wire (SURVEY 8e mitigation): every rank pushes its masks and
-        # raises a ticket, the root rebuilds the remote shards' `separated` (avsep_separate) -- same bytes in the same
-        # root buffers, half of the traffic into the root
-        masks_only_entry = None
-        if not os.environ.get("AVSEP_BENCH_NO_MASKS_ONLY"):
-            sg_m = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets, gather="masks")
+        # side entry: the same step with the other wire format
+        wire_what = {
+            "masks": "ranks push masks + a ticket (avsep_flag_signal), the root waits in stream order (avsep_flag_wait) "
+                     "and rebuilds the remote shards' separated = masks x mixed (avsep_separate, bit-identical)",
+            "both": "ranks push separated and masks as two tensors"}
+        other_entry = None
+        if not os.environ.get("AVSEP_BENCH_ONE_WIRE"):
+            sg_o = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets,
+                                  copy_lanes=lanes, gather=other_wire)
             if rank == 0:
-                for (gm, gf), (hm, hf) in zip(sg.root_in, sg_m.root_in):
+                for (gm, gf), (hm, hf) in zip(sg.root_in, sg_o.root_in):
                     hm.copy_(gm)
                     hf.copy_(gf)
             barrier()
-            ms_m, ms_m_wall, spread_m = sg_timed(sg_m, args.steps, max(args.warmup, 2 * 2 * n_sets))
-            ok_m = sg_verify(sg_m)
+            ms_o, ms_o_wall, spread_o = sg_timed(sg_o, args.steps, max(args.warmup, 2 * 2 * n_sets))
+            ok_o = sg_verify(sg_o)
             barrier()
-            ms_mm = max(ms_m, ms_m_wall)
-            masks_only_entry = {
-                "ms_per_step": round(ms_mm, 4), "value": throughput(world, B, ms_mm),
-                "bytes_into_rank0_per_step": sg_m.bytes_out_per_step * (world - 1),
-                "bytes_out_of_rank0_per_step": sg_m.bytes_in_per_step * (world - 1),
-                "root_buffers_equal_local_forward": ok_m, "step_spread": spread_m,
-                "what": "scatter -> forward -> gather with masks only on the wire: ranks push masks + a ticket "
-                        "(avsep_flag_signal), the root waits in stream order (avsep_flag_wait) and rebuilds the remote "
-                        "shards' separated = masks x mixed (avsep_separate, bit-identical); separated + masks (fp32) of "
-                        "the global batch end up in the root's buffers as in the headline"}
-            phase("masks-only gather timed")
+            ms_oo = max(ms_o, ms_o_wall)
+            other_entry = {
+                "wire": other_wire, "ms_per_step": round(ms_oo, 4), "value": throughput(world, B, ms_oo),
+                "bytes_into_rank0_per_step": sg_o.bytes_out_per_step * (world - 1),
+                "bytes_out_of_rank0_per_step": sg_o.bytes_in_per_step * (world - 1),
+                "gathered_equals_local_forward": ok_o, "step_spread": spread_o,
+                "what": "the headline's scatter -> forward -> gather step with the other wire format: "
+                        + wire_what[other_wire]}
+            phase("other wire format timed")
         sharded_entry = {"ms_per_step": round(ms_sharded, 4), "value": throughput(world, B, ms_sharded),
                          "what": "every rank's shard stays on its GPU: inputs generated per rank, outputs not gathered"}
         ms_per_step = max(ms_sg, ms_sg_wall)     # device time of the slowest rank; wall clock as the cross-rank check
@@ -742,7 +755,8 @@ def run_ours(args, rank, local_rank, world):
                        if B * T >= 4096 else f"{n_sets} rotating input sets (small batch: the working set fits L2, as it does in use)"}
     if world > 1:
         cfg_entry["parallelism"] = (f"batch-sharded x{world}: inputs scattered from rank 0, separated+masks (fp32) gathered "
-                                    "to rank 0 inside the timed region, copy engines over NVLink peer memory")
+                                    "into rank 0's buffers inside the timed region, copy engines over NVLink peer memory; "
+                                    "on the wire: " + wire_what[wire])
     else:
         cfg_entry["parallelism"] = "batch-sharded x1"
     out = {
@@ -765,9 +779,10 @@ def run_ours(args, rank, local_rank, world):
         out["python_api"] = python_api
     if world > 1:
         out["sharded_no_traffic"] = sharded_entry
-        if masks_only_entry is not None:
-            out["scatter_gather_masks_only"] = masks_only_entry
+        if other_entry is not None:
+            out["scatter_gather_masks_only" if other_wire == "masks" else "scatter_gather_two_tensors"] = other_entry
         out["scatter_gather"] = {
+            "wire": wire,
             "ms_per_step_device": round(ms_sg, 4), "ms_per_step_wall": round(ms_sg_wall, 4),
             "step_spread": dict(sg_spread, what="forward-to-forward intervals inside the timed region, max over ranks "
                                                 "(diagnostic: a one-off stall shows as slowest >> median)"),

@@ -52,4 +52,6 @@ def test_multi_gpu_line_is_whole_job_throughput():
     sg = d["scatter_gather"]
     assert sg["gathered_equals_local_forward"] is True
     assert sg["bytes_out_of_rank0_per_step"] == 7 * d["e2e"]["h2d_bytes_per_step"]
-    assert sg["bytes_into_rank0_per_step"] == 7 * d["e2e"]["d2h_bytes_per_step"]
+    # on the wire back: both tensors, or masks only with `separated` rebuilt on the root (half of the bytes)
+    per_rank = d["e2e"]["d2h_bytes_per_step"] // (2 if sg.get("wire") == "masks" else 1)
+    assert sg["bytes_into_rank0_per_step"] == 7 * per_rank

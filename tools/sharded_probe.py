@@ -104,6 +104,15 @@ def run(label, fwd_fn, skip=(), lanes=1, gather="both"):
 
 
 noop = lambda *a: None  # noqa: E731
+ONLY = os.environ.get("PROBE_ONLY")            # e.g. "full,masks": run only the labels containing one of these words
+_run = run
+
+
+def run(label, *a, **k):  # noqa: F811
+    if ONLY is None or any(w in label for w in ONLY.split(",")):
+        _run(label, *a, **k)
+
+
 for _ in range(int(os.environ.get("PROBE_REPEAT", "1"))):
     run("full", _raw)
     run("copies only (no forward)", noop)
