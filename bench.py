@@ -15,11 +15,12 @@ N = 1: `value` = forward with the inputs resident in HBM.
 N > 1: `value` = the north-star data path: the root (rank 0) holds the global batch, every rank pulls its
 shard of the inputs over NVLink and runs the forward, and `separated` + `masks` (fp32) of the global batch end up in
 the root's global buffers -- scatter and gather inside the timed region, executed by the copy engines on peer memory
-(avsep_b200/sharded.py).  On the way back the ranks push `masks` and a ticket; the root rebuilds the remote rows of
-`separated` = masks x mixed from the mixture it holds (one fp32 multiply, bit-identical to what the rank computed --
-checked in the run), which halves the bytes into the root's NVLink ports.  The two-tensor wire format
-(`scatter_gather_two_tensors`; AVSEP_GATHER=both makes it the headline) and the no-traffic variant
-(`sharded_no_traffic`) are reported beside it.  Weak scaling: the per-GPU batch is fixed.
+(avsep_b200/sharded.py).  On the way back the ranks push either `separated` and `masks`, or -- once the traffic through
+the root's NVLink ports would take longer than a forward (8 GPUs) -- `masks` and a ticket: the root then rebuilds the
+remote rows of `separated` = masks x mixed from the mixture it holds (one fp32 multiply, bit-identical to what the rank
+computed, checked in the run), which halves the bytes into the root.  `scatter_gather.wire` names the format used
+(choose_wire; AVSEP_GATHER=both|masks overrides), the other one is timed beside it (`scatter_gather_two_tensors` /
+`scatter_gather_masks_only`), as is the no-traffic variant (`sharded_no_traffic`).  Weak scaling: the per-GPU batch is fixed.
 Prints ONE JSON line (rank 0).  Metric: separated utterance-seconds per second = B_total * clip seconds / time.
 """
 from __future__ import annotations
@@ -198,6 +199,23 @@ def kernel_work(B, model=None, T=None, N=None):
     ln_rows = (1 + 2 * Le) * Ma + (1 + 2 * Le) * Mv + 2 * Lf * Ma
     bytes_["add_layernorm"] = ln_rows * d * 14
     return flops, bytes_, base_total
+
+
+ROOT_LINK_TBS = 1.0     # rank 0's NVLink ports with scatter and gather running at once: ~0.5 + 0.5 TB/s measured
+                        # (tools/nvlink_probe.py, profiles/r2_nvlink_root_copy_rates_n8.txt)
+
+
+def choose_wire(world, in_bytes_per_rank, out_bytes_per_rank, ms_forward, override=None):
+    """Wire format of the gather: 'both' (separated + masks pushed) while the root's links carry a step's traffic in
+    less than a forward, else 'masks' (the root rebuilds `separated`: half of the bytes into it, at the price of an
+    HBM-bound pass over the remote rows on the root).  Measured: 2 GPUs 0.536 (both) vs 0.561 ms (masks); 8 GPUs 1.07 vs
+    0.73 ms.  AVSEP_GATHER=both|masks overrides."""
+    if override in ("both", "masks"):
+        return override
+    if override not in (None, "", "auto"):
+        raise SystemExit("AVSEP_GATHER must be 'auto', 'masks' or 'both'")
+    link_ms = (world - 1) * (in_bytes_per_rank + out_bytes_per_rank) / (ROOT_LINK_TBS * 1e12) * 1e3
+    return "masks" if link_ms > ms_forward else "both"
 
 
 def shard_bounds(rank, world, per_rank_batch):
@@ -422,13 +440,12 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         from avsep_b200.sharded import PeerMemoryCuda, ShardedForward
         shapes = dict(mixed=(F, T), frames=(N, HW, HW), out=(S, F, T))
-        # what crosses NVLink on the way back: "masks" (default; ranks push masks + a ticket, the root rebuilds the remote
-        # rows of `separated` from the mixture it holds -- bit-identical, half of the bytes into the root) or "both"
-        # (separated and masks pushed as two tensors).  Either way separated + masks (fp32) of the global batch end up in
+        # what crosses NVLink on the way back: "masks" (ranks push masks + a ticket, the root rebuilds the remote rows of
+        # `separated` from the mixture it holds -- bit-identical, half of the bytes into the root) or "both" (separated
+        # and masks pushed as two tensors); chosen by choose_wire from the traffic through the root.  Either way separated + masks (fp32) of the global batch end up in
         # the root's buffers inside the timed region; the other wire format is timed right after as a side entry.
-        wire = os.environ.get("AVSEP_GATHER", "masks")
-        if wire not in ("masks", "both"):
-            raise SystemExit("AVSEP_GATHER must be 'masks' or 'both'")
+        wire = choose_wire(world, 4 * B * (F * T + N * HW * HW), 4 * B * 2 * S * F * T, ms_sharded,
+                           os.environ.get("AVSEP_GATHER"))
         other_wire = "both" if wire == "masks" else "masks"
         lanes = int(os.environ.get("AVSEP_COPY_LANES", "1"))
         sg = ShardedForward(PeerMemoryCuda(eng), fwd_raw, B, shapes, rank, world, n_input_sets=n_sets,

@@ -5,6 +5,8 @@ import json
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASE = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
         "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
@@ -55,3 +57,13 @@ def test_multi_gpu_line_is_whole_job_throughput():
     # on the wire back: both tensors, or masks only with `separated` rebuilt on the root (half of the bytes)
     per_rank = d["e2e"]["d2h_bytes_per_step"] // (2 if sg.get("wire") == "masks" else 1)
     assert sg["bytes_into_rank0_per_step"] == 7 * per_rank
+
+
+def test_gather_wire_format_follows_the_traffic_through_the_root():
+    import bench
+    i_b, o_b, fwd = 69008384, 66318336, 0.53          # B=256 per rank: input / output bytes, ms per forward
+    assert [bench.choose_wire(n, i_b, o_b, fwd) for n in (2, 4, 8)] == ["both", "both", "masks"]
+    assert bench.choose_wire(8, i_b, o_b, fwd, "both") == "both" and bench.choose_wire(2, i_b, o_b, fwd, "masks") == "masks"
+    assert bench.choose_wire(8, i_b, o_b, fwd, "auto") == "masks"
+    with pytest.raises(SystemExit):
+        bench.choose_wire(2, i_b, o_b, fwd, "bf16")
