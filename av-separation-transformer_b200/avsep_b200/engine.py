@@ -237,7 +237,7 @@ class Engine:
 
     def forward_host_async(self, mixed: torch.Tensor, frames: torch.Tensor, sep: torch.Tensor, masks: torch.Tensor,
                            slot: int):
-        """Streaming form: enqueue one batch on I/O slot 0/1 and return; ``host_wait(slot)`` completes it.  All four
+        """Streaming form: enqueue one batch on I/O slot 0 .. 3 (AVSEP_HOST_SLOTS) and return; ``host_wait(slot)`` completes it.  All four
         tensors must be contiguous float32 CPU tensors (pinned for real overlap) that outlive the wait."""
         for t in (mixed, frames, sep, masks):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():

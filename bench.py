@@ -145,11 +145,15 @@ def measured_peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
 
 
-def source_hash():
-    """Identifies the kernel sources of the build being timed (profiles/traffic.json is only valid for its own build)."""
+def source_hash(files=None):
+    """Identifies kernel sources of the build being timed.  files = None: every source of the library; a list: those
+    files of csrc/ (profiles/traffic.json records, per kernel, the translation unit the kernel is compiled from -- its
+    .cu file and common.cuh -- and the hash of both at capture time: the capture stays valid while that kernel's own
+    sources are unchanged, and is reported as absent once they differ)."""
     h = hashlib.sha256()
     csrc = os.path.join(PKG, "csrc")
-    for name in sorted(os.listdir(csrc)):
+    names = sorted(os.listdir(csrc)) if files is None else sorted(files)
+    for name in names:
         if name.endswith((".cu", ".cuh", ".h")):
             with open(os.path.join(csrc, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
@@ -745,11 +749,13 @@ def run_ours(args, rank, local_rank, world):
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("src_hash") == source_hash() and tj.get("batch") == B and tj.get("config") == args.config:
-            traffic = tj.get("kernels", {}).get(top, {}).get("traffic")
-            traffic_note = tj.get("source")
+        ent = tj.get("kernels", {}).get(top, {})
+        if ent.get("src") and ent.get("src_hash") == source_hash(ent["src"]) and tj.get("batch") == B and \
+                tj.get("config") == args.config:
+            traffic = ent.get("traffic")
+            traffic_note = tj.get("source") + "; valid for this build: " + " + ".join(ent["src"]) + " unchanged since the capture"
         else:
-            traffic_note = "profiles/traffic.json was captured from a different build / workload"
+            traffic_note = "profiles/traffic.json was captured from different kernel sources / another workload"
     n_top = max(1, te["launches_per_step"])
     if "tflops" in te:
         roofline = {"kernel": top, "bound": "tensor", "achieved": te["tflops"], "peak": peaks["tensor_burst"],

@@ -199,8 +199,13 @@ def test_host_path_streaming_slots_overlap_safely():
         for (mt, ft, rs, rm), (os_, om) in zip(batches, outs):
             assert torch.equal(os_, rs) and torch.equal(om, rm)
             os_.zero_(); om.zero_()
-    with pytest.raises(RuntimeError, match="slot"):
-        eng.forward_host_async(batches[0][0], batches[0][1], outs[0][0], outs[0][1], 2)
+    # slots 2 and 3 exist too (AVSEP_HOST_SLOTS = 4): the same batch through one of them, then an index past the end
+    eng.forward_host_async(batches[1][0], batches[1][1], outs[1][0], outs[1][1], 3)
+    eng.host_wait(3)
+    assert torch.equal(outs[1][0], batches[1][2]) and torch.equal(outs[1][1], batches[1][3])
+    for bad in (4, -1):
+        with pytest.raises(RuntimeError, match="slot"):
+            eng.forward_host_async(batches[0][0], batches[0][1], outs[0][0], outs[0][1], bad)
 
 
 def test_submodule_dropins_match_oracle():
