@@ -147,14 +147,14 @@ def _fake_forward(mixed, frames, sep, masks):
         sep[:, s] = masks[:, s] * mixed
 
 
-def _sharded_worker(rank, world, port, out, lanes=1, gather="both"):
+def _sharded_worker(rank, world, port, out, lanes=1, gather="both", n_steps=5):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from avsep_b200.sharded import ShardedForward, shard_slices
     be = _HostBackend()
     try:
         B, shapes = 3, dict(mixed=(5, 7), frames=(4, 2, 2), out=(2, 5, 7))
-        assert shard_slices(world, B) == [(0, 3), (3, 6)]
+        assert shard_slices(world, B) == [(r * 3, r * 3 + 3) for r in range(world)]
         be.out_shape = shapes["out"]
         sf = ShardedForward(be, _fake_forward, B, shapes, rank, world, n_input_sets=3, copy_lanes=lanes, gather=gather)
         if rank == 0:
@@ -163,7 +163,6 @@ def _sharded_worker(rank, world, port, out, lanes=1, gather="both"):
                 m.copy_(torch.randn(m.shape, generator=g))
                 f.copy_(torch.rand(f.shape, generator=g))
         dist.barrier()
-        n_steps = 5
         for i in range(n_steps):
             sf.step(i)
         sf.finish()
@@ -218,3 +217,14 @@ def test_sharded_forward_masks_only_gather_world_two_gloo():
         assert out["bytes"] == (4 * 3 * (35 + 16), 4 * 3 * 70)          # half of the bytes into the root
         assert out["root_waits"] == 5          # one ticket wait per step on the root ...
         assert out["peer_waits"] == 3          # ... and one acknowledge wait per reuse of an output slot (steps 2, 3, 4)
+
+
+def test_sharded_forward_masks_only_gather_world_three_gloo():
+    """Two remote ranks: the root's rebuild waits for both tickets, rebuilds both shards in one pass and acknowledges
+    both; eight steps walk every (input set, output slot) pair and reuse each output slot three times."""
+    world, port = 3, _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_sharded_worker, args=(world, port, out, 2, "masks", 8), nprocs=world, join=True)
+        assert out["ok"] is True, dict(out)
+        assert out["root_waits"] == 8 and out["peer_waits"] == 6
